@@ -1,0 +1,377 @@
+// C ABI entry points (include/geniconet_b200.h): argument checking, plan validation, launches.
+// No allocation, no device state; the only global is the launch counter and the per-thread
+// error string.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/geniconet_b200.h"
+#include "gin_common.cuh"
+#include "gin_gemm_simt.cuh"
+#include "gin_gemm_tc.cuh"
+#include "gin_loss.cuh"
+#include "gin_resample.cuh"
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void gin_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) return fail(GIN_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return GIN_OK;
+}
+
+// The launch geometry comes from the HOST copy of the plan (the blob gin_plan_build wrote); the
+// kernels read the tables from the device copy.
+const int32_t* plan_header(const void* plan_host) {
+  const int32_t* w = reinterpret_cast<const int32_t*>(plan_host);
+  if (!w || w[0] != GIN_MAGIC) { gin_set_error("plan_host is null or has a bad magic"); return nullptr; }
+  return w;
+}
+
+int grid_for(long long work_items, int threads, int max_waves = 8) {
+  long long blocks = (work_items + threads - 1) / threads;
+  long long cap = 148LL * max_waves;
+  if (blocks < 1) blocks = 1;
+  return (int)(blocks < cap ? blocks : cap);
+}
+
+bool use_tc(int impl, int K, int N) {
+  if (impl == GIN_IMPL_SIMT) return false;
+  const bool ok = gin::tc_supported(K, N);
+  return impl == GIN_IMPL_TC ? ok : ok;
+}
+
+int run_gather_gemm(const int32_t* plan_dev, const GinSide& side, int group, GinSrcView X, const char* packed, int B, int K,
+                    int N, bool dgrad, const float* bias, float* Y, int impl, cudaStream_t st, int Cin, int Cout) {
+  const int groups = (B + group - 1) / group;
+  const long long ntiles = (long long)groups * side.ntiles;
+  if (ntiles <= 0) return GIN_OK;
+  if (impl == GIN_IMPL_TC && !gin::tc_supported(K, N))
+    return fail(GIN_ERR_UNSUPPORTED, "tcgen05 path needs K %% 64 == 0 and N %% 64 == 0 (K=%d N=%d)", K, N);
+  if (use_tc(impl, K, N) && X.sc == 1 && X.sp == K) {
+    const void* wb = packed + (dgrad ? packed_off_bd(Cin, Cout) : packed_off_bf(Cin, Cout));
+    int rc = gin::launch_gather_gemm_tc(plan_dev, side, group, X.p, wb, bias, Y, B, K, N, (int)ntiles, st);
+    if (rc != GIN_OK) return fail(rc, "tcgen05 gather-GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return GIN_OK;
+  }
+  const float* W = reinterpret_cast<const float*>(packed + (dgrad ? packed_off_wd(Cin, Cout) : packed_off_wf(Cin, Cout)));
+  dim3 grid((unsigned)ntiles, (unsigned)((N + gin::SIMT_TN - 1) / gin::SIMT_TN));
+  const bool vec = X.sc == 1 && (K % 4 == 0) && (X.sp % 4 == 0) && (X.sb % 4 == 0) && ((uintptr_t)X.p % 16 == 0);
+  if (vec) gin::gather_gemm_simt_kernel<true><<<grid, gin::SIMT_THREADS, 0, st>>>(plan_dev, side, X, W, bias, Y, group, B, K, N);
+  else gin::gather_gemm_simt_kernel<false><<<grid, gin::SIMT_THREADS, 0, st>>>(plan_dev, side, X, W, bias, Y, group, B, K, N);
+  return check_launch("gather_gemm_simt");
+}
+
+}  // namespace
+
+extern "C" {
+
+int gin_version(void) { return 100; }
+const char* gin_last_error(void) { return g_err; }
+int64_t gin_launch_count(void) { return (int64_t)g_launches.load(); }
+
+size_t gin_hexconv_packed_bytes(int Cin, int Cout) {
+  if (Cin <= 0 || Cout <= 0) return 0;
+  return packed_total(Cin, Cout);
+}
+
+int gin_hexconv_pack_weights(const float* weight, void* packed, int Cin, int Cout, void* stream) {
+  if (!weight || !packed || Cin <= 0 || Cout <= 0) return fail(GIN_ERR_ARG, "gin_hexconv_pack_weights: bad argument");
+  char* pk = reinterpret_cast<char*>(packed);
+  const long long n = 7LL * Cin * Cout;
+  gin::pack_weights_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      weight, reinterpret_cast<float*>(pk + packed_off_wf(Cin, Cout)), reinterpret_cast<float*>(pk + packed_off_wd(Cin, Cout)),
+      reinterpret_cast<unsigned short*>(pk + packed_off_bf(Cin, Cout)), reinterpret_cast<unsigned short*>(pk + packed_off_bd(Cin, Cout)),
+      Cin, Cout);
+  return check_launch("pack_weights");
+}
+
+static int conv_hdr(const void* plan_host, const void* plan_dev, const GinConvPlanHdr** out) {
+  if (!plan_dev) return fail(GIN_ERR_ARG, "null plan");
+  const int32_t* w = plan_header(plan_host);
+  if (!w) return GIN_ERR_PLAN;
+  const GinConvPlanHdr* h = reinterpret_cast<const GinConvPlanHdr*>(w);
+  if (h->kind != GIN_PLAN_HEXCONV) return fail(GIN_ERR_PLAN, "plan is not a hexconv plan (kind %d)", h->kind);
+  *out = h;
+  return GIN_OK;
+}
+
+int gin_hexconv_fwd(const void* plan_host, const void* plan_dev, const float* x, int64_t sb, int64_t sp, int64_t sc, const void* packed,
+                    const float* bias, float* y, int B, int Cin, int Cout, int impl, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!x || !packed || !y || B < 0 || Cin <= 0 || Cout <= 0) return fail(GIN_ERR_ARG, "gin_hexconv_fwd: bad argument");
+  const GinConvPlanHdr* h;
+  int rc = conv_hdr(plan_host, plan_dev, &h);
+  if (rc) return rc;
+  if (B == 0) return GIN_OK;
+  GinSrcView X{x, (long long)sb, (long long)sp, (long long)sc, h->fwd.P_src};
+  return run_gather_gemm(plan_words(plan_dev), h->fwd, h->group, X, reinterpret_cast<const char*>(packed), B, Cin, Cout, false,
+                         bias, y, impl, st, Cin, Cout);
+}
+
+int gin_hexconv_dgrad(const void* plan_host, const void* plan_dev, const float* dy, const void* packed, float* dx, int B, int Cin, int Cout, int impl,
+                      void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!dy || !packed || !dx || B < 0 || Cin <= 0 || Cout <= 0) return fail(GIN_ERR_ARG, "gin_hexconv_dgrad: bad argument");
+  const GinConvPlanHdr* h;
+  int rc = conv_hdr(plan_host, plan_dev, &h);
+  if (rc) return rc;
+  if (B == 0) return GIN_OK;
+  GinSrcView X{dy, (long long)h->dg.P_src * Cout, (long long)Cout, 1, h->dg.P_src};
+  return run_gather_gemm(plan_words(plan_dev), h->dg, h->group, X, reinterpret_cast<const char*>(packed), B, Cout, Cin, true,
+                         nullptr, dx, impl, st, Cin, Cout);
+}
+
+size_t gin_hexconv_wgrad_ws_bytes(int Cin, int Cout) {
+  if (Cin <= 0 || Cout <= 0) return 0;
+  return (size_t)28 * Cin * Cout;
+}
+
+int gin_hexconv_wgrad(const void* plan_host, const void* plan_dev, const float* x, int64_t sb, int64_t sp, int64_t sc, const float* dy, float* dW,
+                      float* db, void* ws, int B, int Cin, int Cout, int impl, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!x || !dy || !dW || !ws || B < 0 || Cin <= 0 || Cout <= 0) return fail(GIN_ERR_ARG, "gin_hexconv_wgrad: bad argument");
+  const GinConvPlanHdr* h;
+  int rc = conv_hdr(plan_host, plan_dev, &h);
+  if (rc) return rc;
+  float* dWp = reinterpret_cast<float*>(ws);
+  if (cudaMemsetAsync(dWp, 0, (size_t)28 * Cin * Cout, st) != cudaSuccess) return fail(GIN_ERR_CUDA, "memset failed");
+  if (db && cudaMemsetAsync(db, 0, (size_t)4 * Cout, st) != cudaSuccess) return fail(GIN_ERR_CUDA, "memset failed");
+  if (B > 0) {
+    const GinSide& side = h->fwd;
+    const int groups = (B + h->group - 1) / h->group;
+    const int total_tiles = groups * side.ntiles;
+    GinSrcView X{x, (long long)sb, (long long)sp, (long long)sc, side.P_src};
+    if (impl == GIN_IMPL_TC && !gin::tc_wgrad_supported(Cin, Cout))
+      return fail(GIN_ERR_UNSUPPORTED, "tcgen05 wgrad needs Cin %% 64 == 0 and Cout %% 64 == 0");
+    if (impl != GIN_IMPL_SIMT && gin::tc_wgrad_supported(Cin, Cout) && sc == 1 && sp == Cin) {
+      rc = gin::launch_wgrad_tc(plan_words(plan_dev), side, h->group, x, dy, dWp, B, Cin, Cout, total_tiles, st);
+      if (rc != GIN_OK) return fail(rc, "tcgen05 wgrad launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else {
+      const int nblk = ((Cin + gin::WG_TC - 1) / gin::WG_TC) * ((Cout + gin::WG_TC - 1) / gin::WG_TC);
+      int slices = (148 * 4 + 7 * nblk - 1) / (7 * nblk);
+      if (slices > total_tiles) slices = total_tiles;
+      if (slices < 1) slices = 1;
+      const int tiles_per_cta = (total_tiles + slices - 1) / slices;
+      dim3 grid((unsigned)((total_tiles + tiles_per_cta - 1) / tiles_per_cta), 7, (unsigned)nblk);
+      const bool vec = sc == 1 && (Cin % 4 == 0) && (sp % 4 == 0) && (sb % 4 == 0) && ((uintptr_t)x % 16 == 0);
+      if (vec) gin::wgrad_simt_kernel<true><<<grid, 256, 0, st>>>(plan_words(plan_dev), side, X, dy, dWp, h->group, B, Cin, Cout, tiles_per_cta, total_tiles);
+      else gin::wgrad_simt_kernel<false><<<grid, 256, 0, st>>>(plan_words(plan_dev), side, X, dy, dWp, h->group, B, Cin, Cout, tiles_per_cta, total_tiles);
+      rc = check_launch("wgrad_simt");
+      if (rc) return rc;
+    }
+    if (db) {
+      const long long rows = (long long)B * side.P_dst;
+      int ctas = (int)((rows + 255) / 256);
+      if (ctas > 148 * 4) ctas = 148 * 4;
+      const int rows_per_cta = (int)((rows + ctas - 1) / ctas);
+      gin::bias_grad_kernel<<<ctas, 256, 0, st>>>(dy, db, rows, Cout, rows_per_cta);
+      rc = check_launch("bias_grad");
+      if (rc) return rc;
+    }
+  }
+  gin::unpack_wgrad_kernel<<<grid_for(7LL * Cin * Cout, 256), 256, 0, st>>>(dWp, dW, Cin, Cout);
+  return check_launch("unpack_wgrad");
+}
+
+static int up_hdr(const void* plan_host, const void* plan_dev, const GinUpPlanHdr** out) {
+  if (!plan_dev) return fail(GIN_ERR_ARG, "null plan");
+  const int32_t* w = plan_header(plan_host);
+  if (!w) return GIN_ERR_PLAN;
+  const GinUpPlanHdr* h = reinterpret_cast<const GinUpPlanHdr*>(w);
+  if (h->kind != GIN_PLAN_UPSAMPLE) return fail(GIN_ERR_PLAN, "plan is not an upsample plan (kind %d)", h->kind);
+  *out = h;
+  return GIN_OK;
+}
+
+int gin_upsample_fwd(const void* plan_host, const void* plan_dev, const float* x, float* y, int B, int C, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!x || !y || B < 0 || C <= 0 || (C & 3)) return fail(GIN_ERR_ARG, "gin_upsample_fwd: bad argument (C must be a multiple of 4)");
+  const GinUpPlanHdr* h;
+  int rc = up_hdr(plan_host, plan_dev, &h);
+  if (rc) return rc;
+  if (B == 0) return GIN_OK;
+  const long long work = (long long)B * h->Pf * (C / 4);
+  gin::upsample_fwd_kernel<<<grid_for(work, 256, 16), 256, 0, st>>>(plan_words(plan_dev), x, y, B, C);
+  return check_launch("upsample_fwd");
+}
+
+int gin_upsample_bwd(const void* plan_host, const void* plan_dev, const float* dy, float* dx, int B, int C, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!dy || !dx || B < 0 || C <= 0 || (C & 3)) return fail(GIN_ERR_ARG, "gin_upsample_bwd: bad argument (C must be a multiple of 4)");
+  const GinUpPlanHdr* h;
+  int rc = up_hdr(plan_host, plan_dev, &h);
+  if (rc) return rc;
+  if (B == 0) return GIN_OK;
+  const long long work = (long long)B * h->Pc * (C / 4);
+  gin::upsample_bwd_kernel<<<grid_for(work, 256, 16), 256, 0, st>>>(plan_words(plan_dev), dy, dx, B, C);
+  return check_launch("upsample_bwd");
+}
+
+int gin_reparam_fwd(const float* mu, const float* logvar, float* eps, float* z, int64_t n, uint64_t seed, uint64_t offset,
+                    void* stream) {
+  if (!mu || !logvar || !eps || !z || n < 0) return fail(GIN_ERR_ARG, "gin_reparam_fwd: bad argument");
+  if (n == 0) return GIN_OK;
+  if (((uintptr_t)mu | (uintptr_t)logvar | (uintptr_t)eps | (uintptr_t)z) % 16) return fail(GIN_ERR_ARG, "gin_reparam_fwd: pointers must be 16-byte aligned");
+  gin::reparam_fwd_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(mu, logvar, eps, z, n, seed, offset);
+  return check_launch("reparam_fwd");
+}
+
+int gin_reparam_bwd(const float* dz, const float* logvar, const float* eps, float* dmu, float* dlogvar, int64_t n, void* stream) {
+  if (!dz || !logvar || !eps || !dmu || !dlogvar || n < 0) return fail(GIN_ERR_ARG, "gin_reparam_bwd: bad argument");
+  if (n == 0) return GIN_OK;
+  gin::reparam_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dz, logvar, eps, dmu, dlogvar, n);
+  return check_launch("reparam_bwd");
+}
+
+int gin_kld_fwd(const float* mu, const float* logvar, float* out, void* ws, int64_t n, void* stream) {
+  if (!mu || !logvar || !out || !ws || n <= 0) return fail(GIN_ERR_ARG, "gin_kld_fwd: bad argument");
+  int parts = grid_for(n, 256, 2);
+  if (parts > 512) parts = 512;
+  gin::kld_partial_kernel<<<parts, 256, 0, (cudaStream_t)stream>>>(mu, logvar, reinterpret_cast<double*>(ws), n);
+  int rc = check_launch("kld_partial");
+  if (rc) return rc;
+  gin::kld_final_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double*>(ws), parts, out, -0.5 / (double)n);
+  return check_launch("kld_final");
+}
+
+int gin_kld_bwd(const float* mu, const float* logvar, const float* dout, float scale, float* dmu, float* dlogvar, int64_t n,
+                void* stream) {
+  if (!mu || !logvar || !dout || !dmu || !dlogvar || n <= 0) return fail(GIN_ERR_ARG, "gin_kld_bwd: bad argument");
+  gin::kld_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(mu, logvar, dout, scale * (float)(-0.5 / (double)n), dmu,
+                                                                         dlogvar, n);
+  return check_launch("kld_bwd");
+}
+
+static int loss_hdr(const void* plan_host, const void* plan_dev, const GinLossPlanHdr** out) {
+  if (!plan_dev) return fail(GIN_ERR_ARG, "null plan");
+  const int32_t* w = plan_header(plan_host);
+  if (!w) return GIN_ERR_PLAN;
+  const GinLossPlanHdr* h = reinterpret_cast<const GinLossPlanHdr*>(w);
+  if (h->kind != GIN_PLAN_LOSS) return fail(GIN_ERR_PLAN, "plan is not a loss plan (kind %d)", h->kind);
+  *out = h;
+  return GIN_OK;
+}
+
+int gin_pole_vertices_fwd(const void* plan_host, const void* plan_dev, const float* x, int64_t sb, int64_t sp, int64_t sc, float* v, int B, int C,
+                          void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!x || !v || B < 0 || C <= 0) return fail(GIN_ERR_ARG, "gin_pole_vertices_fwd: bad argument");
+  const GinLossPlanHdr* h;
+  int rc = loss_hdr(plan_host, plan_dev, &h);
+  if (rc) return rc;
+  if (B == 0) return GIN_OK;
+  GinSrcView X{x, (long long)sb, (long long)sp, (long long)sc, h->P};
+  gin::pole_vertices_fwd_kernel<<<grid_for((long long)B * h->V * C, 256), 256, 0, st>>>(plan_words(plan_dev), X, v, B, C);
+  return check_launch("pole_vertices_fwd");
+}
+
+int gin_pole_vertices_bwd(const void* plan_host, const void* plan_dev, const float* dv, float* dx, int64_t sb, int64_t sp, int64_t sc, int B, int C,
+                          void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!dv || !dx || B < 0 || C <= 0) return fail(GIN_ERR_ARG, "gin_pole_vertices_bwd: bad argument");
+  const GinLossPlanHdr* h;
+  int rc = loss_hdr(plan_host, plan_dev, &h);
+  if (rc) return rc;
+  if (B == 0) return GIN_OK;
+  gin::pole_vertices_bwd_kernel<<<grid_for((long long)B * h->P * C, 256), 256, 0, st>>>(plan_words(plan_dev), dv, dx, sb, sp, sc, B, C);
+  return check_launch("pole_vertices_bwd");
+}
+
+int gin_vertex_normals_fwd(const void* plan_host, const void* plan_dev, const float* v, float* nrm, int B, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!v || !nrm || B < 0) return fail(GIN_ERR_ARG, "gin_vertex_normals_fwd: bad argument");
+  const GinLossPlanHdr* h;
+  int rc = loss_hdr(plan_host, plan_dev, &h);
+  if (rc) return rc;
+  if (B == 0) return GIN_OK;
+  gin::normals_laplacian_kernel<<<grid_for((long long)B * h->V, 256), 256, 0, st>>>(plan_words(plan_dev), v, nrm, nullptr, B);
+  return check_launch("vertex_normals_fwd");
+}
+
+int gin_laplacian_fwd(const void* plan_host, const void* plan_dev, const float* v, float* lap, int B, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!v || !lap || B < 0) return fail(GIN_ERR_ARG, "gin_laplacian_fwd: bad argument");
+  const GinLossPlanHdr* h;
+  int rc = loss_hdr(plan_host, plan_dev, &h);
+  if (rc) return rc;
+  if (B == 0) return GIN_OK;
+  gin::normals_laplacian_kernel<<<grid_for((long long)B * h->V, 256), 256, 0, st>>>(plan_words(plan_dev), v, nullptr, lap, B);
+  return check_launch("laplacian_fwd");
+}
+
+// workspace layout: [v: B*V*3 f32][g: B*V*6 f32][dv: B*V*3 f32][partials: 1024*3 f64]
+size_t gin_p2p_ws_bytes(int B, int level) {
+  if (B < 0 || level < 0 || level > 9) return 0;
+  const size_t V = (size_t)(10 << (2 * level)) + 2;
+  return (size_t)B * V * 12 * 4 + 1024 * 3 * 8 + 64;
+}
+
+int gin_p2p_loss_fwd(const void* plan_host, const void* plan_dev, const float* x, int64_t sb, int64_t sp, int64_t sc, const float* target, float f_pos,
+                     float f_nor, float f_lap, float* out, void* ws, int B, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!x || !target || !out || !ws || B <= 0) return fail(GIN_ERR_ARG, "gin_p2p_loss_fwd: bad argument");
+  const GinLossPlanHdr* h;
+  int rc = loss_hdr(plan_host, plan_dev, &h);
+  if (rc) return rc;
+  const size_t BV = (size_t)B * h->V;
+  float* v = reinterpret_cast<float*>(ws);
+  double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + ((BV * 12 * 4 + 63) / 64) * 64);
+  GinSrcView X{x, (long long)sb, (long long)sp, (long long)sc, h->P};
+  gin::pole_vertices_fwd_kernel<<<grid_for((long long)BV * 3, 256), 256, 0, st>>>(plan_words(plan_dev), X, v, B, 3);
+  if ((rc = check_launch("pole_vertices_fwd"))) return rc;
+  int parts = grid_for((long long)BV, 256, 4);
+  if (parts > 1024) parts = 1024;
+  gin::p2p_fwd_kernel<<<parts, 256, 0, st>>>(plan_words(plan_dev), v, target, partial, B);
+  if ((rc = check_launch("p2p_fwd"))) return rc;
+  gin::p2p_final_kernel<<<1, 256, 0, st>>>(partial, parts, out, 1.0 / (double)BV, f_pos, f_nor, f_lap);
+  return check_launch("p2p_final");
+}
+
+int gin_p2p_loss_bwd(const void* plan_host, const void* plan_dev, const float* x, int64_t sb, int64_t sp, int64_t sc, const float* target, float f_pos,
+                     float f_nor, float f_lap, const float* dout, float* dx, void* ws, int B, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!x || !target || !dout || !dx || !ws || B <= 0) return fail(GIN_ERR_ARG, "gin_p2p_loss_bwd: bad argument");
+  const GinLossPlanHdr* h;
+  int rc = loss_hdr(plan_host, plan_dev, &h);
+  if (rc) return rc;
+  const size_t BV = (size_t)B * h->V;
+  float* v = reinterpret_cast<float*>(ws);
+  float* g = v + BV * 3;
+  float* dv = g + BV * 6;
+  GinSrcView X{x, (long long)sb, (long long)sp, (long long)sc, h->P};
+  gin::pole_vertices_fwd_kernel<<<grid_for((long long)BV * 3, 256), 256, 0, st>>>(plan_words(plan_dev), X, v, B, 3);
+  if ((rc = check_launch("pole_vertices_fwd"))) return rc;
+  gin::p2p_bwd_vertex_kernel<<<grid_for((long long)BV, 256), 256, 0, st>>>(plan_words(plan_dev), v, target, dout, f_pos, f_nor, f_lap, g, dv, B);
+  if ((rc = check_launch("p2p_bwd_vertex"))) return rc;
+  gin::p2p_bwd_gather_kernel<<<grid_for((long long)BV, 256), 256, 0, st>>>(plan_words(plan_dev), v, g, dv, B);
+  if ((rc = check_launch("p2p_bwd_gather"))) return rc;
+  gin::pole_vertices_bwd_kernel<<<grid_for((long long)B * h->P * 3, 256), 256, 0, st>>>(plan_words(plan_dev), dv, dx, sb, sp, sc, B, 3);
+  return check_launch("pole_vertices_bwd");
+}
+
+}  // extern "C"

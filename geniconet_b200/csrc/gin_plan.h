@@ -1,0 +1,54 @@
+// Plan blobs shared between the host builders (gin_host.cpp) and the device kernels.
+// A plan is a position-independent array of int32 words; offsets are in words from the
+// start of the blob.  The caller uploads it once per (layer geometry) and passes the
+// device pointer back to the op entry points (include/geniconet_b200.h).
+#pragma once
+#include <stdint.h>
+
+#define GIN_MAGIC 0x47494E31  // "GIN1"
+#define GIN_TILE_M 128        // rows (pixels) per gather-GEMM tile == UMMA M
+#define GIN_MAX_SLOTS 24      // (bank, tap) slots a tile may carry
+
+// Source codes inside the gather tables:
+//   c >= 0  : pixel index inside the tile's sample group (sg*P_src + p)
+//   c == -1 : contributes zero
+//   c <= -2 : pole mean;  q = -2 - c,  sample-in-group = q >> 1,  pole = q & 1  (0 north, 1 south)
+#define GIN_SRC_ZERO (-1)
+
+struct GinTileDesc {          // 8 words
+  int32_t nslots;             // number of (tap) slots this tile accumulates over
+  int32_t src_off;            // word offset (relative to side.src_off) of int32 src[nslots][128]
+  int8_t tap[GIN_MAX_SLOTS];  // weight (tap) index used by each slot
+};
+
+struct GinSide {              // one gather-GEMM problem: rows of dst gathered from src
+  int32_t ntiles;             // tiles per sample group
+  int32_t tiles_off;          // GinTileDesc[ntiles]
+  int32_t src_off;            // base of all src tables
+  int32_t rows_off;           // int32 dst_row[ntiles*128]: dst pixel inside group or -1
+  int32_t P_src, P_dst;       // pixels per sample on the gathered / written side
+  int32_t ring_off;           // int32 ring[2][5]: the pole rings at the src level
+  int32_t max_slots;
+};
+
+struct GinConvPlanHdr {
+  int32_t magic, kind, level_in, level_out, stride, corner_mode, group, total_words;
+  GinSide fwd;                // y rows gathered from x   (also drives wgrad)
+  GinSide dg;                 // dx rows gathered from dy (adjoint of pad o conv)
+};
+
+struct GinUpPlanHdr {
+  int32_t magic, kind, level, corner_mode, Pc, Pf, total_words;
+  int32_t fwd_off;            // int32 src[Pf][2]   (codes as above, sample-in-group = 0)
+  int32_t ring_off;           // int32 ring[2][5] at the coarse level
+  int32_t bwd_deg;            // ELL width of the adjoint
+  int32_t bwd_idx_off;        // int32 idx[Pc][deg] fine pixel or -1
+  int32_t bwd_w_off;          // float w[Pc][deg]
+};
+
+struct GinLossPlanHdr {
+  int32_t magic, kind, level, P, V, total_words;
+  int32_t ring_off;           // int32 nb[V][6] one-ring, counter-clockwise seen from outside, -1 padded
+  int32_t pole_off;           // int32 ring[2][5] pixels averaged into the poles
+  int32_t flag_off;           // int32 poleflag[P]: 1 = in north ring, 2 = in south ring
+};

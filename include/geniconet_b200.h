@@ -1,0 +1,140 @@
+/*
+ * geniconet_b200 -- C ABI of the B200-native icosahedral-convolution hot path.
+ *
+ * The reference (hrdkjain/GenIcoNet) has NO FFI: its hot path is the Python module
+ * surface  icocnn.ico_conv.{IcoConvS2S,IcoUpsampleS2S}  (models.py:5-6) and the loss
+ * classes of losses.py.  This header is the boundary a maintainer binds instead
+ * (ctypes stub shown in INTEGRATION.md); every entry point names the reference
+ * interface it replaces.
+ *
+ * Conventions
+ *   - plain C, no torch types; device pointers are raw CUDA device pointers that the
+ *     caller owns; `stream` is a cudaStream_t passed as void*.
+ *   - every function returns 0 on success, a negative gin_status on failure; the text of
+ *     the last failure on the calling thread is gin_last_error().
+ *   - the library never allocates device memory and keeps no device state: index tables
+ *     ("plans") are built on the HOST into a caller buffer (gin_plan_build) and uploaded by
+ *     the caller; ops take both copies: `plan_host` (launch geometry is read from its
+ *     header) and `plan_dev` (the kernels read the tables).
+ *   - activations are fp32, pixel-major / channel-minor ("channels last"):
+ *     element (b, p, c) of a level-s map lives at  b*P*C + p*C + c,  P = 10*4^s,
+ *     p = chart*n*2n + i*2n + j  (data.py:64-69, ico_utils.py:20-23).  The input of
+ *     gin_hexconv_fwd / gin_hexconv_wgrad may instead use arbitrary element strides
+ *     (sb, sp, sc) so the NCHW xyz input of models.py:104 needs no transpose.
+ *   - corner_mode: 0 = 'zeros', 1 = 'average' (models.py:11, run.py:683).
+ *   - impl: GIN_IMPL_SIMT = fp32 CUDA-core kernels (exact fp32 accumulate),
+ *           GIN_IMPL_TC   = tcgen05 implicit GEMM, bf16 operands / fp32 accumulate in TMEM,
+ *           GIN_IMPL_AUTO = TC when the channel widths make it a dense contraction
+ *                           (Cin % 64 == 0 and Cout % 64 == 0), SIMT otherwise.
+ */
+#ifndef GENICONET_B200_H
+#define GENICONET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  GIN_OK = 0,
+  GIN_ERR_ARG = -1,       /* bad argument (shape, level, null pointer, alignment) */
+  GIN_ERR_PLAN = -2,      /* plan blob does not match the call */
+  GIN_ERR_CUDA = -3,      /* a CUDA runtime call / launch failed */
+  GIN_ERR_UNSUPPORTED = -4
+} gin_status;
+
+enum { GIN_IMPL_AUTO = 0, GIN_IMPL_SIMT = 1, GIN_IMPL_TC = 2 };
+enum { GIN_CORNER_ZEROS = 0, GIN_CORNER_AVERAGE = 1 };
+
+int gin_version(void);
+const char* gin_last_error(void);
+
+/* ------------------------------------------------------------------ host: geometry -- */
+/* Row a1: the chart-padding index map that icocnn builds inside
+ * IcoConvS2S/IcoUpsampleS2S (absent source; rule restated in-tree at losses.py:22-31).
+ * out[k][i+1][j+1], k<5, i in [-1,n], j in [-1,2n]  =  source pixel id, P (north pole),
+ * P+1 (south pole) or -1 (cell never read).  gin_index_map_len = 5*(n+2)*(2n+2). */
+int gin_index_map_len(int level);
+int gin_index_map(int level, int32_t* out);
+
+/* icocnn.utils.ico_geometry.get_ico_faces (losses.py:34) / get_icosahedral_grid
+ * (generate.py:151): faces [20*4^s][3] (outward winding), vertices [P+2][3] (unit sphere). */
+int gin_ico_faces_len(int level);
+int gin_ico_faces(int level, int32_t* out);
+int gin_ico_vertices(int level, float* out);
+
+/* ------------------------------------------------------------------ host: plans ----- */
+/* kind of plan: */
+enum { GIN_PLAN_HEXCONV = 1, GIN_PLAN_UPSAMPLE = 2, GIN_PLAN_LOSS = 3 };
+/* level = INPUT subdivision level of the layer (models.py:14,25-33: `subdivisions`);
+ * stride in {1,2} (ignored unless HEXCONV). Returns bytes (0 on error). */
+size_t gin_plan_bytes(int kind, int level, int stride, int corner_mode);
+int gin_plan_build(int kind, int level, int stride, int corner_mode, void* host_buf, size_t bytes);
+
+/* ------------------------------------------------------------------ device: hexconv -- */
+/* Packed weights: one buffer holding the kernel-native copies of weight[Cout][Cin][7]
+ * (fp32 [7][Cin][Cout] and [7][Cout][Cin]; bf16 K-major copies for tcgen05). */
+size_t gin_hexconv_packed_bytes(int Cin, int Cout);
+int gin_hexconv_pack_weights(const float* weight, void* packed, int Cin, int Cout, void* stream);
+
+/* IcoConvS2S.forward (models.py:14,25-33,45-55,104,165,269,279): rows a1+a2+a3.
+ * y[b,p,:] = bias + sum_t W_t^T x~[b, p+t, :] with the padding fused into the gather. */
+int gin_hexconv_fwd(const void* plan_host, const void* plan_dev, const float* x, int64_t sb, int64_t sp, int64_t sc,
+                    const void* packed, const float* bias /* may be NULL */, float* y,
+                    int B, int Cin, int Cout, int impl, void* stream);
+/* autograd backward of the above (run.py:249), row a5: dgrad = adjoint of pad o conv. */
+int gin_hexconv_dgrad(const void* plan_host, const void* plan_dev, const float* dy, const void* packed, float* dx,
+                      int B, int Cin, int Cout, int impl, void* stream);
+/* wgrad: dW[Cout][Cin][7], db[Cout] (db may be NULL). ws: gin_hexconv_wgrad_ws_bytes(). */
+size_t gin_hexconv_wgrad_ws_bytes(int Cin, int Cout);
+int gin_hexconv_wgrad(const void* plan_host, const void* plan_dev, const float* x, int64_t sb, int64_t sp, int64_t sc,
+                      const float* dy, float* dW, float* db, void* ws,
+                      int B, int Cin, int Cout, int impl, void* stream);
+
+/* ------------------------------------------------------------------ device: upsample - */
+/* IcoUpsampleS2S.forward (models.py:13,45,53), row a4, and its backward. */
+int gin_upsample_fwd(const void* plan_host, const void* plan_dev, const float* x, float* y, int B, int C, void* stream);
+int gin_upsample_bwd(const void* plan_host, const void* plan_dev, const float* dy, float* dx, int B, int C, void* stream);
+
+/* ------------------------------------------------------------------ device: VAE ------ */
+/* VAE.reparameterize (models.py:89-92), row a6: eps ~ N(0,1) from Philox4x32-10
+ * (seed, offset), z = eps*exp(0.5*logvar)+mu; eps is written out for the backward. */
+int gin_reparam_fwd(const float* mu, const float* logvar, float* eps, float* z, int64_t n,
+                    uint64_t seed, uint64_t offset, void* stream);
+int gin_reparam_bwd(const float* dz, const float* logvar, const float* eps, float* dmu, float* dlogvar,
+                    int64_t n, void* stream);
+/* KLD_Loss.forward (losses.py:92-108), row a9: out[0] = mean_b(-0.5*mean_i(1+lv-mu^2-exp(lv))). */
+int gin_kld_fwd(const float* mu, const float* logvar, float* out, void* ws /* 4096 B */, int64_t n, void* stream);
+int gin_kld_bwd(const float* mu, const float* logvar, const float* dout /* device scalar */, float scale,
+                float* dmu, float* dlogvar, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------ device: losses --- */
+/* Pole averaging + grid->vertex list (losses.py:22-31,49-51; ico_utils.py:10-24), row a7:
+ * x [B,C,5n,2n] with element strides (sb, sp, sc) -> v [B][P+2][C]. */
+int gin_pole_vertices_fwd(const void* plan_host, const void* plan_dev, const float* x, int64_t sb, int64_t sp, int64_t sc,
+                          float* v, int B, int C, void* stream);
+int gin_pole_vertices_bwd(const void* plan_host, const void* plan_dev, const float* dv, float* dx, int64_t sb, int64_t sp, int64_t sc,
+                          int B, int C, void* stream);
+/* compute_vertex_normals / compute_laplacian_batch (mesh.utils; losses.py:54,57). */
+int gin_vertex_normals_fwd(const void* plan_host, const void* plan_dev, const float* v, float* nrm, int B, void* stream);
+int gin_laplacian_fwd(const void* plan_host, const void* plan_dev, const float* v, float* lap, int B, void* stream);
+/* Point2Point_Loss.forward (losses.py:47-82), row a8, fused: out[0..3] = l_pos, l_nor, l_lap,
+ * f_pos*l_pos + f_nor*l_nor + f_lap*l_lap.  target [B][9][P+2] (generate.py:200-203).
+ * ws: gin_p2p_ws_bytes(B, level). The backward re-derives everything from x/target. */
+size_t gin_p2p_ws_bytes(int B, int level);
+int gin_p2p_loss_fwd(const void* plan_host, const void* plan_dev, const float* x, int64_t sb, int64_t sp, int64_t sc,
+                     const float* target, float f_pos, float f_nor, float f_lap,
+                     float* out, void* ws, int B, void* stream);
+int gin_p2p_loss_bwd(const void* plan_host, const void* plan_dev, const float* x, int64_t sb, int64_t sp, int64_t sc,
+                     const float* target, float f_pos, float f_nor, float f_lap,
+                     const float* dout /* device scalar */, float* dx, void* ws, int B, void* stream);
+
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
+int64_t gin_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
