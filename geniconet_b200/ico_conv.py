@@ -1,0 +1,232 @@
+"""Host-side mirror of ``icocnn.ico_conv`` over the C ABI.
+
+Same constructor signatures and tensor contracts as the reference's call sites
+(/root/reference/models.py:13-15, 25-33, 45-55, 104, 165, 269, 279):
+
+    IcoConvS2S(in_features, out_features, stride, bias, subdivisions, corner_mode=...)
+        forward: [B, Cin, 5n, 2n] float32 -> [B, Cout, 5n/stride, 2n/stride]
+    IcoUpsampleS2S(in_features, subdivisions, corner_mode)
+        forward: [B, C, 5n, 2n] -> [B, C, 10n, 4n]
+
+`subdivisions` is the INPUT level.  Outputs are ordinary 4-D float32 tensors with logical NCHW
+shape and channels-last strides, so the stock BatchNorm2d/ReLU/add of models.py:37-39 run on
+them unchanged and without a transpose.  There is no CPU implementation: tensors that are
+not on a CUDA device raise.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_PLANS = {}
+
+
+class Plan:
+    """Host blob + device copy of one plan; both stay alive for the life of the process."""
+
+    def __init__(self, kind, level, stride, corner_mode, device):
+        self.host = _lib.plan_blob(kind, level, stride, corner_mode)
+        self.dev = torch.from_numpy(self.host).to(device)
+        self.host_ptr = self.host.ctypes.data
+        self.dev_ptr = self.dev.data_ptr()
+
+
+def get_plan(kind, level, stride, corner_mode, device):
+    device = torch.device(device)
+    if device.type != 'cuda':
+        raise RuntimeError('geniconet_b200 has no CPU path: expected a CUDA device, got %s' % device)
+    if device.index is None:
+        device = torch.device('cuda', torch.cuda.current_device())
+    key = (kind, level, stride, corner_mode, device.index)
+    p = _PLANS.get(key)
+    if p is None:
+        p = _PLANS[key] = Plan(kind, level, stride, corner_mode, device)
+    return p
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda_f32(x, what):
+    if not x.is_cuda:
+        raise RuntimeError('%s: geniconet_b200 has no CPU path (tensor is on %s)' % (what, x.device))
+    if x.dtype != torch.float32:
+        raise TypeError('%s: expected float32, got %s' % (what, x.dtype))
+
+
+def pixel_strides(x):
+    """(tensor, sb, sp, sc) element strides of a [B,C,H,W] map seen as (sample, pixel, channel)."""
+    B, C, H, W = x.shape
+    s0, s1, s2, s3 = x.stride()
+    if H * W > 1 and s2 != W * s3 and H > 1:
+        x = x.contiguous(memory_format=torch.channels_last)
+        s0, s1, s2, s3 = x.stride()
+    return x, s0, s3, s1
+
+
+def as_channels_last(x):
+    """[B,C,H,W] with channels-last strides (no copy when it already is)."""
+    B, C, H, W = x.shape
+    if x.stride() == (H * W * C, 1, W * C, C):
+        return x
+    return x.contiguous(memory_format=torch.channels_last) if C > 1 and H * W > 1 else \
+        x.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+
+
+def _new_map(B, C, H, W, device):
+    return torch.empty((B, H, W, C), dtype=torch.float32, device=device).permute(0, 3, 1, 2)
+
+
+class _HexConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, mod):
+        _require_cuda_f32(x, 'IcoConvS2S')
+        B, C, H, W = x.shape
+        n = mod._n
+        if C != mod.in_features or H != 5 * n or W != 2 * n:
+            raise ValueError('IcoConvS2S(level %d): expected [B,%d,%d,%d], got %s'
+                             % (mod.subdivisions, mod.in_features, 5 * n, 2 * n, tuple(x.shape)))
+        plan = get_plan(_lib.PLAN_HEXCONV, mod.subdivisions, mod.stride, mod.corner_mode, x.device)
+        packed = mod._packed_weights(weight)
+        xs, sb, sp, sc = pixel_strides(x)
+        Ho, Wo = H // mod.stride, W // mod.stride
+        y = _new_map(B, mod.out_features, Ho, Wo, x.device)
+        if B > 0:
+            _lib.check(_lib.lib.gin_hexconv_fwd(plan.host_ptr, plan.dev_ptr, xs.data_ptr(), sb, sp, sc, packed.data_ptr(),
+                                                bias.data_ptr() if bias is not None else None, y.data_ptr(),
+                                                B, mod.in_features, mod.out_features, mod.impl, _stream()), 'gin_hexconv_fwd')
+        ctx.mod, ctx.plan, ctx.strides, ctx.has_bias = mod, plan, (sb, sp, sc), bias is not None
+        ctx.save_for_backward(xs, packed)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xs, packed = ctx.saved_tensors
+        mod, plan = ctx.mod, ctx.plan
+        B = xs.shape[0]
+        dy = as_channels_last(dy)
+        dx = dW = db = None
+        st = _stream()
+        if B == 0:
+            return (torch.zeros_like(xs) if ctx.needs_input_grad[0] else None,
+                    torch.zeros(mod.out_features, mod.in_features, 7, device=xs.device),
+                    torch.zeros(mod.out_features, device=xs.device) if ctx.has_bias else None, None)
+        if ctx.needs_input_grad[0]:
+            dx = _new_map(B, mod.in_features, xs.shape[2], xs.shape[3], xs.device)
+            _lib.check(_lib.lib.gin_hexconv_dgrad(plan.host_ptr, plan.dev_ptr, dy.data_ptr(), packed.data_ptr(), dx.data_ptr(),
+                                                  B, mod.in_features, mod.out_features, mod.impl, st), 'gin_hexconv_dgrad')
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dW = torch.empty((mod.out_features, mod.in_features, 7), dtype=torch.float32, device=xs.device)
+            db = torch.empty((mod.out_features,), dtype=torch.float32, device=xs.device) if ctx.has_bias else None
+            ws = torch.empty((_lib.lib.gin_hexconv_wgrad_ws_bytes(mod.in_features, mod.out_features),), dtype=torch.uint8,
+                             device=xs.device)
+            sb, sp, sc = ctx.strides
+            _lib.check(_lib.lib.gin_hexconv_wgrad(plan.host_ptr, plan.dev_ptr, xs.data_ptr(), sb, sp, sc, dy.data_ptr(),
+                                                  dW.data_ptr(), db.data_ptr() if db is not None else None, ws.data_ptr(),
+                                                  B, mod.in_features, mod.out_features, mod.impl, st), 'gin_hexconv_wgrad')
+        return dx, dW, db, None
+
+
+class IcoConvS2S(torch.nn.Module):
+    """Hex-masked 3x3 convolution over the 5 icosahedral charts with the chart padding fused in.
+
+    Parameters: ``weight [Cout, Cin, 7]`` (taps: centre, N, S, W, E, NE, SW in lattice terms, see
+    gin_host.cpp kTap) and ``bias [Cout]``.
+    """
+
+    def __init__(self, in_features, out_features, stride=1, bias=True, subdivisions=0, corner_mode='zeros', impl='auto'):
+        super().__init__()
+        if stride not in (1, 2):
+            raise ValueError('stride must be 1 or 2')
+        if stride == 2 and subdivisions < 1:
+            raise ValueError('stride 2 needs subdivisions >= 1')
+        if corner_mode not in _lib.CORNER:
+            raise ValueError('corner_mode must be zeros or average, got %r' % (corner_mode,))
+        self.in_features, self.out_features = int(in_features), int(out_features)
+        self.stride, self.subdivisions, self.corner_mode = int(stride), int(subdivisions), corner_mode
+        self.impl = {'auto': _lib.IMPL_AUTO, 'simt': _lib.IMPL_SIMT, 'tc': _lib.IMPL_TC}[impl]
+        self._n = 2 ** self.subdivisions
+        self.weight = torch.nn.Parameter(torch.empty(self.out_features, self.in_features, 7))
+        self.bias = torch.nn.Parameter(torch.empty(self.out_features)) if bias else None
+        bound = 1.0 / math.sqrt(self.in_features * 7)
+        torch.nn.init.uniform_(self.weight, -bound, bound)
+        if bias:
+            torch.nn.init.uniform_(self.bias, -bound, bound)
+        self._packed = None
+        self._packed_key = None
+
+    def _packed_weights(self, weight):
+        key = (weight.data_ptr(), weight._version, weight.device)
+        if self._packed is None or self._packed_key != key:
+            nbytes = _lib.lib.gin_hexconv_packed_bytes(self.in_features, self.out_features)
+            # a fresh buffer per weight version: a pending backward may still hold the previous one
+            self._packed = torch.empty((nbytes,), dtype=torch.uint8, device=weight.device)
+            w = weight.detach()
+            if not w.is_contiguous():
+                w = w.contiguous()
+            _lib.check(_lib.lib.gin_hexconv_pack_weights(w.data_ptr(), self._packed.data_ptr(), self.in_features,
+                                                         self.out_features, _stream()), 'gin_hexconv_pack_weights')
+            self._packed_key = key
+        return self._packed
+
+    def forward(self, x):
+        return _HexConvFn.apply(x, self.weight, self.bias, self)
+
+    def extra_repr(self):
+        return '%d -> %d, stride=%d, level=%d, corner_mode=%s' % (self.in_features, self.out_features, self.stride,
+                                                                   self.subdivisions, self.corner_mode)
+
+
+class _UpsampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mod):
+        _require_cuda_f32(x, 'IcoUpsampleS2S')
+        B, C, H, W = x.shape
+        n = 2 ** mod.subdivisions
+        if H != 5 * n or W != 2 * n:
+            raise ValueError('IcoUpsampleS2S(level %d): expected [B,C,%d,%d], got %s' % (mod.subdivisions, 5 * n, 2 * n, tuple(x.shape)))
+        if C % 4:
+            raise ValueError('IcoUpsampleS2S: channel count must be a multiple of 4, got %d' % C)
+        plan = get_plan(_lib.PLAN_UPSAMPLE, mod.subdivisions, 1, mod.corner_mode, x.device)
+        xs = as_channels_last(x)
+        y = _new_map(B, C, 2 * H, 2 * W, x.device)
+        _lib.check(_lib.lib.gin_upsample_fwd(plan.host_ptr, plan.dev_ptr, xs.data_ptr(), y.data_ptr(), B, C, _stream()), 'gin_upsample_fwd')
+        ctx.plan, ctx.shape = plan, (B, C, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, C, H, W = ctx.shape
+        dy = as_channels_last(dy)
+        dx = _new_map(B, C, H, W, dy.device)
+        _lib.check(_lib.lib.gin_upsample_bwd(ctx.plan.host_ptr, ctx.plan.dev_ptr, dy.data_ptr(), dx.data_ptr(), B, C, _stream()),
+                   'gin_upsample_bwd')
+        return dx, None
+
+
+class IcoUpsampleS2S(torch.nn.Module):
+    """Level s -> s+1: coarse vertices copy, edge midpoints average their two endpoints (parameter free)."""
+
+    def __init__(self, in_features, subdivisions, corner_mode='zeros'):
+        super().__init__()
+        if corner_mode not in _lib.CORNER:
+            raise ValueError('corner_mode must be zeros or average, got %r' % (corner_mode,))
+        self.in_features, self.subdivisions, self.corner_mode = int(in_features), int(subdivisions), corner_mode
+
+    def forward(self, x):
+        return _UpsampleFn.apply(x, self)
+
+    def extra_repr(self):
+        return '%d ch, level %d -> %d, corner_mode=%s' % (self.in_features, self.subdivisions, self.subdivisions + 1, self.corner_mode)
+
+
+def set_impl(module, impl):
+    """Force 'auto' | 'simt' | 'tc' on every IcoConvS2S below `module` (parity tests use this)."""
+    code = {'auto': _lib.IMPL_AUTO, 'simt': _lib.IMPL_SIMT, 'tc': _lib.IMPL_TC}[impl]
+    for m in module.modules():
+        if isinstance(m, IcoConvS2S):
+            m.impl = code
+    return module

@@ -1,0 +1,241 @@
+"""GPU parity (run with -m gpu): every hot-path op through the C ABI vs the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import icocnn_ref
+import oracle_models as om
+
+pytestmark = pytest.mark.gpu
+
+# fp32 CUDA-core path vs fp32 oracle
+RTOL32, ATOL32 = 1e-4, 1e-5
+
+
+def _conv_pair(cin, cout, stride, level, cm, impl):
+    from geniconet_b200.ico_conv import IcoConvS2S
+    torch.manual_seed(1)
+    ref = icocnn_ref.IcoConvS2S(cin, cout, stride, True, level, cm)
+    mod = IcoConvS2S(cin, cout, stride, True, level, cm, impl=impl).cuda()
+    mod.load_state_dict(ref.state_dict())
+    return ref, mod
+
+
+def _check_conv(cin, cout, stride, level, cm, B, impl, rtol, atol, layout='cl'):
+    ref, mod = _conv_pair(cin, cout, stride, level, cm, impl)
+    n = 2 ** level
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, cin, 5 * n, 2 * n, generator=g)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    gy = torch.randn(yr.shape, generator=g)
+    yr.backward(gy)
+    xc = x.cuda()
+    if layout == 'cl':
+        xc = xc.contiguous(memory_format=torch.channels_last)
+    xc.requires_grad_(True)
+    yc = mod(xc)
+    assert yc.shape == yr.shape
+    yc.backward(gy.cuda())
+    torch.cuda.synchronize()
+
+    def close(a, b, what):
+        a = a.detach().cpu()
+        scale = b.abs().max().item()
+        err = (a - b).abs().max().item()
+        assert err <= atol * max(1.0, scale) + rtol * scale, '%s: max err %.3e (scale %.3e)' % (what, err, scale)
+    close(yc, yr.detach(), 'fwd')
+    close(xc.grad, xr.grad, 'dgrad')
+    close(mod.weight.grad, ref.weight.grad, 'wgrad')
+    close(mod.bias.grad, ref.bias.grad, 'bgrad')
+
+
+SIMT_CASES = [
+    # (cin, cout, stride, level, corner_mode, B, layout)
+    (3, 64, 1, 5, 'average', 2, 'nchw'),      # encoder.0 (models.py:104), NCHW xyz input
+    (3, 16, 1, 2, 'zeros', 5, 'nchw'),
+    (8, 12, 1, 3, 'average', 3, 'cl'),
+    (8, 12, 2, 3, 'average', 3, 'cl'),
+    (5, 7, 2, 2, 'zeros', 6, 'nchw'),          # ragged channels, partial sample group
+    (16, 8, 1, 1, 'average', 19, 'cl'),        # level 1: 16 samples per tile group, ragged batch
+    (64, 64, 1, 4, 'average', 2, 'cl'),
+    (64, 128, 2, 4, 'average', 2, 'cl'),
+]
+
+
+@pytest.mark.parametrize('case', SIMT_CASES)
+def test_hexconv_simt_matches_oracle(case):
+    cin, cout, stride, level, cm, B, layout = case
+    _check_conv(cin, cout, stride, level, cm, B, 'simt', RTOL32, ATOL32, layout)
+
+
+def test_hexconv_empty_batch():
+    from geniconet_b200.ico_conv import IcoConvS2S
+    mod = IcoConvS2S(8, 8, 1, True, 2, 'average', impl='simt').cuda()
+    y = mod(torch.zeros(0, 8, 20, 8, device='cuda'))
+    assert tuple(y.shape) == (0, 8, 20, 8)
+
+
+def test_hexconv_rejects_cpu_and_bad_shapes():
+    from geniconet_b200.ico_conv import IcoConvS2S
+    mod = IcoConvS2S(8, 8, 1, True, 2, 'average')
+    with pytest.raises(RuntimeError):
+        mod(torch.zeros(1, 8, 20, 8))
+    with pytest.raises(ValueError):
+        mod.cuda()(torch.zeros(1, 8, 40, 16, device='cuda'))
+    with pytest.raises(ValueError):
+        IcoConvS2S(8, 8, 3, True, 2, 'average')
+    with pytest.raises(ValueError):
+        IcoConvS2S(8, 8, 1, True, 2, 'mirror')
+
+
+@pytest.mark.parametrize('level,cm,C,B', [(2, 'average', 256, 3), (3, 'zeros', 8, 2), (4, 'average', 128, 2), (1, 'average', 4, 5)])
+def test_upsample_matches_oracle(level, cm, C, B):
+    from geniconet_b200.ico_conv import IcoUpsampleS2S
+    ref = icocnn_ref.IcoUpsampleS2S(C, level, cm)
+    mod = IcoUpsampleS2S(C, level, cm)
+    n = 2 ** level
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, C, 5 * n, 2 * n, generator=g)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    gy = torch.randn(yr.shape, generator=g)
+    yr.backward(gy)
+    xc = x.cuda().requires_grad_(True)
+    yc = mod(xc)
+    yc.backward(gy.cuda())
+    assert torch.allclose(yc.cpu(), yr.detach(), rtol=1e-6, atol=1e-6)
+    assert torch.allclose(xc.grad.cpu(), xr.grad, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('level,B,factors', [(2, 3, (0.6, 0.2, 0.2)), (3, 2, (1., 0., 0.)), (5, 2, (0.6, 0.2, 0.2))])
+@pytest.mark.parametrize('layout', ['nchw', 'cl'])
+def test_p2p_loss_matches_oracle(level, B, factors, layout):
+    from geniconet_b200 import losses
+    n = 2 ** level
+    V = 10 * 4 ** level + 2
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, 3, 5 * n, 2 * n, generator=g) * 0.5
+    tgt = torch.randn(B, 9, V, generator=g)
+    xr = x.clone().requires_grad_(True)
+    lr, parts = om.ref_p2p_loss(level, xr, tgt, *factors)
+    lr.backward()
+    crit = losses.P2P_Loss(level, *factors)
+    xc = x.cuda()
+    if layout == 'cl':
+        xc = xc.contiguous(memory_format=torch.channels_last)
+    xc.requires_grad_(True)
+    lc = crit(xc, tgt.cuda())
+    lc.backward()
+    got = crit.get_last_losses()
+    assert abs(lc.item() - lr.item()) <= 1e-5 * max(1, abs(lr.item()))
+    for a, b in zip(got[:3], parts):
+        assert abs(a - b.item()) <= 2e-5 * max(1, abs(b.item()))
+    gerr = (xc.grad.cpu() - xr.grad).abs().max().item()
+    assert gerr <= 1e-4 * xr.grad.abs().max().item() + 1e-9, gerr
+
+
+def test_kld_and_reparam():
+    from geniconet_b200 import losses
+    from geniconet_b200.reparam import reparameterize
+    g = torch.Generator().manual_seed(5)
+    mu = torch.randn(3, 512, 20, 8, generator=g)
+    lv = torch.randn(3, 512, 20, 8, generator=g) * 0.5
+    mur, lvr = mu.clone().requires_grad_(True), lv.clone().requires_grad_(True)
+    kr = om.ref_kld(mur, lvr)
+    kr.backward()
+    muc = mu.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    lvc = lv.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    kc = losses._KLDFn.apply(muc, lvc)
+    kc.backward()
+    assert abs(kc.item() - kr.item()) <= 1e-5 * abs(kr.item())
+    assert torch.allclose(muc.grad.cpu(), mur.grad, rtol=1e-4, atol=1e-9)
+    assert torch.allclose(lvc.grad.cpu(), lvr.grad, rtol=1e-4, atol=1e-9)
+    # reparameterisation: z reproduces from the returned eps; eps is N(0,1); (seed, offset) is deterministic
+    muc.grad = lvc.grad = None
+    z, eps = reparameterize(muc, lvc, seed=42, offset=3, return_eps=True)
+    z2, eps2 = reparameterize(muc, lvc, seed=42, offset=3, return_eps=True)
+    z3, eps3 = reparameterize(muc, lvc, seed=42, offset=4, return_eps=True)
+    assert torch.equal(eps, eps2) and torch.equal(z, z2) and not torch.equal(eps, eps3)
+    e = eps.detach().cpu()
+    zr = e * torch.exp(0.5 * lvr.detach()) + mur.detach()
+    assert torch.allclose(z.detach().cpu(), zr, rtol=1e-5, atol=1e-6)
+    assert abs(e.mean().item()) < 5e-3 and abs(e.std().item() - 1) < 5e-3 and abs((e ** 4).mean().item() - 3) < 0.05
+    gz = torch.randn(z.shape, generator=g)
+    z.backward(gz.cuda())
+    mur.grad = lvr.grad = None
+    (e * torch.exp(0.5 * lvr) + mur).backward(gz)
+    assert torch.allclose(muc.grad.cpu(), mur.grad, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(lvc.grad.cpu(), lvr.grad, rtol=1e-4, atol=1e-7)
+
+
+def test_output2vertices():
+    from geniconet_b200.losses import output2vertices
+    from oracle import ico_geometry_ref as geo
+    x = torch.randn(2, 3, 160, 64)
+    rings = torch.from_numpy(geo.pole_rings(5))
+    flat = x.reshape(2, 3, -1)
+    ref = torch.cat((flat, flat[:, :, rings].mean(-1)), dim=2).transpose(1, 2)
+    got = output2vertices(5, x.cuda())
+    assert torch.allclose(got.cpu(), ref, rtol=1e-6, atol=1e-6)
+
+
+# ---------------------------------------------------------------- tcgen05 path
+# bf16 operands / fp32 accumulate: vs the fp32 oracle rtol 2e-2 of the tensor scale;
+# vs an oracle fed bf16-rounded inputs and weights the only difference is summation order: 2e-3.
+TC_CASES = [
+    # (cin, cout, stride, level, corner_mode, B)  -- every (Cin,Cout,stride) of models.py at reduced batch
+    (64, 64, 1, 3, 'average', 2),
+    (64, 128, 2, 4, 'average', 2),
+    (128, 128, 1, 3, 'average', 3),
+    (128, 256, 2, 3, 'average', 2),
+    (256, 256, 1, 2, 'average', 5),        # level 2: 4 samples per tile group, ragged batch
+    (256, 256, 2, 3, 'average', 4),
+    (256, 128, 1, 3, 'zeros', 2),
+    (128, 64, 1, 4, 'average', 1),
+    (256, 512, 2, 3, 'average', 3),
+    (512, 256, 1, 3, 'average', 1),
+]
+
+
+def _bf16_round(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.mark.parametrize('case', TC_CASES)
+def test_hexconv_tc_matches_oracle(case):
+    from geniconet_b200.ico_conv import IcoConvS2S
+    cin, cout, stride, level, cm, B = case
+    torch.manual_seed(2)
+    ref = icocnn_ref.IcoConvS2S(cin, cout, stride, True, level, cm)
+    mod = IcoConvS2S(cin, cout, stride, True, level, cm, impl='tc').cuda()
+    mod.load_state_dict(ref.state_dict())
+    n = 2 ** level
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(B, cin, 5 * n, 2 * n, generator=g)
+    # reference A: true fp32
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    gy = torch.randn(yr.shape, generator=g)
+    yr.backward(gy)
+    full = dict(y=yr.detach(), dx=xr.grad.clone(), dw=ref.weight.grad.clone(), db=ref.bias.grad.clone())
+    # reference B: operands rounded to bf16 where the kernel rounds them (x and W for fwd; dy and W for dgrad; x and dy for wgrad)
+    with torch.no_grad():
+        refq = icocnn_ref.IcoConvS2S(cin, cout, stride, True, level, cm)
+        refq.load_state_dict(ref.state_dict())
+        refq.weight.copy_(_bf16_round(ref.weight))
+    xq = _bf16_round(x).requires_grad_(True)
+    yq = refq(xq)
+    yq.backward(_bf16_round(gy))
+    xc = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    yc = mod(xc)
+    yc.backward(gy.cuda())
+    torch.cuda.synchronize()
+
+    def rel(a, b):
+        return ((a.detach().cpu() - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+    assert rel(yc, full['y']) < 2e-2 and rel(yc, yq.detach()) < 2e-3, ('fwd', rel(yc, full['y']), rel(yc, yq.detach()))
+    assert rel(xc.grad, full['dx']) < 2e-2 and rel(xc.grad, xq.grad) < 2e-3, ('dgrad', rel(xc.grad, full['dx']), rel(xc.grad, xq.grad))
+    assert rel(mod.weight.grad, full['dw']) < 2e-2 and rel(mod.weight.grad, refq.weight.grad) < 2e-3, \
+        ('wgrad', rel(mod.weight.grad, full['dw']), rel(mod.weight.grad, refq.weight.grad))
+    assert rel(mod.bias.grad, full['db']) < 1e-4
