@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Headline benchmark: ico2ico training meshes/s at I5, batch 36 per GPU (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W          # ours (one process per GPU under torchrun for N > 1)
+    python bench.py --impl reference ...                   # the reference's CPU path (oracle port) on the host cores
+
+One step = forward + P2P loss + backward + gradient all-reduce + Adam step of the reference's
+ico2ico graph (models.py:219-232) on one synthetic batch.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_MESH = {('ico2ico', 5): 31.4e9, ('ico2ico_vae', 5): 35.3e9, ('ico2ico', 6): 125.5e9}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--model', default='ico2ico', choices=['ico2ico', 'ico2ico_vae'])
+    ap.add_argument('--level', type=int, default=5)
+    ap.add_argument('--batch', type=int, default=None, help='per-GPU batch (default 36 at I5, 16 at I6)')
+    ap.add_argument('--conv-impl', default='auto', choices=['auto', 'simt', 'tc'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-kernel-table', action='store_true')
+    ap.add_argument('--cpu-batch', type=int, default=4)
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        mhz, mx, reasons, pw = [], None, set(), []
+        for r in self.rows:
+            try:
+                mhz.append(float(r[0])); mx = float(r[1]); pw.append(float(r[2]))
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                pass
+        busy = [m for m, p in zip(mhz, pw) if p > 250] or mhz
+        return {'sm_mhz': statistics.median(busy) if busy else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'power_w_max': max(pw) if pw else None, 'samples': len(mhz)}
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_step_time(model_name, level, batch, steps, warmup):
+    """The reference's CPU path: models.<name> graph over the oracle icocnn port + losses (fp32, all host threads)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import oracle_models as om
+    from geniconet_b200 import models as gm, data
+    params = gm.default_params(model_name, level)
+    torch.manual_seed(0)
+    model = om.build_oracle_model(model_name, params)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    x, tgt = data.synthetic_batch(level, 0, batch)
+    f = (params['ico']['factor_pos'], params['ico']['factor_nor'], params['ico']['factor_lap'])
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        out = model(x)
+        if model_name == 'ico2ico_vae':
+            rec, mu, lv = out
+            loss = om.ref_p2p_loss(level, rec, tgt, *f)[0] + om.ref_kld(mu, lv)
+        else:
+            loss = om.ref_p2p_loss(level, out, tgt, *f)[0]
+        loss.backward()
+        opt.step()
+        float(loss)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return statistics.median(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    import torch
+    batch = args.cpu_batch
+    steps = max(1, min(args.steps, 5))
+    warmup = max(1, min(args.warmup, 2))
+    t, threads = cpu_reference_step_time(args.model, args.level, batch, steps, warmup)
+    val = batch / t
+    B = args.batch or (36 if args.level == 5 else 16)
+    line = {'impl': 'reference', 'metric': 'train_meshes_per_sec', 'value': val, 'unit': 'meshes/s', 'n_gpus': args.gpus,
+            'steps': steps, 'warmup': warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': '%s I%d train step (fwd+loss+bwd+Adam), batch %d/GPU' % (args.model, args.level, B)},
+            'cpu_baseline': {'value': val, 'unit': 'meshes/s', 'cores': threads, 'kind': 'port',
+                             'sample': 'batch %d per step, median of %d steps after %d warm-up; oracle port of icocnn under the '
+                                       'reference graph, PyTorch CPU (oneDNN), fp32' % (batch, steps, warmup)},
+            'e2e': {'value': val, 'unit': 'meshes/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- ours
+def kernel_table(model, B, level, peaks, steps=5):
+    """Per-layer CUDA-event timings of the hex-conv kernels through the C ABI on activations of the real shapes.
+
+    Every timed launch works on tensors far larger than nothing-in-L2 can explain only when
+    input+output > L2 (126 MB); the `l2` column says which layers that holds for.
+    """
+    import torch
+    from geniconet_b200 import _lib
+    from geniconet_b200.ico_conv import IcoConvS2S, get_plan
+    rows = []
+    seen = {}
+    for name, m in model.named_modules():
+        if not isinstance(m, IcoConvS2S) or m.in_features % 64 or m.out_features % 64:
+            continue
+        key = (m.in_features, m.out_features, m.stride, m.subdivisions)
+        if key in seen:
+            seen[key]['count'] += 1
+            continue
+        n = 2 ** m.subdivisions
+        Pin, Pout = 10 * 4 ** m.subdivisions, 10 * 4 ** m.subdivisions // (m.stride ** 2)
+        x = torch.randn(B, 5 * n, 2 * n, m.in_features, device='cuda').permute(0, 3, 1, 2)
+        dy = torch.randn(B, 5 * n // m.stride, 2 * n // m.stride, m.out_features, device='cuda').permute(0, 3, 1, 2)
+        y = torch.empty_like(dy)
+        dx = torch.empty_like(x)
+        dW = torch.empty(m.out_features, m.in_features, 7, device='cuda')
+        db = torch.empty(m.out_features, device='cuda')
+        ws = torch.empty(_lib.lib.gin_hexconv_wgrad_ws_bytes(m.in_features, m.out_features), dtype=torch.uint8, device='cuda')
+        plan = get_plan(_lib.PLAN_HEXCONV, m.subdivisions, m.stride, m.corner_mode, 'cuda')
+        packed = m._packed_weights(m.weight)
+        st = torch.cuda.current_stream().cuda_stream
+        Ci, Co = m.in_features, m.out_features
+        sb, sp, sc = Pin * Ci, Ci, 1
+
+        def fwd():
+            _lib.check(_lib.lib.gin_hexconv_fwd(plan.host_ptr, plan.dev_ptr, x.data_ptr(), sb, sp, sc, packed.data_ptr(), m.bias.data_ptr(),
+                                                y.data_ptr(), B, Ci, Co, m.impl, st))
+
+        def dgrad():
+            _lib.check(_lib.lib.gin_hexconv_dgrad(plan.host_ptr, plan.dev_ptr, dy.data_ptr(), packed.data_ptr(), dx.data_ptr(), B, Ci, Co, m.impl, st))
+
+        def wgrad():
+            _lib.check(_lib.lib.gin_hexconv_wgrad(plan.host_ptr, plan.dev_ptr, x.data_ptr(), sb, sp, sc, dy.data_ptr(), dW.data_ptr(),
+                                                  db.data_ptr(), ws.data_ptr(), B, Ci, Co, m.impl, st))
+        flops = 2.0 * 7 * Ci * Co * Pout * B
+        act_bytes = 4.0 * B * (Ci * Pin + Co * Pout)
+        ent = {'layer': name, 'cin': Ci, 'cout': Co, 'stride': m.stride, 'level': m.subdivisions, 'count': 1,
+               'gflop': flops / 1e9, 'mbytes': act_bytes / 1e6, 'l2': 'exceeds' if act_bytes > 126e6 else 'fits'}
+        for tag, fn in (('fwd', fwd), ('dgrad', dgrad), ('wgrad', wgrad)):
+            for _ in range(2):
+                fn()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+            ev[0].record()
+            for i in range(steps):
+                fn()
+                ev[i + 1].record()
+            torch.cuda.synchronize()
+            ms = statistics.median(ev[i].elapsed_time(ev[i + 1]) for i in range(steps))
+            ent[tag + '_us'] = ms * 1e3
+            ent[tag + '_tflops'] = flops / (ms * 1e-3) / 1e12
+            ent[tag + '_gbs'] = act_bytes / (ms * 1e-3) / 1e9
+        seen[key] = ent
+        rows.append(ent)
+    return rows
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from geniconet_b200 import _lib, models as gm, losses, data
+    from geniconet_b200.dp import GradBuckets, shard_sample_ids, broadcast_parameters
+    from geniconet_b200.ico_conv import set_impl
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- geniconet_b200 has no CPU path')
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    B = args.batch or (36 if args.level == 5 else 16)
+    params = gm.default_params(args.model, args.level)
+    torch.manual_seed(0)
+    model = getattr(gm, args.model)(params).cuda()
+    set_impl(model, args.conv_impl)
+    if world > 1:
+        broadcast_parameters(model)
+    f = (params['ico']['factor_pos'], params['ico']['factor_nor'], params['ico']['factor_lap'])
+    crit = losses.P2PKLD_Loss(args.level, *f, 1.0) if args.model == 'ico2ico_vae' else losses.P2P_Loss(args.level, *f)
+    buckets = GradBuckets(model.parameters(), world)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+
+    # one synthetic shard per rank, staged in pinned host memory
+    ids = shard_sample_ids(0, rank, world, B)
+    xs, ts = zip(*(data.synthetic_mesh(args.level, i) for i in ids))
+    x_host, t_host = torch.stack(xs).pin_memory(), torch.stack(ts).pin_memory()
+    x_dev, t_dev = x_host.cuda(), t_host.cuda()
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step(x, t):
+        buckets.reset()
+        loss = crit(model(x), t)
+        loss.backward()
+        buckets.finish()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        last = step(x_dev, t_dev)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = _lib.launch_count()
+    ms_total = timed(lambda: step(x_dev, t_dev), args.steps)
+    launches = _lib.launch_count() - l0
+    ms_step = ms_total / args.steps
+
+    def e2e_step():
+        xd = x_host.to('cuda', non_blocking=True)
+        td = t_host.to('cuda', non_blocking=True)
+        loss = step(xd, td)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=False)
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    clk = clocks.stop() if rank == 0 else None
+    final_loss = float(last)
+
+    table, roof = None, None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        hbm = peaks.get('hbm_gbs', 6650.0)
+        tf_burst = peaks.get('bf16_tflops', 1590.0)
+        src = 'measured' if peaks else 'fallback'
+        if not args.no_kernel_table:
+            table = kernel_table(model, B, args.level, peaks)
+            # dominant kernel = largest share of the step among (layer, pass) entries
+            best = None
+            for r in table:
+                for tag in ('fwd', 'dgrad', 'wgrad'):
+                    share = r[tag + '_us'] * r['count']
+                    if best is None or share > best[0]:
+                        best = (share, r, tag)
+            _, r, tag = best
+            t_s = r[tag + '_us'] * 1e-6
+            ai = r['gflop'] * 1e9 / (r['mbytes'] * 1e6)
+            ridge = tf_burst * 1e12 / (hbm * 1e9)
+            if ai >= ridge:
+                roof = {'bound': 'tensor', 'achieved': r['gflop'] / 1e3 / t_s, 'peak': tf_burst, 'unit': 'TFLOP/s'}
+            else:
+                roof = {'bound': 'hbm', 'achieved': r['mbytes'] / 1e3 / t_s, 'peak': hbm, 'unit': 'GB/s'}
+            roof['frac'] = roof['achieved'] / roof['peak']
+            roof['traffic'] = None
+            roof['kernel'] = 'hexconv %s %d->%d stride %d level %d (x%d per step)' % (tag, r['cin'], r['cout'], r['stride'], r['level'], r['count'])
+            roof['peak_source'] = src + ' (MEASURED_PEAKS.json burst figure: kernel timed alone)' if peaks else 'fallback 6650 GB/s / 1590 TFLOP/s'
+            roof['algorithmic'] = {'gflop_per_launch': r['gflop'], 'mbytes_per_launch': r['mbytes'], 'us_per_launch': r[tag + '_us']}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        t_cpu, threads = cpu_reference_step_time(args.model, args.level, args.cpu_batch, 3, 1)
+        cpu = {'value': args.cpu_batch / t_cpu, 'unit': 'meshes/s', 'cores': threads, 'kind': 'port',
+               'sample': 'batch %d train step (fwd+loss+bwd+Adam), median of 3 after 1 warm-up; oracle port of icocnn under the '
+                         'reference graph on PyTorch CPU fp32' % args.cpu_batch}
+    if rank == 0:
+        meshes = B * world
+        act_gb = 12.0 * B / 36 * (4 ** (args.level - 5))
+        line = {'metric': 'train_meshes_per_sec', 'value': meshes / (ms_step * 1e-3), 'unit': 'meshes/s', 'n_gpus': world,
+                'steps': args.steps, 'warmup': W, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'bf16 operands / f32 accumulate (tcgen05); f32 activations, BN, loss, Adam',
+                'data': 'synthetic',
+                'config': {'workload': '%s I%d train step (fwd+loss+bwd+allreduce+Adam), batch %d/GPU' % (args.model, args.level, B),
+                           'conv_impl': args.conv_impl, 'parallelism': 'dp%d' % world,
+                           'l2': 'no flush: one step streams ~%.0f GB of activations, far beyond the 126 MB L2' % act_gb},
+                'e2e': {'value': meshes / (ms_e2e * 1e-3), 'unit': 'meshes/s', 'ms_per_step': ms_e2e,
+                        'h2d_bytes_per_step': x_host.numel() * 4 + t_host.numel() * 4, 'd2h_bytes_per_step': 4},
+                'gpu_launches': int(launches), 'clocks': clk, 'loss': final_loss,
+                'tflops_algorithmic': FLOP_PER_MESH.get((args.model, args.level), 0) * meshes / (ms_step * 1e-3) / 1e12,
+                'roofline': roof, 'cpu_baseline': cpu}
+        if table is not None:
+            os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+            with open(os.path.join(ROOT, 'gpurun_out', 'kernel_table.json'), 'w') as fh:
+                json.dump(table, fh, indent=1)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

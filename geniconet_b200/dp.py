@@ -1,0 +1,96 @@
+"""Data-parallel training harness: one process per GPU, gradients averaged with NCCL.
+
+The reference is single-device (run.py:713); SURVEY 8e: the path shards over independent samples,
+BatchNorm statistics stay per replica, and the only exchange is one gradient all-reduce per step
+(4.63 M fp32 = 18.5 MB for ico2ico).  Gradients live in a few flat bucket buffers (param.grad are
+views into them); a bucket's all-reduce is launched from autograd hooks as soon as its last
+gradient of the step has been accumulated, so the exchange overlaps the rest of backward.
+"""
+import torch
+import torch.distributed as dist
+
+
+class GradBuckets:
+    def __init__(self, params, world_size, bucket_bytes=8 << 20, process_group=None):
+        self.world = int(world_size)
+        self.group = process_group
+        # reverse registration order ~ the order gradients become ready in backward
+        self.params = [p for p in params if p.requires_grad][::-1]
+        self.buckets = []          # (flat tensor, [params])
+        cur, cur_n = [], 0
+        for p in self.params:
+            cur.append(p)
+            cur_n += p.numel() * 4
+            if cur_n >= bucket_bytes:
+                self._seal(cur)
+                cur, cur_n = [], 0
+        if cur:
+            self._seal(cur)
+        self._pending = [0] * len(self.buckets)
+        self._handles = []
+        self._bucket_of = {}
+        for bi, (_, ps) in enumerate(self.buckets):
+            for p in ps:
+                self._bucket_of[p] = bi
+                if self.world > 1:
+                    p.register_post_accumulate_grad_hook(self._on_grad)
+        self.reset()
+
+    def _seal(self, ps):
+        n = sum(p.numel() for p in ps)
+        flat = torch.zeros(n, dtype=ps[0].dtype, device=ps[0].device)
+        off = 0
+        for p in ps:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.buckets.append((flat, list(ps)))
+
+    def reset(self):
+        """Zero the gradients (keeps the views) and re-arm the bucket counters; call before backward."""
+        for bi, (flat, ps) in enumerate(self.buckets):
+            flat.zero_()
+            self._pending[bi] = len(ps)
+        self._handles = []
+
+    def _on_grad(self, p):
+        bi = self._bucket_of[p]
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0:
+            self._launch(bi)
+
+    def _launch(self, bi):
+        flat = self.buckets[bi][0]
+        if dist.get_backend(self.group) == 'nccl':
+            h = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+            self._handles.append((h, None))
+        else:
+            h = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._handles.append((h, flat))
+
+    def finish(self):
+        """Wait for every bucket; call after backward and before optimizer.step."""
+        if self.world <= 1:
+            return
+        for bi, n in enumerate(self._pending):      # parameters that got no gradient this step
+            if n > 0:
+                self._pending[bi] = 0
+                self._launch(bi)
+        for h, flat in self._handles:
+            h.wait()
+            if flat is not None:
+                flat.div_(self.world)
+        self._handles = []
+
+    def total_bytes(self):
+        return sum(f.numel() * 4 for f, _ in self.buckets)
+
+
+def shard_sample_ids(step, rank, world, batch):
+    """Disjoint synthetic sample ids per rank: step*world*B + rank*B + i."""
+    first = step * world * batch + rank * batch
+    return list(range(first, first + batch))
+
+
+def broadcast_parameters(model, src=0, process_group=None):
+    for t in list(model.parameters()) + list(model.buffers()):
+        dist.broadcast(t.data, src=src, group=process_group)

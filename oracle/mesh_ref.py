@@ -38,7 +38,7 @@ def compute_adjacency_matrix_sparse(n_vertices, faces):
     e = torch.cat((e, e.flip(1)), dim=0)
     key = torch.unique(e[:, 0] * int(n_vertices) + e[:, 1])
     idx = torch.stack((key // int(n_vertices), key % int(n_vertices)))
-    return torch.sparse_coo_tensor(idx, torch.ones(idx.shape[1]), (int(n_vertices), int(n_vertices))).coalesce()
+    return torch.sparse_coo_tensor(idx, torch.ones(idx.shape[1]), (int(n_vertices), int(n_vertices)), check_invariants=False).coalesce()
 
 
 def compute_laplacian(vertices, adj):

@@ -1,0 +1,161 @@
+"""GPU parity of the whole graphs (run with -m gpu): ico2ico / ico2ico_vae through the CUDA layers vs the
+same graph over the CPU oracle layers, same weights, same inputs."""
+import pytest
+import torch
+
+import oracle_models as om
+
+pytestmark = pytest.mark.gpu
+
+
+def _grads(model):
+    return {k: p.grad.detach().cpu().clone() for k, p in model.named_parameters() if p.grad is not None}
+
+
+def _compare_grads(gc, gr, cos_min, what):
+    assert set(gc) == set(gr)
+    worst = 1.0
+    for k in gr:
+        a, b = gc[k].flatten().double(), gr[k].flatten().double()
+        if b.norm() < 1e-12:
+            continue
+        cos = (a @ b / (a.norm() * b.norm())).item()
+        worst = min(worst, cos)
+        assert cos >= cos_min, '%s: gradient cosine of %s = %.5f' % (what, k, cos)
+    return worst
+
+
+# Measured on B200 (tools/diag_parity.py, profiles/r01_parity_by_layer.txt): the fp32 CUDA-core path tracks the fp32
+# oracle to 4e-6 on activations and cosine 1.000000 on every gradient; the tcgen05 path rounds every conv operand to
+# bf16, which accumulates to 2e-2 on the output and, through 25 layers of backward at batch 2, to cosine 0.984 on the
+# first layer's weight gradient (0.996 at batch 8).  Tolerances below are those measurements with ~2x head-room.
+@pytest.mark.parametrize('impl,loss_tol,cos_min', [('simt', 1e-4, 0.9999), ('auto', 2e-2, 0.97)])
+def test_ico2ico_step_matches_oracle(impl, loss_tol, cos_min):
+    from geniconet_b200 import models as gm, losses, data
+    from geniconet_b200.ico_conv import set_impl
+    level, B = 5, 2
+    torch.backends.cudnn.allow_tf32 = False      # the stock 1x1 Conv2d head (models.py:151) would otherwise run in TF32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    params = gm.default_params('ico2ico', level)
+    ref = om.fill_params_deterministic(om.build_oracle_model('ico2ico', params))
+    mod = gm.ico2ico(params)
+    mod.load_state_dict(ref.state_dict())
+    mod = set_impl(mod.cuda(), impl)
+    x, tgt = data.synthetic_batch(level, 0, B)
+    out_r = ref(x)
+    loss_r, _ = om.ref_p2p_loss(level, out_r, tgt, 1., 0., 0.)
+    loss_r.backward()
+    crit = losses.P2P_Loss(level, 1., 0., 0.)
+    out_c = mod(x.cuda())
+    assert out_c.shape == out_r.shape
+    loss_c = crit(out_c, tgt.cuda())
+    loss_c.backward()
+    torch.cuda.synchronize()
+    assert abs(loss_c.item() - loss_r.item()) <= loss_tol * abs(loss_r.item()), (loss_c.item(), loss_r.item())
+    err = (out_c.detach().cpu() - out_r.detach()).abs().max().item()
+    assert err <= (2e-4 if impl == 'simt' else 5e-2), err
+    _compare_grads(_grads(mod), _grads(ref), cos_min, impl)
+
+
+def test_ico2ico_vae_step_matches_oracle():
+    from geniconet_b200 import models as gm, losses, data
+    from geniconet_b200.ico_conv import set_impl
+    from geniconet_b200 import reparam
+    level, B = 5, 2
+    torch.backends.cudnn.allow_tf32 = False
+    params = gm.default_params('ico2ico_vae', level)
+    ref = om.fill_params_deterministic(om.build_oracle_model('ico2ico_vae', params))
+    mod = gm.ico2ico_vae(params)
+    mod.load_state_dict(ref.state_dict())
+    mod = set_impl(mod.cuda(), 'simt')
+    x, tgt = data.synthetic_batch(level, 3, B)
+    # CUDA first: take its eps and feed the same noise to the oracle graph
+    eps_box = {}
+    orig = gm._reparameterize
+
+    def capture(mu, logvar):
+        z, eps = reparam.reparameterize(mu, logvar, seed=42, offset=1, return_eps=True)
+        eps_box['eps'] = eps.detach().cpu()
+        return z
+    gm._reparameterize = capture
+    try:
+        rec_c, mu_c, lv_c = mod(x.cuda())
+    finally:
+        gm._reparameterize = orig
+    crit = losses.P2PKLD_Loss(level, 0.6, 0.2, 0.2, 1.0)
+    loss_c = crit((rec_c, mu_c, lv_c), tgt.cuda())
+    loss_c.backward()
+    gm._reparameterize = lambda mu, lv: eps_box['eps'] * torch.exp(0.5 * lv) + mu
+    try:
+        rec_r, mu_r, lv_r = ref(x)
+    finally:
+        gm._reparameterize = orig
+    loss_r = om.ref_p2p_loss(level, rec_r, tgt, 0.6, 0.2, 0.2)[0] + om.ref_kld(mu_r, lv_r)
+    loss_r.backward()
+    torch.cuda.synchronize()
+    assert abs(loss_c.item() - loss_r.item()) <= 1e-3 * abs(loss_r.item()), (loss_c.item(), loss_r.item())
+    last = crit.get_last_losses()
+    assert abs(last[4] - loss_r.item()) <= 1e-3 * abs(loss_r.item())
+    _compare_grads(_grads(mod), _grads(ref), 0.999, 'vae')
+
+
+def test_reference_style_training_loop_decreases_loss():
+    """run.py:240-250 step semantics through the public API: 8 Adam steps on one batch reduce the loss."""
+    from geniconet_b200 import models as gm, losses, data
+    params = gm.default_params('ico2ico', 5)
+    torch.manual_seed(0)
+    model = gm.ico2ico(params).cuda()
+    crit = losses.P2P_Loss(5, 1., 0., 0.)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    x, tgt = data.synthetic_batch(5, 0, 4)
+    x, tgt = x.cuda(), tgt.cuda()
+    hist = []
+    for _ in range(8):
+        opt.zero_grad()
+        loss = crit(model(x), tgt)
+        loss.backward()
+        opt.step()
+        hist.append(crit.get_last_losses()[-1])
+    assert hist[-1] < 0.7 * hist[0], hist
+
+
+def test_cuda_path_reproduces_reference_golden():
+    """tests/golden/reference_over_oracle.json was produced by the reference's OWN models.py + losses.py (over the oracle
+    layers) in the build container; the CUDA path must land on the same loss, outputs and gradient norms."""
+    import json
+    import os
+    from geniconet_b200 import models as gm, losses
+    from geniconet_b200.ico_conv import set_impl
+    torch.backends.cudnn.allow_tf32 = False
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_over_oracle.json')))
+    g = gold['ico2ico']
+    gen = torch.Generator().manual_seed(g['input_seed'])
+    x = torch.randn(g['batch'], 3, 160, 64, generator=gen) * 0.3
+    tgt = torch.randn(g['batch'], 9, 10242, generator=gen) * 0.5
+    for impl, tol in (('simt', 1e-4), ('auto', 2e-2)):
+        mod = om.fill_params_deterministic(gm.ico2ico(gm.default_params('ico2ico')))
+        mod = set_impl(mod.cuda(), impl)
+        crit = losses.P2P_Loss(5, 1., 0., 0.)
+        y = mod(x.cuda())
+        loss = crit(y, tgt.cuda())
+        loss.backward()
+        assert abs(loss.item() - g['loss']) <= tol * abs(g['loss']), (impl, loss.item(), g['loss'])
+        f = y.detach().flatten().cpu()
+        samp = f[torch.linspace(0, f.numel() - 1, 64).long()]
+        assert (samp - torch.tensor(g['output_sample'])).abs().max().item() <= (2e-4 if impl == 'simt' else 5e-2)
+        last = crit.get_last_losses()
+        for a, b in zip(last, g['last_losses']):
+            assert abs(a - b) <= max(tol, 1e-4) * max(1.0, abs(b)), (impl, last, g['last_losses'])
+        for k, p in mod.named_parameters():
+            want = g['grad_norms'][k]
+            assert abs(p.grad.norm().item() - want) <= (1e-2 if impl == 'simt' else 0.25) * want + 1e-9, (impl, k)
+    # the loss kernels alone, all three terms live (losses.py:71-80)
+    g3 = gold['p2p_level3']
+    gen = torch.Generator().manual_seed(g3['input_seed'])
+    x3 = (torch.randn(g3['batch'], 3, 40, 16, generator=gen) * 0.3).cuda().requires_grad_(True)
+    t3 = (torch.randn(g3['batch'], 9, 642, generator=gen) * 0.5).cuda()
+    c3 = losses.P2P_Loss(3, 0.6, 0.2, 0.2)
+    l3 = c3(x3, t3)
+    l3.backward()
+    assert abs(l3.item() - g3['loss']) <= 1e-5 * abs(g3['loss'])
+    assert abs(x3.grad.norm().item() - g3['grad_norm']) <= 1e-4 * g3['grad_norm']

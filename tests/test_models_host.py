@@ -1,0 +1,142 @@
+"""Host-side logic that needs no GPU: model assembly mirrors the reference (state-dict keys and shapes), the golden
+fixture made from the reference's own models.py/losses.py over the oracle is reproduced by OUR graphs over the oracle
+layers, and the product refuses to run on the CPU."""
+import json
+import os
+
+import pytest
+import torch
+
+import oracle_models as om
+from geniconet_b200 import models as gm
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, 'golden', 'reference_over_oracle.json')))
+
+
+def _inputs(level, B, seed):
+    g = torch.Generator().manual_seed(seed)
+    n = 2 ** level
+    return (torch.randn(B, 3, 5 * n, 2 * n, generator=g) * 0.3, torch.randn(B, 9, 10 * 4 ** level + 2, generator=g) * 0.5)
+
+
+def _sample(t, k=64):
+    f = t.detach().flatten()
+    return f[torch.linspace(0, f.numel() - 1, k).long()]
+
+
+@pytest.mark.parametrize('name', ['ico2ico', 'ico2ico_vae'])
+def test_state_dict_matches_reference(name):
+    m = getattr(gm, name)(gm.default_params(name))
+    want = GOLD[name]['state_dict']
+    got = {k: list(v.shape) for k, v in m.state_dict().items()}
+    assert list(got) == list(want) and got == want
+    n_param = sum(p.numel() for p in m.parameters())
+    assert n_param == {'ico2ico': 4627715, 'ico2ico_vae': 6004739}[name]
+
+
+def test_split_models_share_keys():
+    p = gm.default_params('ico2ico')
+    full = set(gm.ico2ico(p).state_dict())
+    assert set(gm.ico2enc(p).state_dict()) | set(gm.enc2ico(p).state_dict()) == full
+    pv = gm.default_params('ico2ico_vae')
+    fullv = set(gm.ico2ico_vae(pv).state_dict())
+    assert set(gm.ico2enc_vae(pv).state_dict()) | set(gm.enc2ico_vae(pv).state_dict()) == fullv
+
+
+def test_our_graph_over_oracle_reproduces_reference_golden():
+    """reference models.py + losses.py over the oracle (golden)  ==  geniconet_b200.models over the oracle."""
+    g = GOLD['ico2ico']
+    x, tgt = _inputs(5, g['batch'], g['input_seed'])
+    m = om.fill_params_deterministic(om.build_oracle_model('ico2ico', gm.default_params('ico2ico')))
+    y = m(x)
+    loss, parts = om.ref_p2p_loss(5, y, tgt, 1., 0., 0.)
+    loss.backward()
+    assert abs(loss.item() - g['loss']) <= 1e-5 * abs(g['loss'])
+    assert torch.allclose(_sample(y), torch.tensor(g['output_sample']), rtol=1e-4, atol=1e-5)
+    for k, p in m.named_parameters():
+        assert abs(p.grad.norm().item() - g['grad_norms'][k]) <= 1e-3 * g['grad_norms'][k] + 1e-9, k
+    for a, b in zip(parts, g['last_losses'][:3]):
+        assert abs(a.item() - b) <= 1e-5 * max(1.0, abs(b))
+
+
+def test_vae_graph_over_oracle_reproduces_reference_golden():
+    g = GOLD['ico2ico_vae']
+    x, tgt = _inputs(5, g['batch'], g['input_seed'])
+    orig = gm._reparameterize
+    gm._reparameterize = lambda mu, lv: torch.randn_like(lv) * torch.exp(0.5 * lv) + mu      # models.py:89-92 on the CPU generator
+    try:
+        m = om.fill_params_deterministic(om.build_oracle_model('ico2ico_vae', gm.default_params('ico2ico_vae')))
+        torch.manual_seed(g['eps_seed'])
+        rec, mu, lv = m(x)
+    finally:
+        gm._reparameterize = orig
+    loss = om.ref_p2p_loss(5, rec, tgt, 0.6, 0.2, 0.2)[0] + om.ref_kld(mu, lv)
+    assert abs(loss.item() - g['loss']) <= 1e-5 * abs(g['loss'])
+    assert torch.allclose(_sample(mu), torch.tensor(g['mu_sample']), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(_sample(rec), torch.tensor(g['output_sample']), rtol=1e-4, atol=1e-5)
+
+
+def test_oracle_layers_reproduce_golden():
+    from oracle import icocnn_ref
+    for key, g in GOLD['layers'].items():
+        parts = key.split('_')
+        gen = torch.Generator().manual_seed(g['input_seed'])
+        if parts[0] == 'conv':
+            cin, cout, stride, level, cm = int(parts[1]), int(parts[2]), int(parts[3][1:]), int(parts[4][1:]), parts[5]
+            mod = om.fill_params_deterministic(icocnn_ref.IcoConvS2S(cin, cout, stride, True, level, cm), seed=5)
+            c = cin
+        else:
+            c, level, cm = int(parts[1]), int(parts[2][1:]), parts[3]
+            mod = icocnn_ref.IcoUpsampleS2S(c, level, cm)
+        n = 2 ** level
+        y = mod(torch.randn(2, c, 5 * n, 2 * n, generator=gen))
+        assert torch.allclose(_sample(y), torch.tensor(g['output_sample']), rtol=1e-5, atol=1e-6), key
+
+
+def test_reference_files_import_over_the_shim_packages():
+    """`import icocnn` / `import mesh` resolve to the B200 implementation; the reference's models.py imports unchanged."""
+    import icocnn.ico_conv
+    import icocnn.utils.ico_geometry as ig
+    import mesh.utils
+    from geniconet_b200.ico_conv import IcoConvS2S
+    assert icocnn.ico_conv.IcoConvS2S is IcoConvS2S
+    assert ig.get_ico_faces(5).max() + 1 == 10242 and ig.get_ico_faces(5).shape == (20480, 3)
+    ref_models = '/root/reference/models.py'
+    if os.path.exists(ref_models):                       # build container only
+        import importlib.util
+        spec = importlib.util.spec_from_file_location('_ref_models_over_product', ref_models)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        p = {'ico': {'corner_mode': 'average', 'subdivisions': 5}, 'ico2ico': {'model': 'residualS2S'}, 'model_name': 'ico2ico'}
+        m = mod.ico2ico(p)
+        assert isinstance(m.encoder[0], IcoConvS2S)
+        assert list(m.state_dict()) == list(GOLD['ico2ico']['state_dict'])
+
+
+def test_no_cpu_fallback():
+    from geniconet_b200 import losses
+    from geniconet_b200.ico_conv import IcoConvS2S, IcoUpsampleS2S
+    from geniconet_b200.reparam import reparameterize
+    with pytest.raises(RuntimeError):
+        IcoConvS2S(4, 4, 1, True, 2, 'average')(torch.zeros(1, 4, 20, 8))
+    with pytest.raises(RuntimeError):
+        IcoUpsampleS2S(4, 2, 'average')(torch.zeros(1, 4, 20, 8))
+    with pytest.raises(RuntimeError):
+        losses.P2P_Loss(2, 1., 0., 0.)(torch.zeros(1, 3, 20, 8), torch.zeros(1, 9, 162))
+    with pytest.raises(RuntimeError):
+        reparameterize(torch.zeros(4), torch.zeros(4))
+    with pytest.raises(RuntimeError):
+        gm.ico2ico(gm.default_params())(torch.zeros(1, 3, 160, 64))
+
+
+def test_synthetic_data_contract():
+    from geniconet_b200 import data
+    x, t = data.synthetic_mesh(3, 7)
+    assert tuple(x.shape) == (3, 40, 16) and tuple(t.shape) == (9, 642) and x.dtype == torch.float32
+    assert torch.equal(x.reshape(3, -1), t[:3, :-2])                       # data.py:67-68
+    assert t[:3].norm(dim=0).max() < 1.0
+    assert torch.allclose(t[3:6].norm(dim=0), torch.ones(642), atol=1e-5)  # unit normals, outward
+    assert (t[3:6] * t[:3]).sum(0).min() > 0
+    x2, _ = data.synthetic_mesh(3, 7)
+    assert torch.equal(x, x2)
