@@ -169,21 +169,33 @@ def kernel_table(model, B, level, peaks, steps=5):
         Ci, Co = m.in_features, m.out_features
         sb, sp, sc = Pin * Ci, Ci, 1
 
+        lvl_out = m.subdivisions - (1 if m.stride == 2 else 0)
+        xb = torch.empty(_lib.lib.gin_cast_bf16_bytes(B, m.subdivisions, Ci) // 2, dtype=torch.bfloat16, device='cuda')
+        dyb = torch.empty(_lib.lib.gin_cast_bf16_bytes(B, lvl_out, Co) // 2, dtype=torch.bfloat16, device='cuda')
+
+        def cast_x():
+            _lib.check(_lib.lib.gin_cast_bf16(plan.host_ptr, plan.dev_ptr, 0, x.data_ptr(), xb.data_ptr(), B, Ci, st))
+
+        def cast_dy():
+            _lib.check(_lib.lib.gin_cast_bf16(plan.host_ptr, plan.dev_ptr, 1, dy.data_ptr(), dyb.data_ptr(), B, Co, st))
+
         def fwd():
-            _lib.check(_lib.lib.gin_hexconv_fwd(plan.host_ptr, plan.dev_ptr, x.data_ptr(), sb, sp, sc, packed.data_ptr(), m.bias.data_ptr(),
-                                                y.data_ptr(), B, Ci, Co, m.impl, st))
+            _lib.check(_lib.lib.gin_hexconv_fwd_bf16(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), packed.data_ptr(), m.bias.data_ptr(),
+                                                     y.data_ptr(), B, Ci, Co, st))
 
         def dgrad():
-            _lib.check(_lib.lib.gin_hexconv_dgrad(plan.host_ptr, plan.dev_ptr, dy.data_ptr(), packed.data_ptr(), dx.data_ptr(), B, Ci, Co, m.impl, st))
+            _lib.check(_lib.lib.gin_hexconv_dgrad_bf16(plan.host_ptr, plan.dev_ptr, dyb.data_ptr(), packed.data_ptr(), dx.data_ptr(), B, Ci, Co, st))
 
         def wgrad():
-            _lib.check(_lib.lib.gin_hexconv_wgrad(plan.host_ptr, plan.dev_ptr, x.data_ptr(), sb, sp, sc, dy.data_ptr(), dW.data_ptr(),
-                                                  db.data_ptr(), ws.data_ptr(), B, Ci, Co, m.impl, st))
+            _lib.check(_lib.lib.gin_hexconv_wgrad_bf16(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), dyb.data_ptr(), dy.data_ptr(), dW.data_ptr(),
+                                                       db.data_ptr(), ws.data_ptr(), B, Ci, Co, st))
+        cast_x()
+        cast_dy()
         flops = 2.0 * 7 * Ci * Co * Pout * B
         act_bytes = 4.0 * B * (Ci * Pin + Co * Pout)
         ent = {'layer': name, 'cin': Ci, 'cout': Co, 'stride': m.stride, 'level': m.subdivisions, 'count': 1,
                'gflop': flops / 1e9, 'mbytes': act_bytes / 1e6, 'l2': 'exceeds' if act_bytes > 126e6 else 'fits'}
-        for tag, fn in (('fwd', fwd), ('dgrad', dgrad), ('wgrad', wgrad)):
+        for tag, fn in (('fwd', fwd), ('dgrad', dgrad), ('wgrad', wgrad), ('cast_x', cast_x), ('cast_dy', cast_dy)):
             for _ in range(2):
                 fn()
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]

@@ -6,12 +6,15 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/geniconet_b200.h"
 #include "gin_common.cuh"
 #include "gin_gemm_simt.cuh"
 #include "gin_gemm_tc.cuh"
+#include "gin_gemm_tcp.cuh"
+#include "gin_wgrad_tcp.cuh"
 #include "gin_loss.cuh"
 #include "gin_resample.cuh"
 
@@ -57,32 +60,52 @@ int grid_for(long long work_items, int threads, int max_waves = 8) {
   return (int)(blocks < cap ? blocks : cap);
 }
 
-bool use_tc(int impl, int K, int N) {
-  if (impl == GIN_IMPL_SIMT) return false;
-  const bool ok = gin::tc_supported(K, N);
-  return impl == GIN_IMPL_TC ? ok : ok;
+// GIN_TC_MODE=gather forces the gather-mode tcgen05 kernels (A/B experiments); default is patch mode where a plan has it
+bool patch_mode_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GIN_TC_MODE"); v = (e && strcmp(e, "gather") == 0) ? 0 : 1; }
+  return v == 1;
 }
 
-int run_gather_gemm(const int32_t* plan_dev, const GinSide& side, int group, GinSrcView X, const char* packed, int B, int K,
-                    int N, bool dgrad, const float* bias, float* Y, int impl, cudaStream_t st, int Cin, int Cout) {
+// fp32 CUDA-core path
+int run_gather_gemm_simt(const int32_t* plan_dev, const GinSide& side, int group, GinSrcView X, const char* packed, int B, int K, int N,
+                         bool dgrad, const float* bias, float* Y, cudaStream_t st, int Cin, int Cout) {
   const int groups = (B + group - 1) / group;
   const long long ntiles = (long long)groups * side.ntiles;
   if (ntiles <= 0) return GIN_OK;
-  if (impl == GIN_IMPL_TC && !gin::tc_supported(K, N))
-    return fail(GIN_ERR_UNSUPPORTED, "tcgen05 path needs K %% 64 == 0 and N %% 64 == 0 (K=%d N=%d)", K, N);
-  if (use_tc(impl, K, N) && X.sc == 1 && X.sp == K) {
-    const void* wb = packed + (dgrad ? packed_off_bd(Cin, Cout) : packed_off_bf(Cin, Cout));
-    int rc = gin::launch_gather_gemm_tc(plan_dev, side, group, X.p, wb, bias, Y, B, K, N, (int)ntiles, st);
-    if (rc != GIN_OK) return fail(rc, "tcgen05 gather-GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return GIN_OK;
-  }
   const float* W = reinterpret_cast<const float*>(packed + (dgrad ? packed_off_wd(Cin, Cout) : packed_off_wf(Cin, Cout)));
   dim3 grid((unsigned)ntiles, (unsigned)((N + gin::SIMT_TN - 1) / gin::SIMT_TN));
   const bool vec = X.sc == 1 && (K % 4 == 0) && (X.sp % 4 == 0) && (X.sb % 4 == 0) && ((uintptr_t)X.p % 16 == 0);
   if (vec) gin::gather_gemm_simt_kernel<true><<<grid, gin::SIMT_THREADS, 0, st>>>(plan_dev, side, X, W, bias, Y, group, B, K, N);
   else gin::gather_gemm_simt_kernel<false><<<grid, gin::SIMT_THREADS, 0, st>>>(plan_dev, side, X, W, bias, Y, group, B, K, N);
   return check_launch("gather_gemm_simt");
+}
+
+// tcgen05 path on the bf16 activation copy: patch mode for stride 1, gather mode otherwise
+int run_gemm_tc(const int32_t* plan_dev, const GinConvPlanHdr* h, const void* Xb, const char* packed, int B, bool dgrad,
+                const float* bias, float* Y, cudaStream_t st, int Cin, int Cout) {
+  const GinSide& side = dgrad ? h->dg : h->fwd;
+  const int K = dgrad ? Cout : Cin, N = dgrad ? Cin : Cout;
+  const int groups = (B + h->group - 1) / h->group;
+  if (!gin::tc_supported(K, N)) return fail(GIN_ERR_UNSUPPORTED, "tcgen05 path needs channel counts that are multiples of 64 (K=%d N=%d)", K, N);
+  const void* wb = packed + (dgrad ? packed_off_bd(Cin, Cout) : packed_off_bf(Cin, Cout));
+  const GinPSide& ps = dgrad ? h->pdg : h->pfwd;
+  int rc;
+  if (h->stride == 1 && patch_mode_enabled() && gin::tcp_supported(ps, K, N)) {
+    rc = gin::launch_patch_gemm_tc(plan_dev, ps, h->group, side.P_dst, Xb, wb, bias, Y, B, K, N, dgrad ? 1 : 0, st);
+    if (rc != GIN_OK) return fail(rc, "tcgen05 patch-GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (dgrad && h->dgx.ntiles > 0) {       // cross-seam and pole entries, accumulated on top
+      rc = gin::launch_gather_gemm_tc(plan_dev, h->dgx, h->group, Xb, wb, nullptr, Y, B, K, N, groups * h->dgx.ntiles, st, 2);
+      if (rc != GIN_OK) return fail(rc, "tcgen05 seam pass launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    return GIN_OK;
+  }
+  rc = gin::launch_gather_gemm_tc(plan_dev, side, h->group, Xb, wb, bias, Y, B, K, N, groups * side.ntiles, st);
+  if (rc != GIN_OK) return fail(rc, "tcgen05 gather-GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return GIN_OK;
 }
 
 }  // namespace
@@ -127,9 +150,10 @@ int gin_hexconv_fwd(const void* plan_host, const void* plan_dev, const float* x,
   int rc = conv_hdr(plan_host, plan_dev, &h);
   if (rc) return rc;
   if (B == 0) return GIN_OK;
+  if (impl == GIN_IMPL_TC) return fail(GIN_ERR_UNSUPPORTED, "the tcgen05 path reads bf16: use gin_cast_bf16 + gin_hexconv_fwd_bf16");
   GinSrcView X{x, (long long)sb, (long long)sp, (long long)sc, h->fwd.P_src};
-  return run_gather_gemm(plan_words(plan_dev), h->fwd, h->group, X, reinterpret_cast<const char*>(packed), B, Cin, Cout, false,
-                         bias, y, impl, st, Cin, Cout);
+  return run_gather_gemm_simt(plan_words(plan_dev), h->fwd, h->group, X, reinterpret_cast<const char*>(packed), B, Cin, Cout, false,
+                              bias, y, st, Cin, Cout);
 }
 
 int gin_hexconv_dgrad(const void* plan_host, const void* plan_dev, const float* dy, const void* packed, float* dx, int B, int Cin, int Cout, int impl,
@@ -140,9 +164,10 @@ int gin_hexconv_dgrad(const void* plan_host, const void* plan_dev, const float* 
   int rc = conv_hdr(plan_host, plan_dev, &h);
   if (rc) return rc;
   if (B == 0) return GIN_OK;
+  if (impl == GIN_IMPL_TC) return fail(GIN_ERR_UNSUPPORTED, "the tcgen05 path reads bf16: use gin_cast_bf16 + gin_hexconv_dgrad_bf16");
   GinSrcView X{dy, (long long)h->dg.P_src * Cout, (long long)Cout, 1, h->dg.P_src};
-  return run_gather_gemm(plan_words(plan_dev), h->dg, h->group, X, reinterpret_cast<const char*>(packed), B, Cout, Cin, true,
-                         nullptr, dx, impl, st, Cin, Cout);
+  return run_gather_gemm_simt(plan_words(plan_dev), h->dg, h->group, X, reinterpret_cast<const char*>(packed), B, Cout, Cin, true,
+                              nullptr, dx, st, Cin, Cout);
 }
 
 size_t gin_hexconv_wgrad_ws_bytes(int Cin, int Cout) {
@@ -150,28 +175,28 @@ size_t gin_hexconv_wgrad_ws_bytes(int Cin, int Cout) {
   return (size_t)28 * Cin * Cout;
 }
 
-int gin_hexconv_wgrad(const void* plan_host, const void* plan_dev, const float* x, int64_t sb, int64_t sp, int64_t sc, const float* dy, float* dW,
-                      float* db, void* ws, int B, int Cin, int Cout, int impl, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  if (!x || !dy || !dW || !ws || B < 0 || Cin <= 0 || Cout <= 0) return fail(GIN_ERR_ARG, "gin_hexconv_wgrad: bad argument");
-  const GinConvPlanHdr* h;
-  int rc = conv_hdr(plan_host, plan_dev, &h);
-  if (rc) return rc;
+static int wgrad_common(const GinConvPlanHdr* h, const void* plan_dev, const float* x, int64_t sb, int64_t sp, int64_t sc, const void* xb,
+                        const void* dyb, const float* dy, float* dW, float* db, void* ws, int B, int Cin, int Cout, cudaStream_t st) {
   float* dWp = reinterpret_cast<float*>(ws);
+  int rc;
   if (cudaMemsetAsync(dWp, 0, (size_t)28 * Cin * Cout, st) != cudaSuccess) return fail(GIN_ERR_CUDA, "memset failed");
   if (db && cudaMemsetAsync(db, 0, (size_t)4 * Cout, st) != cudaSuccess) return fail(GIN_ERR_CUDA, "memset failed");
   if (B > 0) {
     const GinSide& side = h->fwd;
     const int groups = (B + h->group - 1) / h->group;
     const int total_tiles = groups * side.ntiles;
-    GinSrcView X{x, (long long)sb, (long long)sp, (long long)sc, side.P_src};
-    if (impl == GIN_IMPL_TC && !gin::tc_wgrad_supported(Cin, Cout))
-      return fail(GIN_ERR_UNSUPPORTED, "tcgen05 wgrad needs Cin %% 64 == 0 and Cout %% 64 == 0");
-    if (impl != GIN_IMPL_SIMT && gin::tc_wgrad_supported(Cin, Cout) && sc == 1 && sp == Cin) {
-      rc = gin::launch_wgrad_tc(plan_words(plan_dev), side, h->group, x, dy, dWp, B, Cin, Cout, total_tiles, st);
-      if (rc != GIN_OK) return fail(rc, "tcgen05 wgrad launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (xb) {
+      if (!gin::tc_wgrad_supported(Cin, Cout)) return fail(GIN_ERR_UNSUPPORTED, "tcgen05 wgrad needs Cin %% 64 == 0 and Cout %% 64 == 0");
+      if (h->stride == 1 && patch_mode_enabled() && gin::tcwp_supported(h->pfwd, Cin, Cout)) {
+        rc = gin::launch_wgrad_patch_tc(plan_words(plan_dev), h->pfwd, h->group, side.P_dst, xb, dyb, dWp, B, Cin, Cout, st);
+        if (rc != GIN_OK) return fail(rc, "tcgen05 patch wgrad launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      } else {
+        rc = gin::launch_wgrad_tc(plan_words(plan_dev), side, h->group, xb, dyb, dWp, B, Cin, Cout, total_tiles, st);
+        if (rc != GIN_OK) return fail(rc, "tcgen05 wgrad launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      }
       g_launches.fetch_add(1, std::memory_order_relaxed);
     } else {
+      GinSrcView X{x, (long long)sb, (long long)sp, (long long)sc, side.P_src};
       const int nblk = ((Cin + gin::WG_TC - 1) / gin::WG_TC) * ((Cout + gin::WG_TC - 1) / gin::WG_TC);
       int slices = (148 * 4 + 7 * nblk - 1) / (7 * nblk);
       if (slices > total_tiles) slices = total_tiles;
@@ -187,7 +212,7 @@ int gin_hexconv_wgrad(const void* plan_host, const void* plan_dev, const float* 
     if (db) {
       const long long rows = (long long)B * side.P_dst;
       int ctas = (int)((rows + 255) / 256);
-      if (ctas > 148 * 4) ctas = 148 * 4;
+      if (ctas > 148 * 2) ctas = 148 * 2;
       const int rows_per_cta = (int)((rows + ctas - 1) / ctas);
       gin::bias_grad_kernel<<<ctas, 256, 0, st>>>(dy, db, rows, Cout, rows_per_cta);
       rc = check_launch("bias_grad");
@@ -196,6 +221,65 @@ int gin_hexconv_wgrad(const void* plan_host, const void* plan_dev, const float* 
   }
   gin::unpack_wgrad_kernel<<<grid_for(7LL * Cin * Cout, 256), 256, 0, st>>>(dWp, dW, Cin, Cout);
   return check_launch("unpack_wgrad");
+}
+
+int gin_hexconv_wgrad(const void* plan_host, const void* plan_dev, const float* x, int64_t sb, int64_t sp, int64_t sc, const float* dy, float* dW,
+                      float* db, void* ws, int B, int Cin, int Cout, int impl, void* stream) {
+  if (!x || !dy || !dW || !ws || B < 0 || Cin <= 0 || Cout <= 0) return fail(GIN_ERR_ARG, "gin_hexconv_wgrad: bad argument");
+  if (impl == GIN_IMPL_TC) return fail(GIN_ERR_UNSUPPORTED, "the tcgen05 path reads bf16: use gin_cast_bf16 + gin_hexconv_wgrad_bf16");
+  const GinConvPlanHdr* h;
+  int rc = conv_hdr(plan_host, plan_dev, &h);
+  if (rc) return rc;
+  return wgrad_common(h, plan_dev, x, sb, sp, sc, nullptr, nullptr, dy, dW, db, ws, B, Cin, Cout, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ bf16 (tcgen05) entry points
+size_t gin_cast_bf16_bytes(int B, int level, int C) {
+  if (B < 0 || level < 0 || level > 9 || C <= 0) return 0;
+  return ((size_t)B * (10 << (2 * level)) + 2 * (size_t)B) * C * 2;
+}
+
+int gin_cast_bf16(const void* plan_host, const void* plan_dev, int which, const float* x, void* xb, int B, int C, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!x || !xb || B < 0 || C <= 0 || (C & 7) || (which != 0 && which != 1)) return fail(GIN_ERR_ARG, "gin_cast_bf16: bad argument (C must be a multiple of 8)");
+  const GinConvPlanHdr* h;
+  int rc = conv_hdr(plan_host, plan_dev, &h);
+  if (rc) return rc;
+  if (B == 0) return GIN_OK;
+  const GinSide& side = which == 0 ? h->fwd : h->dg;      // the gathered tensor of the forward / of dgrad
+  const long long n8 = (long long)B * side.P_src * (C / 8) + 2LL * B * (C / 8);
+  gin::cast_bf16_kernel<<<grid_for(n8, 256, 16), 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(xb), plan_words(plan_dev) + side.ring_off,
+                                                                B, side.P_src, C);
+  return check_launch("cast_bf16");
+}
+
+int gin_hexconv_fwd_bf16(const void* plan_host, const void* plan_dev, const void* xb, const void* packed, const float* bias, float* y, int B,
+                         int Cin, int Cout, void* stream) {
+  if (!xb || !packed || !y || B < 0 || Cin <= 0 || Cout <= 0) return fail(GIN_ERR_ARG, "gin_hexconv_fwd_bf16: bad argument");
+  const GinConvPlanHdr* h;
+  int rc = conv_hdr(plan_host, plan_dev, &h);
+  if (rc) return rc;
+  if (B == 0) return GIN_OK;
+  return run_gemm_tc(plan_words(plan_dev), h, xb, reinterpret_cast<const char*>(packed), B, false, bias, y, (cudaStream_t)stream, Cin, Cout);
+}
+
+int gin_hexconv_dgrad_bf16(const void* plan_host, const void* plan_dev, const void* dyb, const void* packed, float* dx, int B, int Cin, int Cout,
+                           void* stream) {
+  if (!dyb || !packed || !dx || B < 0 || Cin <= 0 || Cout <= 0) return fail(GIN_ERR_ARG, "gin_hexconv_dgrad_bf16: bad argument");
+  const GinConvPlanHdr* h;
+  int rc = conv_hdr(plan_host, plan_dev, &h);
+  if (rc) return rc;
+  if (B == 0) return GIN_OK;
+  return run_gemm_tc(plan_words(plan_dev), h, dyb, reinterpret_cast<const char*>(packed), B, true, nullptr, dx, (cudaStream_t)stream, Cin, Cout);
+}
+
+int gin_hexconv_wgrad_bf16(const void* plan_host, const void* plan_dev, const void* xb, const void* dyb, const float* dy, float* dW, float* db,
+                           void* ws, int B, int Cin, int Cout, void* stream) {
+  if (!xb || !dyb || !dW || !ws || (db && !dy) || B < 0 || Cin <= 0 || Cout <= 0) return fail(GIN_ERR_ARG, "gin_hexconv_wgrad_bf16: bad argument");
+  const GinConvPlanHdr* h;
+  int rc = conv_hdr(plan_host, plan_dev, &h);
+  if (rc) return rc;
+  return wgrad_common(h, plan_dev, nullptr, 0, 0, 0, xb, dyb, dy, dW, db, ws, B, Cin, Cout, (cudaStream_t)stream);
 }
 
 static int up_hdr(const void* plan_host, const void* plan_dev, const GinUpPlanHdr** out) {

@@ -18,8 +18,8 @@ __host__ GIN_DEVINL const int32_t* plan_words(const void* plan) { return reinter
 // Packed-weight blob layout (gin_hexconv_pack_weights), offsets in bytes from the start:
 //   [0]                      float wf[7][Cin][Cout]   forward   B operand (SIMT)
 //   [28*Cin*Cout]            float wd[7][Cout][Cin]   dgrad     B operand (SIMT)
-//   [56*Cin*Cout]            bf16  bf[7][Cout][Cin]   forward   B operand (tcgen05, K-major rows = Cout)
-//   [70*Cin*Cout]            bf16  bd[7][Cin][Cout]   dgrad     B operand (tcgen05, K-major rows = Cin)
+//   [56*Cin*Cout]            bf16  bf[7][Cin/64][Cout][64]  forward B tiles (tcgen05), pre-swizzled smem image
+//   [70*Cin*Cout]            bf16  bd[7][Cout/64][Cin][64]  dgrad   B tiles (tcgen05), pre-swizzled smem image
 GIN_DEVINL __host__ size_t packed_off_wf(int, int) { return 0; }
 GIN_DEVINL __host__ size_t packed_off_wd(int Cin, int Cout) { return (size_t)28 * Cin * Cout; }
 GIN_DEVINL __host__ size_t packed_off_bf(int Cin, int Cout) { return (size_t)56 * Cin * Cout; }

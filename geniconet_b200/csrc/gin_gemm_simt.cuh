@@ -290,8 +290,18 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
     unsigned short h = (unsigned short)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);  // round-to-nearest-even bf16
     wf[((size_t)t * Cin + ci) * Cout + co] = v;
     wd[((size_t)t * Cout + co) * Cin + ci] = v;
-    bf[((size_t)t * Cout + co) * Cin + ci] = h;
-    bd[((size_t)t * Cin + ci) * Cout + co] = h;
+    // tcgen05 B operand tiles, stored exactly as the smem image: [tap][k/64][n][64] with the 16-byte chunk index
+    // XOR-swizzled by (n & 7), so one contiguous bulk copy of N_TILE*128 bytes lands a ready SWIZZLE_128B tile.
+    if ((Cin & 63) == 0 && (Cout & 63) == 0) {
+      {  // forward: n = co, k = ci
+        const int kc = ci >> 6, c = (ci >> 3) & 7, e = ci & 7;
+        bf[((((size_t)t * (Cin >> 6) + kc) * Cout + co) << 6) + (((c ^ (co & 7)) << 3) | e)] = h;
+      }
+      {  // dgrad: n = ci, k = co
+        const int kc = co >> 6, c = (co >> 3) & 7, e = co & 7;
+        bd[((((size_t)t * (Cout >> 6) + kc) * Cin + ci) << 6) + (((c ^ (ci & 7)) << 3) | e)] = h;
+      }
+    }
   }
 }
 

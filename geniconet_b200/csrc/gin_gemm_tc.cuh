@@ -110,15 +110,45 @@ GIN_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
 // byte offset of 16-byte chunk `c` of row `r` inside a 128B-swizzled tile whose base is 1024-aligned
 GIN_DEVINL uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS); src_bytes == 0 writes zeros instead of reading
+GIN_DEVINL void cp_async16(uint32_t dst_smem, const void* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival once every cp.async issued so far by this thread has landed
+GIN_DEVINL void cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+GIN_DEVINL void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// contiguous global -> shared bulk copy (TMA engine, no tensor map); completion is counted in bytes on `bar`
+GIN_DEVINL void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// Source rows of the bf16 activation copy made by cast_bf16_kernel: rows [0, B*P) are the pixels, rows
+// B*P + 2*sample + pole hold the pole means (corner_mode 'average'), so a pole cell is an ordinary row.
+GIN_DEVINL int resolve_row(int code, long long base, long long total_pix, int sample0, int B) {
+  if (code >= 0) { const long long gp = base + code; return gp < total_pix ? (int)gp : -1; }
+  if (code <= -2) { const int q = -2 - code, sample = sample0 + (q >> 1); return sample < B ? (int)(total_pix + 2 * sample + (q & 1)) : -1; }
+  return -1;
+}
+
 struct Params {
   const int32_t* plan;
   GinSide side;
   int group, B, K, N;
-  const float* X;            // [B*P_src][K] fp32
-  const __nv_bfloat16* W;    // [7][N][K] bf16 (K contiguous)
+  const __nv_bfloat16* X;    // [B*P_src + 2B][K] bf16 (pixels, then pole-mean rows)
+  const __nv_bfloat16* W;    // pre-swizzled bf16 tiles [7][K/64][N][64] (see pack_weights_kernel)
   const float* bias;         // [N] or null
   float* Y;                  // [B*P_dst][N] fp32
+  int accumulate;            // 1: Y += result; 2: atomic Y += result (seam pass of a split dgrad: rows may share a pixel)
 };
+
+constexpr int WARPS = PRODUCER_WARPS + 2;        // + MMA/TMEM warp + weight-copy warp
+constexpr int THREADS2 = WARPS * 32;
 
 template <int N_TILE, int STAGES>
 struct Smem {
@@ -129,8 +159,10 @@ struct Smem {
   static constexpr int TOTAL = SRC_OFF + GIN_MAX_SLOTS * BM * 4 + BM * 8 + 1024;  // + src table + dst rows + align slack
 };
 
+// Gather-mode kernel: one CTA = one 128-row tile x N_TILE channels; every (slot, 64-channel chunk) is a stage whose
+// 128 rows are fetched by cp.async straight into the swizzled tile.  Used for stride-2 convs and the seam pass.
 template <int N_TILE, int STAGES>
-__global__ void __launch_bounds__(THREADS, (N_TILE <= 128 ? 2 : 1)) gather_gemm_tc_kernel(const Params p) {
+__global__ void __launch_bounds__(THREADS2, (N_TILE <= 128 ? 2 : 1)) gather_gemm_tc_kernel(const Params p) {
   using L = Smem<N_TILE, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -138,7 +170,7 @@ __global__ void __launch_bounds__(THREADS, (N_TILE <= 128 ? 2 : 1)) gather_gemm_
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* accum_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-  int32_t* src_s = reinterpret_cast<int32_t*>(smem + L::SRC_OFF);            // [nslots][128] global src pixel / code
+  int32_t* src_s = reinterpret_cast<int32_t*>(smem + L::SRC_OFF);            // [nslots][128] resolved source rows
   long long* dst_s = reinterpret_cast<long long*>(src_s + GIN_MAX_SLOTS * BM);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -148,28 +180,19 @@ __global__ void __launch_bounds__(THREADS, (N_TILE <= 128 ? 2 : 1)) gather_gemm_
   const int nslots = desc->nslots;
   const int kchunks = p.K / BK;
   const int total_stages = nslots * kchunks;
-  const int32_t* ring = p.plan + p.side.ring_off;
 
-  // ---- one-time setup
   if (warp == PRODUCER_WARPS) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], PRODUCER_THREADS); mbar_init(&empty_bar[s], 1); }
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], PRODUCER_THREADS + 1); mbar_init(&empty_bar[s], 1); }
       mbar_init(accum_bar, 1);
       fence_barrier_init();
     }
     __syncwarp();
     tmem_alloc(tmem_slot, N_TILE < 32 ? 32 : N_TILE);
-  } else {
-    // resolve the gather table of this tile once: global source pixel, -1 = zero, <= -2 = pole (absolute sample)
+  } else if (warp < PRODUCER_WARPS) {
     const long long base_src = (long long)G * p.group * p.side.P_src, total_src = (long long)p.B * p.side.P_src;
     const int32_t* src_tab = p.plan + p.side.src_off + desc->src_off;
-    for (int i = tid; i < nslots * BM; i += PRODUCER_THREADS) {
-      const int code = src_tab[i];
-      int v = -1;
-      if (code >= 0) { long long gp = base_src + code; v = (gp < total_src) ? (int)gp : -1; }
-      else if (code <= -2) { int q = -2 - code; int sample = G * p.group + (q >> 1); v = (sample < p.B) ? -2 - (2 * sample + (q & 1)) : -1; }
-      src_s[i] = v;
-    }
+    for (int i = tid; i < nslots * BM; i += PRODUCER_THREADS) src_s[i] = resolve_row(src_tab[i], base_src, total_src, G * p.group, p.B);
     if (tid < BM) {
       const long long base_dst = (long long)G * p.group * p.side.P_dst, total_dst = (long long)p.B * p.side.P_dst;
       const int r = p.plan[p.side.rows_off + t * BM + tid];
@@ -183,52 +206,22 @@ __global__ void __launch_bounds__(THREADS, (N_TILE <= 128 ? 2 : 1)) gather_gemm_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < PRODUCER_WARPS) {
-    // =========================================================== producers: gather + convert + swizzled store
-    const int sub = lane >> 3;        // which of the 4 rows this warp touches per pass
-    const int c8 = lane & 7;          // 16-byte bf16 chunk (8 channels) of the row
+    // =========================================================== producers: asynchronous row gather
+    const int sub = lane >> 3, c8 = lane & 7;
+    const __nv_bfloat16* __restrict__ Xc = p.X + c8 * 8;
     for (int it = 0; it < total_stages; ++it) {
       const int s = it % STAGES;
       const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
       const int kc = it / nslots, slot = it - kc * nslots;
-      const int k0 = kc * BK;
       mbar_wait(&empty_bar[s], ph ^ 1u);
-      uint8_t* a_tile = smem + s * L::STAGE_BYTES;
-      uint8_t* b_tile = a_tile + A_BYTES;
-      // A: 128 gathered rows, 4 passes of 32 rows (4 per warp)
+      const uint32_t a_tile = smem_u32(smem + s * L::STAGE_BYTES);
 #pragma unroll
-      for (int pass = 0; pass < BM / (PRODUCER_WARPS * 4); ++pass) {
-        const int r = pass * (PRODUCER_WARPS * 4) + warp * 4 + sub;
+      for (int ps = 0; ps < 4; ++ps) {
+        const int r = ps * 32 + warp * 4 + sub;
         const int v = src_s[slot * BM + r];
-        float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
-        if (v >= 0) {
-          const float4* src = reinterpret_cast<const float4*>(p.X + (size_t)v * p.K + k0 + c8 * 8);
-          f0 = __ldg(src); f1 = __ldg(src + 1);
-        } else if (v <= -2) {
-          const int q = -2 - v, sample = q >> 1, pole = q & 1;
-#pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            const float4* src = reinterpret_cast<const float4*>(
-                p.X + ((size_t)sample * p.side.P_src + ring[pole * 5 + j]) * p.K + k0 + c8 * 8);
-            const float4 a = __ldg(src), b = __ldg(src + 1);
-            f0.x += a.x; f0.y += a.y; f0.z += a.z; f0.w += a.w; f1.x += b.x; f1.y += b.y; f1.z += b.z; f1.w += b.w;
-          }
-          f0.x *= 0.2f; f0.y *= 0.2f; f0.z *= 0.2f; f0.w *= 0.2f; f1.x *= 0.2f; f1.y *= 0.2f; f1.z *= 0.2f; f1.w *= 0.2f;
-        }
-        uint4 o;
-        o.x = pack_bf16x2(f0.x, f0.y); o.y = pack_bf16x2(f0.z, f0.w); o.z = pack_bf16x2(f1.x, f1.y); o.w = pack_bf16x2(f1.z, f1.w);
-        *reinterpret_cast<uint4*>(a_tile + swz(r, c8)) = o;
+        cp_async16(a_tile + swz(r, c8), Xc + (size_t)(v < 0 ? 0 : v) * p.K + kc * BK, v >= 0);
       }
-      // B: N_TILE weight rows of this (tap, k-chunk)
-      const int tap = desc->tap[slot];
-      const __nv_bfloat16* wsrc = p.W + ((size_t)tap * p.N + n0) * p.K + k0;
-#pragma unroll
-      for (int pass = 0; pass < N_TILE / (PRODUCER_WARPS * 4); ++pass) {
-        const int r = pass * (PRODUCER_WARPS * 4) + warp * 4 + sub;
-        const uint4 w = __ldg(reinterpret_cast<const uint4*>(wsrc + (size_t)r * p.K + c8 * 8));
-        *reinterpret_cast<uint4*>(b_tile + swz(r, c8)) = w;
-      }
-      fence_async_smem();            // generic-proxy stores -> visible to the tensor-core (async) proxy
-      mbar_arrive(&full_bar[s]);
+      cp_async_arrive(&full_bar[s]);
     }
     // =========================================================== epilogue: TMEM -> registers -> global
     mbar_wait(accum_bar, 0);
@@ -253,12 +246,20 @@ __global__ void __launch_bounds__(THREADS, (N_TILE <= 128 ? 2 : 1)) gather_gemm_
             const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col + j));
             o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
           }
-          *reinterpret_cast<float4*>(yp + j) = o;
+          if (p.accumulate == 2) {          // several rows (of this or other tiles) may share a destination pixel
+            atomicAdd(yp + j, o.x); atomicAdd(yp + j + 1, o.y); atomicAdd(yp + j + 2, o.z); atomicAdd(yp + j + 3, o.w);
+          } else {
+            if (p.accumulate) {
+              const float4 old = *reinterpret_cast<const float4*>(yp + j);
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            *reinterpret_cast<float4*>(yp + j) = o;
+          }
         }
       }
     }
     tc_fence_before();
-  } else {
+  } else if (warp == PRODUCER_WARPS) {
     // =========================================================== MMA issuer (one elected thread)
     constexpr uint32_t idesc = make_idesc_bf16(N_TILE);
     if (lane == 0) {
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(THREADS, (N_TILE <= 128 ? 2 : 1)) gather_gemm_
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(&full_bar[s], ph);
+        fence_async_smem();                  // cp.async (generic proxy) writes -> visible to the tensor-core (async) proxy
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
         const uint64_t da = make_desc_kmajor_sw128(a_addr), db = make_desc_kmajor_sw128(a_addr + A_BYTES);
@@ -275,6 +277,21 @@ __global__ void __launch_bounds__(THREADS, (N_TILE <= 128 ? 2 : 1)) gather_gemm_
         umma_commit(&empty_bar[s]);          // frees the stage once these MMAs have read it
       }
       umma_commit(accum_bar);                // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // =========================================================== weight tiles: one bulk copy per stage
+    if (lane == 0) {
+      for (int it = 0; it < total_stages; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        const int kc = it / nslots, slot = it - kc * nslots;
+        const int tap = desc->tap[slot];
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[s], L::B_BYTES);
+        const __nv_bfloat16* wsrc = p.W + (((size_t)tap * kchunks + kc) * p.N + n0) * BK;
+        bulk_g2s(smem + s * L::STAGE_BYTES + A_BYTES, wsrc, L::B_BYTES, &full_bar[s]);
+      }
     }
     __syncwarp();
   }
@@ -295,7 +312,7 @@ int launch(const Params& p, int ntiles, cudaStream_t st) {
     configured = true;
   }
   dim3 grid((unsigned)ntiles, (unsigned)(p.N / N_TILE));
-  kern<<<grid, THREADS, L::TOTAL, st>>>(p);
+  kern<<<grid, THREADS2, L::TOTAL, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
@@ -303,26 +320,27 @@ int launch(const Params& p, int ntiles, cudaStream_t st) {
 
 inline bool tc_supported(int K, int N) { return K % 64 == 0 && N % 64 == 0 && K >= 64 && N >= 64; }
 
-inline int launch_gather_gemm_tc(const int32_t* plan_dev, const GinSide& side, int group, const float* X, const void* Wb,
-                                 const float* bias, float* Y, int B, int K, int N, int ntiles, cudaStream_t st) {
+inline int launch_gather_gemm_tc(const int32_t* plan_dev, const GinSide& side, int group, const void* Xb, const void* Wb,
+                                 const float* bias, float* Y, int B, int K, int N, int ntiles, cudaStream_t st, int accumulate = 0) {
   tc::Params p;
   p.plan = plan_dev; p.side = side; p.group = group; p.B = B; p.K = K; p.N = N;
-  p.X = X; p.W = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = bias; p.Y = Y;
-  if ((long long)B * side.P_src >= 0x7fffffffLL) return -4;
-  if (N % 256 == 0) return tc::launch<256, 3>(p, ntiles, st);
-  if (N % 128 == 0) return tc::launch<128, 3>(p, ntiles, st);
+  p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.W = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = bias; p.Y = Y;
+  p.accumulate = accumulate;
+  if ((long long)B * side.P_src + 2LL * B >= 0x7fffffffLL) return -4;
+  // widest N tile that still gives every SM a CTA
+  if (N % 256 == 0 && (long long)ntiles * (N / 256) >= 148) return tc::launch<256, 3>(p, ntiles, st);
+  if (N % 128 == 0 && (long long)ntiles * (N / 128) >= 148) return tc::launch<128, 3>(p, ntiles, st);
   return tc::launch<64, 4>(p, ntiles, st);
 }
 
-// ======================================================================================= wgrad
-//   dWp[tap][ci][co] += sum_rows bf16(X[src_tap[row], ci]) * bf16(dY[row, co])
+// ======================================================================================= wgrad (gather mode)
+//   dWp[tap][ci][co] += sum_rows X[src_tap[row], ci] * dY[row, co]          (bf16 operands, fp32 accumulate)
 //
 // GEMM with K = pixels.  Both operands are "MN-major" for the tensor core: a staged tile is
-// [pixel row][64 channels = 128 swizzled bytes] -- the very image the forward producer writes --
-// read by UMMA with K running down the rows.  M = 128 is a PAIR of 64-channel atoms
-// (tap, ci-block): two ci-blocks of one tap when Cin >= 128, two taps when Cin == 64.
-// A CTA owns `npairs` pairs x N_BLK output channels (npairs * N_BLK <= 512 TMEM columns) and a
-// slice of the pixel tiles; partial sums are added to dWp with fp32 atomics.
+// [pixel row][64 channels = 128 swizzled bytes] read by UMMA with K running down the rows.  M = 128 is a PAIR of
+// 64-channel atoms (tap, ci-block): two ci-blocks of one tap when Cin >= 128, two taps when Cin == 64.
+// A CTA owns `npairs` pairs x N_BLK output channels (npairs * N_BLK <= 512 TMEM columns) and a slice of the pixel
+// tiles; partial sums are added to dWp with fp32 atomics.  Used for the stride-2 layers.
 namespace tcw {
 using namespace tc;
 
@@ -330,9 +348,9 @@ struct Params {
   const int32_t* plan;
   GinSide side;
   int group, B, Cin, Cout;
-  const float* X;     // [B*P_src][Cin]
-  const float* dY;    // [B*P_dst][Cout]
-  float* dWp;         // [7][Cin][Cout]
+  const __nv_bfloat16* X;     // [B*P_src + 2B][Cin]
+  const __nv_bfloat16* dY;    // [B*P_dst (+2B)][Cout]
+  float* dWp;                 // [7][Cin][Cout]
   int total_tiles, tiles_per_cta, units_m;   // units_m: number of pair-groups along M
 };
 
@@ -344,8 +362,9 @@ struct Smem {
   static constexpr int B_BYTES_ = (N_BLK / 64) * ATOM_BYTES;     // dY tile, double buffered
   static constexpr int B_OFF = STAGES * A_STAGE;
   static constexpr int BAR_OFF = B_OFF + 2 * B_BYTES_;
-  // a_full[STAGES], a_empty[STAGES], b_full[2], b_empty[2], accum, tmem slot
-  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 5) * 8 + 16 + 1024;
+  // a_full[STAGES], a_empty[STAGES], b_full[2], b_empty[2], accum, tmem slot, then the per-tile row tables
+  static constexpr int TAB_OFF = BAR_OFF + (2 * STAGES + 5) * 8 + 16;
+  static constexpr int TOTAL = TAB_OFF + 8 * BM * 4 + 1024;
 };
 
 GIN_DEVINL uint64_t make_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -356,52 +375,6 @@ GIN_DEVINL uint64_t make_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_byt
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
-}
-
-// gather 128 rows x 64 channels (fp32 -> bf16) into a swizzled atom; rows come from `codes` (plan src codes)
-// or, when codes == nullptr, from the tile's own dst rows (the dY side).
-GIN_DEVINL void stage_atom(uint8_t* atom, const float* __restrict__ base, int C, int c0, const int32_t* __restrict__ codes,
-                           const int32_t* __restrict__ drows, long long base_src, long long total_src, long long base_dst,
-                           long long total_dst, int sample0, int B, int P_src, const int32_t* __restrict__ ring, int warp,
-                           int lane, bool zero_all) {
-  const int sub = lane >> 3, c8 = lane & 7;
-#pragma unroll
-  for (int pass = 0; pass < BM / (PRODUCER_WARPS * 4); ++pass) {
-    const int r = pass * (PRODUCER_WARPS * 4) + warp * 4 + sub;
-    float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
-    const int dr = drows[r];
-    const long long d = (dr >= 0) ? base_dst + dr : -1;
-    const bool row_ok = !zero_all && d >= 0 && d < total_dst;
-    if (row_ok) {
-      if (codes == nullptr) {
-        const float4* src = reinterpret_cast<const float4*>(base + (size_t)d * C + c0 + c8 * 8);
-        f0 = __ldg(src); f1 = __ldg(src + 1);
-      } else {
-        const int code = codes[r];
-        if (code >= 0) {
-          const long long gp = base_src + code;
-          if (gp < total_src) {
-            const float4* src = reinterpret_cast<const float4*>(base + (size_t)gp * C + c0 + c8 * 8);
-            f0 = __ldg(src); f1 = __ldg(src + 1);
-          }
-        } else if (code <= -2) {
-          const int q = -2 - code, sample = sample0 + (q >> 1), pole = q & 1;
-          if (sample < B) {
-#pragma unroll
-            for (int j = 0; j < 5; ++j) {
-              const float4* src = reinterpret_cast<const float4*>(base + ((size_t)sample * P_src + ring[pole * 5 + j]) * C + c0 + c8 * 8);
-              const float4 a = __ldg(src), b = __ldg(src + 1);
-              f0.x += a.x; f0.y += a.y; f0.z += a.z; f0.w += a.w; f1.x += b.x; f1.y += b.y; f1.z += b.z; f1.w += b.w;
-            }
-            f0.x *= 0.2f; f0.y *= 0.2f; f0.z *= 0.2f; f0.w *= 0.2f; f1.x *= 0.2f; f1.y *= 0.2f; f1.z *= 0.2f; f1.w *= 0.2f;
-          }
-        }
-      }
-    }
-    uint4 o;
-    o.x = pack_bf16x2(f0.x, f0.y); o.y = pack_bf16x2(f0.z, f0.w); o.z = pack_bf16x2(f1.x, f1.y); o.w = pack_bf16x2(f1.z, f1.w);
-    *reinterpret_cast<uint4*>(atom + swz(r, c8)) = o;
-  }
 }
 
 // atom index a in [0, 7*Cin/64): tap = a / (Cin/64), ci-block = a % (Cin/64)  (Cin >= 128: consecutive atoms pair up
@@ -417,6 +390,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const Params p) {
   uint64_t* b_empty = b_full + 2;
   uint64_t* accum_bar = b_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  int32_t* tab_s = reinterpret_cast<int32_t*>(smem + L::TAB_OFF);     // [8][128]: rows 0..6 = per-tap source row, row 7 = dst pixel
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cblocks = p.Cin / 64, natoms = 7 * cblocks;
@@ -428,6 +402,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const Params p) {
   const int T0 = blockIdx.x * p.tiles_per_cta, T1 = min(T0 + p.tiles_per_cta, p.total_tiles);
   const int ntile = T1 - T0;
   constexpr int TM_COLS = (NPAIRS * N_BLK <= 32) ? 32 : (NPAIRS * N_BLK <= 64) ? 64 : (NPAIRS * N_BLK <= 128) ? 128 : (NPAIRS * N_BLK <= 256) ? 256 : 512;
+  constexpr int NB = N_BLK / 64;                            // dY atoms per pixel tile
 
   if (warp == PRODUCER_WARPS) {
     if (lane == 0) {
@@ -450,42 +425,63 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const Params p) {
   }
 
   if (warp < PRODUCER_WARPS) {
-    const int32_t* ring = p.plan + p.side.ring_off;
     const long long total_src = (long long)p.B * p.side.P_src, total_dst = (long long)p.B * p.side.P_dst;
-    int it = 0;
+    const int sub = lane >> 3, c8 = lane & 7;
+    uint32_t it = 0;                                        // running A-pair counter (stage ring)
     for (int ti = 0; ti < ntile; ++ti) {
       const int T = T0 + ti, G = T / p.side.ntiles, t = T % p.side.ntiles;
       const GinTileDesc* desc = reinterpret_cast<const GinTileDesc*>(p.plan + p.side.tiles_off) + t;
       const int32_t* src_tab = p.plan + p.side.src_off + desc->src_off;
-      const int32_t* drows = p.plan + p.side.rows_off + t * BM;
       const long long base_src = (long long)G * p.group * p.side.P_src, base_dst = (long long)G * p.group * p.side.P_dst;
-      // dY tile of this pixel block (double buffered)
+      // resolve this tile's tables into shared memory (producers only; addresses are consumed at issue time)
+      asm volatile("bar.sync 1, %0;" ::"n"(PRODUCER_THREADS) : "memory");
+      for (int i = tid; i < 8 * BM; i += PRODUCER_THREADS) {
+        const int trow = i >> 7, r = i & (BM - 1);
+        const int dr = p.plan[p.side.rows_off + t * BM + r];
+        const long long d = (dr >= 0) ? base_dst + dr : -1;
+        const bool row_ok = d >= 0 && d < total_dst;
+        int v = -1;
+        if (trow == 7) v = row_ok ? (int)d : -1;
+        else if (row_ok) {
+          int slot = -1;
+          for (int q = 0; q < desc->nslots; ++q) if (desc->tap[q] == trow) { slot = q; break; }
+          if (slot >= 0) v = resolve_row(src_tab[slot * BM + r], base_src, total_src, G * p.group, p.B);
+        }
+        tab_s[i] = v;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(PRODUCER_THREADS) : "memory");
+      // dY tile (double buffered)
       {
         const int bs = ti & 1;
-        mbar_wait(&b_empty[bs], (((uint32_t)(ti >> 1)) & 1u) ^ 1u);
-        uint8_t* bt = smem + L::B_OFF + bs * L::B_BYTES_;
+        mbar_wait(&b_empty[bs], (((uint32_t)ti >> 1) & 1u) ^ 1u);
+        const uint32_t bt = smem_u32(smem + L::B_OFF + bs * L::B_BYTES_);
 #pragma unroll
-        for (int j = 0; j < N_BLK / 64; ++j)
-          stage_atom(bt + j * ATOM_BYTES, p.dY, p.Cout, n0 + j * 64, nullptr, drows, 0, 0, base_dst, total_dst, 0, p.B, 0, ring, warp, lane, false);
-        fence_async_smem();
-        mbar_arrive(&b_full[bs]);
+        for (int j = 0; j < NB; ++j)
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            const int r = ps * 32 + warp * 4 + sub;
+            const int v = tab_s[7 * BM + r];
+            cp_async16(bt + j * ATOM_BYTES + swz(r, c8), p.dY + (size_t)(v < 0 ? 0 : v) * p.Cout + n0 + j * 64 + c8 * 8, v >= 0);
+          }
+        cp_async_arrive(&b_full[bs]);
       }
       for (int pr = 0; pr < npairs; ++pr, ++it) {
         const int s = it % STAGES;
-        mbar_wait(&a_empty[s], (((uint32_t)(it / STAGES)) & 1u) ^ 1u);
-        uint8_t* at = smem + s * L::A_STAGE;
+        mbar_wait(&a_empty[s], ((it / STAGES) & 1u) ^ 1u);
+        const uint32_t at = smem_u32(smem + s * L::A_STAGE);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int atom = (pair0 + pr) * 2 + h;
           const bool dummy = atom >= natoms;
           const int tap = dummy ? 0 : atom / cblocks, cb = dummy ? 0 : atom % cblocks;
-          int slot = -1;
-          for (int q = 0; q < desc->nslots; ++q) if (desc->tap[q] == tap) { slot = q; break; }
-          stage_atom(at + h * ATOM_BYTES, p.X, p.Cin, cb * 64, src_tab + (slot < 0 ? 0 : slot) * BM, drows, base_src, total_src, base_dst,
-                     total_dst, G * p.group, p.B, p.side.P_src, ring, warp, lane, dummy || slot < 0);
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            const int r = ps * 32 + warp * 4 + sub;
+            const int v = dummy ? -1 : tab_s[tap * BM + r];
+            cp_async16(at + h * ATOM_BYTES + swz(r, c8), p.X + (size_t)(v < 0 ? 0 : v) * p.Cin + cb * 64 + c8 * 8, v >= 0);
+          }
         }
-        fence_async_smem();
-        mbar_arrive(&a_full[s]);
+        cp_async_arrive(&a_full[s]);
       }
     }
     // ---- epilogue: TMEM -> atomics into dWp
@@ -514,15 +510,15 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const Params p) {
   } else {
     constexpr uint32_t idesc = make_idesc_bf16(N_BLK, 1, 1);
     if (lane == 0) {
-      int it = 0;
+      uint32_t it = 0;
       for (int ti = 0; ti < ntile; ++ti) {
         const int bs = ti & 1;
-        mbar_wait(&b_full[bs], ((uint32_t)(ti >> 1)) & 1u);
-        tc_fence_after();
+        mbar_wait(&b_full[bs], ((uint32_t)ti >> 1) & 1u);
         const uint32_t b_addr = smem_u32(smem + L::B_OFF + bs * L::B_BYTES_);
         for (int pr = 0; pr < npairs; ++pr, ++it) {
           const int s = it % STAGES;
-          mbar_wait(&a_full[s], ((uint32_t)(it / STAGES)) & 1u);
+          mbar_wait(&a_full[s], (it / STAGES) & 1u);
+          fence_async_smem();
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * L::A_STAGE);
 #pragma unroll
@@ -570,12 +566,13 @@ int launch(Params p, cudaStream_t st) {
 
 inline bool tc_wgrad_supported(int Cin, int Cout) { return Cin % 64 == 0 && Cout % 64 == 0 && Cin >= 64 && Cout >= 64; }
 
-inline int launch_wgrad_tc(const int32_t* plan_dev, const GinSide& side, int group, const float* X, const float* dY, float* dWp,
+inline int launch_wgrad_tc(const int32_t* plan_dev, const GinSide& side, int group, const void* Xb, const void* dYb, float* dWp,
                            int B, int Cin, int Cout, int total_tiles, cudaStream_t st) {
   tcw::Params p;
   p.plan = plan_dev; p.side = side; p.group = group; p.B = B; p.Cin = Cin; p.Cout = Cout;
-  p.X = X; p.dY = dY; p.dWp = dWp; p.total_tiles = total_tiles; p.tiles_per_cta = 1; p.units_m = 1;
-  if ((long long)B * side.P_src >= 0x7fffffffLL) return -4;
+  p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.dY = reinterpret_cast<const __nv_bfloat16*>(dYb); p.dWp = dWp;
+  p.total_tiles = total_tiles; p.tiles_per_cta = 1; p.units_m = 1;
+  if ((long long)B * side.P_src + 2LL * B >= 0x7fffffffLL) return -4;
   if (Cout % 256 == 0) return tcw::launch<256, 2, 2>(p, st);
   if (Cout % 128 == 0) return tcw::launch<128, 4, 3>(p, st);
   return tcw::launch<64, 7, 4>(p, st);

@@ -214,7 +214,7 @@ bool build_conv(int level, int stride, int corner_mode, std::vector<int32_t>& bl
   }
   Geo gi(level), go(stride == 2 ? level - 1 : level);
   // forward gather table: out pixel -> 7 sources
-  std::vector<std::vector<Entry>> fwd(go.P), adj(gi.P);
+  std::vector<std::vector<Entry>> fwd(go.P), adj(gi.P), adjx(gi.P);   // adjx: entries that cross a chart seam / a pole
   std::vector<std::pair<int, int>> pole_readers[2];  // (out pixel, tap)
   for (int k = 0; k < 5; ++k)
     for (int I = 0; I < go.n; ++I)
@@ -233,6 +233,8 @@ bool build_conv(int level, int stride, int corner_mode, std::vector<int32_t>& bl
           } else {
             fwd[po].push_back({v, t});
             adj[v].push_back({po, t});
+            const int ti = ci + kTap[t][0], tj = cj + kTap[t][1];
+            if (!(ti >= 0 && ti < gi.n && tj >= 0 && tj < gi.W)) adjx[v].push_back({po, t});
           }
         }
       }
@@ -250,7 +252,10 @@ bool build_conv(int level, int stride, int corner_mode, std::vector<int32_t>& bl
            std::find(ring_out + 5 * pole, ring_out + 5 * pole + 5, rd[a].first) != ring_out + 5 * pole + 5;
     }
     if (!ok) { gin_set_error("hexconv plan: unexpected pole reader set"); return false; }
-    for (int j = 0; j < 5; ++j) adj[ring_in[5 * pole + j]].push_back({-2 - pole, rd[0].second});
+    for (int j = 0; j < 5; ++j) {
+      adj[ring_in[5 * pole + j]].push_back({-2 - pole, rd[0].second});
+      adjx[ring_in[5 * pole + j]].push_back({-2 - pole, rd[0].second});
+    }
   }
   const int group = std::max(group_size(gi.P), group_size(go.P));
   SideBuild F, D;
@@ -276,6 +281,63 @@ bool build_conv(int level, int stride, int corner_mode, std::vector<int32_t>& bl
   };
   emit_side(F, ring_in, h.fwd);
   emit_side(D, ring_out, h.dg);
+  if (stride == 1 && level >= 2) {
+    // ---- patch tiles
+    const int R = (level >= 3) ? 8 : 4, Q = 16 / R, octs = gi.W / 8, rblocks = gi.n / R;
+    struct OctCol { int sg, k, i0, j0; };
+    std::vector<OctCol> cols;
+    for (int sg = 0; sg < group; ++sg)
+      for (int k = 0; k < 5; ++k)
+        for (int bi = 0; bi < rblocks; ++bi)
+          for (int jo = 0; jo < octs; ++jo) cols.push_back({sg, k, bi * R, jo * 8});
+    if (cols.size() % Q) { gin_set_error("hexconv plan: octet columns do not tile"); return false; }
+    const int ntiles = (int)cols.size() / Q, U = (R + 2) * Q * 10;
+    std::vector<int32_t> psrc((size_t)ntiles * U), pdsrc((size_t)ntiles * U), prows((size_t)ntiles * GIN_TILE_M);
+    for (int t = 0; t < ntiles; ++t)
+      for (int q = 0; q < Q; ++q) {
+        const OctCol& oc = cols[(size_t)t * Q + q];
+        for (int ip = 0; ip < R + 2; ++ip)
+          for (int c = 0; c < 10; ++c) {
+            const int i = oc.i0 - 1 + ip, j = oc.j0 - 1 + c;
+            const int v = gi.source(oc.k, i, j);
+            int code = GIN_SRC_ZERO;
+            if (v >= 0 && v < gi.P) code = oc.sg * gi.P + v;
+            else if (v >= gi.P && corner_mode == GIN_CORNER_AVERAGE) code = -2 - (2 * oc.sg + (v - gi.P));
+            const bool inside = i >= 0 && i < gi.n && j >= 0 && j < gi.W;
+            const size_t e = (size_t)t * U + ((size_t)ip * Q + q) * 10 + c;
+            psrc[e] = code;
+            pdsrc[e] = inside ? code : GIN_SRC_ZERO;
+          }
+        for (int r = 0; r < R; ++r)
+          for (int px = 0; px < 8; ++px)
+            prows[(size_t)t * GIN_TILE_M + ((size_t)r * Q + q) * 8 + px] = oc.sg * gi.P + gi.vid(oc.k, oc.i0 + r, oc.j0 + px);
+      }
+    auto emit_p = [&](const std::vector<int32_t>& src, const int32_t* ring, GinPSide& ps) {
+      ps.R = R; ps.Q = Q; ps.U = U; ps.ntiles = ntiles;
+      ps.src_off = (int)blob.size();
+      blob.insert(blob.end(), src.begin(), src.end());
+      ps.rows_off = (int)blob.size();
+      blob.insert(blob.end(), prows.begin(), prows.end());
+      ps.ring_off = (int)blob.size();
+      blob.insert(blob.end(), ring, ring + 10);
+    };
+    emit_p(psrc, ring_in, h.pfwd);
+    emit_p(pdsrc, ring_out, h.pdg);
+    // ---- the cross-seam remainder of dgrad: ONE ROW PER ENTRY, rows grouped by tap, so every tile is a plain
+    // single-tap GEMM over gathered dy rows (weights fetched once per tile); rows that share a destination pixel are
+    // combined by the kernel's atomic-add epilogue.
+    SideBuild X;
+    std::vector<std::vector<Entry>> only;
+    std::vector<int> pix;
+    for (int v = 0; v < gi.P; ++v)
+      for (const Entry& e : adjx[v]) { only.push_back({e}); pix.push_back(v); }
+    if (!build_side(only, go.P, (int)only.size(), go.s, group, true, X)) return false;
+    // build_side numbered the rows 0..only.size()-1 per sample; translate back to pixels of the full map
+    for (auto& r : X.rows)
+      if (r >= 0) { const int sg = r / (int)only.size(), idx = r % (int)only.size(); r = sg * gi.P + pix[idx]; }
+    X.P_dst = gi.P;
+    emit_side(X, ring_out, h.dgx);
+  }
   h.magic = GIN_MAGIC; h.kind = GIN_PLAN_HEXCONV; h.level_in = level; h.level_out = go.s; h.stride = stride;
   h.corner_mode = corner_mode; h.group = group; h.total_words = (int)blob.size();
   std::memcpy(blob.data(), &h, sizeof(h));

@@ -31,10 +31,25 @@ struct GinSide {              // one gather-GEMM problem: rows of dst gathered f
   int32_t max_slots;
 };
 
+// Patch ("P") tiles for stride-1 convolutions: a tile is R chart rows x Q octets (8 consecutive pixels of one
+// chart row), R*Q = 16.  The kernel stages the (R+2) x (8Q+2) padded neighbourhood ONCE per 64-channel chunk as
+// three column-shifted copies; the seven taps are then just different start addresses of the UMMA descriptor.
+//   src[tile][((i' * Q + q) * 10 + c)]  = source code of padded cell (row i0-1+i', col j0_q-1+c) of octet-column q
+//   rows[tile][(r * Q + q) * 8 + px]    = destination pixel (inside the sample group)
+struct GinPSide {
+  int32_t R, Q, U;            // U = (R+2)*Q*10 source rows per tile
+  int32_t ntiles;             // per sample group (0 = patch mode not available for this plan)
+  int32_t src_off, rows_off;
+  int32_t ring_off, pad_;
+};
+
 struct GinConvPlanHdr {
   int32_t magic, kind, level_in, level_out, stride, corner_mode, group, total_words;
   GinSide fwd;                // y rows gathered from x   (also drives wgrad)
   GinSide dg;                 // dx rows gathered from dy (adjoint of pad o conv)
+  GinPSide pfwd;              // stride 1 only: forward in patch mode (halo cells come through the chart stitching)
+  GinPSide pdg;               // stride 1 only: in-chart part of dgrad in patch mode (halo cells are zero) ...
+  GinSide dgx;                // ... plus the cross-seam / pole entries, ACCUMULATED on top by a gather-mode pass
 };
 
 struct GinUpPlanHdr {

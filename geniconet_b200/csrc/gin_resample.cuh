@@ -2,6 +2,8 @@
 // KL divergence (a9).  All are pure streaming work: one thread per 16-byte channel vector,
 // coalesced along the channel axis, grid-stride.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "gin_common.cuh"
 
 namespace gin {
@@ -66,6 +68,38 @@ upsample_bwd_kernel(const int32_t* __restrict__ plan, const float* __restrict__ 
       acc = fma4(w[(size_t)p * deg + e], ld4(dyb + (size_t)f * C + c), acc);
     }
     *reinterpret_cast<float4*>(dx + (size_t)bp * C + c) = acc;
+  }
+}
+
+// fp32 [B*P][C] -> bf16 [B*P + 2B][C].  The 2B extra rows are the per-sample pole means (mean of the pole's five ring
+// pixels), so that the tcgen05 producers can fetch a pole cell like any other row.  One thread = 8 channels.
+__global__ void __launch_bounds__(256)
+cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, const int32_t* __restrict__ ring, int B, int P, int C) {
+  const int C8 = C >> 3;
+  const long long n_main = (long long)B * P * C8, n_all = n_main + 2LL * B * C8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_all; i += (long long)gridDim.x * blockDim.x) {
+    float4 a, b;
+    if (i < n_main) {
+      a = ld4(x + i * 8);
+      b = ld4(x + i * 8 + 4);
+    } else {
+      const long long j = i - n_main;
+      const int c = (int)(j % C8) * 8;
+      const int sp = (int)(j / C8), sample = sp >> 1, pole = sp & 1;
+      a = make_float4(0.f, 0.f, 0.f, 0.f); b = a;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const float* src = x + ((size_t)sample * P + ring[pole * 5 + k]) * C + c;
+        a = fma4(0.2f, ld4(src), a);
+        b = fma4(0.2f, ld4(src + 4), b);
+      }
+    }
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+    o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+    *reinterpret_cast<uint4*>(xb + i * 8) = o;
   }
 }
 

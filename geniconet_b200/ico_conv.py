@@ -14,6 +14,7 @@ them unchanged and without a transpose.  There is no CPU implementation: tensors
 not on a CUDA device raise.
 """
 import math
+import weakref
 
 import numpy as np
 import torch
@@ -80,6 +81,42 @@ def _new_map(B, C, H, W, device):
     return torch.empty((B, H, W, C), dtype=torch.float32, device=device).permute(0, 3, 1, 2)
 
 
+class _CastCache:
+    """Last few bf16 activation copies, keyed by the identity of the fp32 tensor: the two sibling convolutions of a
+    residual block (conv00 / conv10, models.py:25-33) read the same input, so it is cast once."""
+
+    def __init__(self, size=3):
+        self.size, self.items = size, []
+
+    def get(self, t, key):
+        for ref, ver, k, out in self.items:
+            if ref() is t and ver == t._version and k == key:
+                return out
+        return None
+
+    def put(self, t, key, out):
+        self.items.append((weakref.ref(t), t._version, key, out))
+        del self.items[:-self.size]
+
+
+_cast_cache = _CastCache()
+
+
+def cast_bf16(x_cl, plan, which, level, use_cache=False):
+    """bf16 copy [B*P + 2B, C] of a channels-last fp32 map (pixels, then the per-sample pole means)."""
+    B, C = x_cl.shape[0], x_cl.shape[1]
+    key = (plan.dev_ptr, which)
+    if use_cache:
+        hit = _cast_cache.get(x_cl, key)
+        if hit is not None:
+            return hit
+    out = torch.empty((_lib.lib.gin_cast_bf16_bytes(B, level, C) // 2,), dtype=torch.bfloat16, device=x_cl.device)
+    _lib.check(_lib.lib.gin_cast_bf16(plan.host_ptr, plan.dev_ptr, which, x_cl.data_ptr(), out.data_ptr(), B, C, _stream()), 'gin_cast_bf16')
+    if use_cache:
+        _cast_cache.put(x_cl, key, out)
+    return out
+
+
 class _HexConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, mod):
@@ -91,42 +128,66 @@ class _HexConvFn(torch.autograd.Function):
                              % (mod.subdivisions, mod.in_features, 5 * n, 2 * n, tuple(x.shape)))
         plan = get_plan(_lib.PLAN_HEXCONV, mod.subdivisions, mod.stride, mod.corner_mode, x.device)
         packed = mod._packed_weights(weight)
-        xs, sb, sp, sc = pixel_strides(x)
         Ho, Wo = H // mod.stride, W // mod.stride
         y = _new_map(B, mod.out_features, Ho, Wo, x.device)
-        if B > 0:
-            _lib.check(_lib.lib.gin_hexconv_fwd(plan.host_ptr, plan.dev_ptr, xs.data_ptr(), sb, sp, sc, packed.data_ptr(),
-                                                bias.data_ptr() if bias is not None else None, y.data_ptr(),
-                                                B, mod.in_features, mod.out_features, mod.impl, _stream()), 'gin_hexconv_fwd')
-        ctx.mod, ctx.plan, ctx.strides, ctx.has_bias = mod, plan, (sb, sp, sc), bias is not None
-        ctx.save_for_backward(xs, packed)
+        tc = mod.uses_tensor_cores()
+        ctx.mod, ctx.plan, ctx.has_bias, ctx.tc, ctx.in_shape = mod, plan, bias is not None, tc, (B, C, H, W)
+        bias_ptr = bias.data_ptr() if bias is not None else None
+        if tc:
+            xs = as_channels_last(x)
+            xb = cast_bf16(xs, plan, 0, mod.subdivisions, use_cache=True) if B > 0 else xs.new_empty(0, dtype=torch.bfloat16)
+            if B > 0:
+                _lib.check(_lib.lib.gin_hexconv_fwd_bf16(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), packed.data_ptr(), bias_ptr, y.data_ptr(),
+                                                         B, mod.in_features, mod.out_features, _stream()), 'gin_hexconv_fwd_bf16')
+            ctx.save_for_backward(xb, packed)           # the bf16 copy is all wgrad needs: half the saved-activation bytes
+        else:
+            xs, sb, sp, sc = pixel_strides(x)
+            if B > 0:
+                _lib.check(_lib.lib.gin_hexconv_fwd(plan.host_ptr, plan.dev_ptr, xs.data_ptr(), sb, sp, sc, packed.data_ptr(), bias_ptr,
+                                                    y.data_ptr(), B, mod.in_features, mod.out_features, _lib.IMPL_SIMT, _stream()), 'gin_hexconv_fwd')
+            ctx.strides = (sb, sp, sc)
+            ctx.save_for_backward(xs, packed)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         xs, packed = ctx.saved_tensors
         mod, plan = ctx.mod, ctx.plan
-        B = xs.shape[0]
+        B, C, H, W = ctx.in_shape
+        dev = dy.device
         dy = as_channels_last(dy)
         dx = dW = db = None
         st = _stream()
+        need_w = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
         if B == 0:
-            return (torch.zeros_like(xs) if ctx.needs_input_grad[0] else None,
-                    torch.zeros(mod.out_features, mod.in_features, 7, device=xs.device),
-                    torch.zeros(mod.out_features, device=xs.device) if ctx.has_bias else None, None)
+            return (torch.zeros(ctx.in_shape, device=dev) if ctx.needs_input_grad[0] else None,
+                    torch.zeros(mod.out_features, mod.in_features, 7, device=dev),
+                    torch.zeros(mod.out_features, device=dev) if ctx.has_bias else None, None)
+        if need_w:
+            dW = torch.empty((mod.out_features, mod.in_features, 7), dtype=torch.float32, device=dev)
+            db = torch.empty((mod.out_features,), dtype=torch.float32, device=dev) if ctx.has_bias else None
+            ws = torch.empty((_lib.lib.gin_hexconv_wgrad_ws_bytes(mod.in_features, mod.out_features),), dtype=torch.uint8, device=dev)
         if ctx.needs_input_grad[0]:
-            dx = _new_map(B, mod.in_features, xs.shape[2], xs.shape[3], xs.device)
-            _lib.check(_lib.lib.gin_hexconv_dgrad(plan.host_ptr, plan.dev_ptr, dy.data_ptr(), packed.data_ptr(), dx.data_ptr(),
-                                                  B, mod.in_features, mod.out_features, mod.impl, st), 'gin_hexconv_dgrad')
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dW = torch.empty((mod.out_features, mod.in_features, 7), dtype=torch.float32, device=xs.device)
-            db = torch.empty((mod.out_features,), dtype=torch.float32, device=xs.device) if ctx.has_bias else None
-            ws = torch.empty((_lib.lib.gin_hexconv_wgrad_ws_bytes(mod.in_features, mod.out_features),), dtype=torch.uint8,
-                             device=xs.device)
-            sb, sp, sc = ctx.strides
-            _lib.check(_lib.lib.gin_hexconv_wgrad(plan.host_ptr, plan.dev_ptr, xs.data_ptr(), sb, sp, sc, dy.data_ptr(),
-                                                  dW.data_ptr(), db.data_ptr() if db is not None else None, ws.data_ptr(),
-                                                  B, mod.in_features, mod.out_features, mod.impl, st), 'gin_hexconv_wgrad')
+            dx = _new_map(B, mod.in_features, H, W, dev)
+        if ctx.tc:
+            level_out = mod.subdivisions - (1 if mod.stride == 2 else 0)
+            dyb = cast_bf16(dy, plan, 1, level_out)                  # one cast serves dgrad and wgrad
+            if dx is not None:
+                _lib.check(_lib.lib.gin_hexconv_dgrad_bf16(plan.host_ptr, plan.dev_ptr, dyb.data_ptr(), packed.data_ptr(), dx.data_ptr(),
+                                                           B, mod.in_features, mod.out_features, st), 'gin_hexconv_dgrad_bf16')
+            if need_w:
+                _lib.check(_lib.lib.gin_hexconv_wgrad_bf16(plan.host_ptr, plan.dev_ptr, xs.data_ptr(), dyb.data_ptr(), dy.data_ptr(),
+                                                           dW.data_ptr(), db.data_ptr() if db is not None else None, ws.data_ptr(),
+                                                           B, mod.in_features, mod.out_features, st), 'gin_hexconv_wgrad_bf16')
+        else:
+            if dx is not None:
+                _lib.check(_lib.lib.gin_hexconv_dgrad(plan.host_ptr, plan.dev_ptr, dy.data_ptr(), packed.data_ptr(), dx.data_ptr(),
+                                                      B, mod.in_features, mod.out_features, _lib.IMPL_SIMT, st), 'gin_hexconv_dgrad')
+            if need_w:
+                sb, sp, sc = ctx.strides
+                _lib.check(_lib.lib.gin_hexconv_wgrad(plan.host_ptr, plan.dev_ptr, xs.data_ptr(), sb, sp, sc, dy.data_ptr(),
+                                                      dW.data_ptr(), db.data_ptr() if db is not None else None, ws.data_ptr(),
+                                                      B, mod.in_features, mod.out_features, _lib.IMPL_SIMT, st), 'gin_hexconv_wgrad')
         return dx, dW, db, None
 
 
@@ -171,6 +232,13 @@ class IcoConvS2S(torch.nn.Module):
                                                          self.out_features, _stream()), 'gin_hexconv_pack_weights')
             self._packed_key = key
         return self._packed
+
+    def uses_tensor_cores(self):
+        """tcgen05 path (bf16 operands, fp32 accumulate) when the conv is a dense contraction: both channel counts % 64 == 0."""
+        wide = self.in_features % 64 == 0 and self.out_features % 64 == 0
+        if self.impl == _lib.IMPL_TC and not wide:
+            raise ValueError('impl="tc" needs in_features and out_features to be multiples of 64')
+        return wide and self.impl != _lib.IMPL_SIMT
 
     def forward(self, x):
         return _HexConvFn.apply(x, self.weight, self.bias, self)

@@ -22,10 +22,10 @@
  *     gin_hexconv_fwd / gin_hexconv_wgrad may instead use arbitrary element strides
  *     (sb, sp, sc) so the NCHW xyz input of models.py:104 needs no transpose.
  *   - corner_mode: 0 = 'zeros', 1 = 'average' (models.py:11, run.py:683).
- *   - impl: GIN_IMPL_SIMT = fp32 CUDA-core kernels (exact fp32 accumulate),
- *           GIN_IMPL_TC   = tcgen05 implicit GEMM, bf16 operands / fp32 accumulate in TMEM,
- *           GIN_IMPL_AUTO = TC when the channel widths make it a dense contraction
- *                           (Cin % 64 == 0 and Cout % 64 == 0), SIMT otherwise.
+ *   - the fp32 entry points gin_hexconv_{fwd,dgrad,wgrad} run the exact-fp32 CUDA-core kernels (impl must be
+ *     GIN_IMPL_AUTO or GIN_IMPL_SIMT); the tcgen05 implicit GEMM (bf16 operands, fp32 accumulate in TMEM) is
+ *     gin_cast_bf16 + gin_hexconv_*_bf16 and is what the Python layer uses whenever both channel counts are
+ *     multiples of 64.
  */
 #ifndef GENICONET_B200_H
 #define GENICONET_B200_H
@@ -92,6 +92,21 @@ size_t gin_hexconv_wgrad_ws_bytes(int Cin, int Cout);
 int gin_hexconv_wgrad(const void* plan_host, const void* plan_dev, const float* x, int64_t sb, int64_t sp, int64_t sc,
                       const float* dy, float* dW, float* db, void* ws,
                       int B, int Cin, int Cout, int impl, void* stream);
+
+/* tcgen05 path.  The tensor-core kernels read a bf16 copy of the gathered activation: gin_cast_bf16 writes
+ * [B*P + 2B][C] bf16 = the pixels followed by the per-sample pole means (so a pole cell is an ordinary row).
+ * `which` = 0 for a conv INPUT (x, level of `subdivisions`), 1 for a conv OUTPUT gradient (dy, output level).
+ * One cast of x serves forward and wgrad, one cast of dy serves dgrad and wgrad.  Operands are bf16, accumulation
+ * is fp32 in TMEM, outputs are fp32.  Needs Cin % 64 == 0 and Cout % 64 == 0. */
+size_t gin_cast_bf16_bytes(int B, int level, int C);
+int gin_cast_bf16(const void* plan_host, const void* plan_dev, int which, const float* x, void* xb, int B, int C, void* stream);
+int gin_hexconv_fwd_bf16(const void* plan_host, const void* plan_dev, const void* xb, const void* packed, const float* bias,
+                         float* y, int B, int Cin, int Cout, void* stream);
+int gin_hexconv_dgrad_bf16(const void* plan_host, const void* plan_dev, const void* dyb, const void* packed, float* dx,
+                           int B, int Cin, int Cout, void* stream);
+/* dy (fp32) is only read for db and may be NULL when db is NULL */
+int gin_hexconv_wgrad_bf16(const void* plan_host, const void* plan_dev, const void* xb, const void* dyb, const float* dy,
+                           float* dW, float* db, void* ws, int B, int Cin, int Cout, void* stream);
 
 /* ------------------------------------------------------------------ device: upsample - */
 /* IcoUpsampleS2S.forward (models.py:13,45,53), row a4, and its backward. */

@@ -128,3 +128,77 @@ def run_up_bwd(blob, dy):
         ok = idx[:, e] >= 0
         dx[:, ok] += w[ok, e][None, :, None] * dy[:, idx[ok, e]]
     return dx
+
+
+# ---------------------------------------------------------------- patch-mode tables
+TAPS = ((0, 0), (-1, 0), (1, 0), (0, -1), (0, 1), (-1, 1), (1, -1))
+
+
+def parse_pside(blob, off):
+    names = ['R', 'Q', 'U', 'ntiles', 'src_off', 'rows_off', 'ring_off', 'pad']
+    return dict(zip(names, [int(x) for x in blob[off:off + 8]]))
+
+
+def parse_conv_full(blob):
+    h = parse_conv(blob)
+    h['pfwd'] = parse_pside(blob, 24)
+    h['pdg'] = parse_pside(blob, 32)
+    h['dgx'] = parse_side(blob, 40)
+    return h
+
+
+def run_pside(blob, ps, group, x, W, mirror, bias=None):
+    """Emulates gin_gemm_tcp.cuh: three column-shifted copies of the padded patch, taps = descriptor offsets."""
+    B, P, K = x.shape
+    N = W.shape[2]
+    R, Q, U = ps['R'], ps['Q'], ps['U']
+    y = np.full((B, P, N), np.nan, dtype=x.dtype)
+    yf = y.reshape(B * P, N)
+    ring = blob[ps['ring_off']:ps['ring_off'] + 10]
+    groups = (B + group - 1) // group
+    for G in range(groups):
+        for t in range(ps['ntiles']):
+            codes = blob[ps['src_off'] + t * U: ps['src_off'] + (t + 1) * U]
+            rows = gather_rows(x, codes, G * group, ring, P)                # [U, K]
+            copies = np.zeros((3, (R + 2) * Q * 8, K), dtype=x.dtype)       # smem image: [copy][cell*8+px]
+            for u in range(U):
+                cell, c = divmod(u, 10)
+                if c <= 7:
+                    copies[0, cell * 8 + c] = rows[u]
+                if 1 <= c <= 8:
+                    copies[1, cell * 8 + c - 1] = rows[u]
+                if c >= 2:
+                    copies[2, cell * 8 + c - 2] = rows[u]
+            acc = np.zeros((TILE, N), dtype=x.dtype)
+            for tap, (di, dj) in enumerate(TAPS):
+                if mirror:
+                    di, dj = -di, -dj
+                start = (1 + di) * Q * 8
+                acc += copies[dj + 1, start:start + TILE] @ W[tap]
+            drow = blob[ps['rows_off'] + t * TILE: ps['rows_off'] + (t + 1) * TILE]
+            for r, d in enumerate(drow):
+                gd = G * group * P + int(d)
+                if gd < B * P:
+                    yf[gd] = acc[r] + (bias if bias is not None else 0)
+    return y
+
+
+def run_side_accumulate(blob, side, group, x, W, y):
+    """Gather-mode pass that ADDS into y (the dgx seam pass)."""
+    B = x.shape[0]
+    yf = y.reshape(B * side['P_dst'], -1)
+    ring = blob[side['ring_off']:side['ring_off'] + 10]
+    groups = (B + group - 1) // group
+    for G in range(groups):
+        for t, (nslots, soff, taps) in enumerate(tiles(blob, side)):
+            acc = np.zeros((TILE, W.shape[2]), dtype=x.dtype)
+            for s in range(nslots):
+                codes = blob[side['src_off'] + soff + s * TILE: side['src_off'] + soff + (s + 1) * TILE]
+                acc += gather_rows(x, codes, G * group, ring, side['P_src']) @ W[taps[s]]
+            rows = blob[side['rows_off'] + t * TILE: side['rows_off'] + (t + 1) * TILE]
+            for r, d in enumerate(rows):
+                if d >= 0:
+                    gd = G * group * side['P_dst'] + int(d)
+                    if gd < B * side['P_dst']:
+                        yf[gd] += acc[r]
+    return y

