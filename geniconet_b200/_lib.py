@@ -53,6 +53,8 @@ _SIGS = {
     'gin_hexconv_wgrad': (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'gin_cast_bf16_bytes': (_sz, [_i, _i, _i]),
     'gin_cast_bf16': (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
+    'gin_cast_bf16_colsum_ws_bytes': (_sz, [_i]),
+    'gin_cast_bf16_colsum': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     'gin_hexconv_fwd_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'gin_hexconv_dgrad_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'gin_hexconv_wgrad_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

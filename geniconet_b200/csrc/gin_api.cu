@@ -16,6 +16,7 @@
 #include "gin_gemm_tcp.cuh"
 #include "gin_wgrad_tcp.cuh"
 #include "gin_loss.cuh"
+#include "gin_narrow.cuh"
 #include "gin_resample.cuh"
 
 static thread_local char g_err[512] = "";
@@ -152,6 +153,13 @@ int gin_hexconv_fwd(const void* plan_host, const void* plan_dev, const float* x,
   if (B == 0) return GIN_OK;
   if (impl == GIN_IMPL_TC) return fail(GIN_ERR_UNSUPPORTED, "the tcgen05 path reads bf16: use gin_cast_bf16 + gin_hexconv_fwd_bf16");
   GinSrcView X{x, (long long)sb, (long long)sp, (long long)sc, h->fwd.P_src};
+  if (impl == GIN_IMPL_AUTO && gin::narrow_supported(Cin, Cout, h->fwd)) {     // xyz input layer: warp-level memory-bound kernel
+    const float* wf = reinterpret_cast<const float*>(reinterpret_cast<const char*>(packed) + packed_off_wf(Cin, Cout));
+    rc = gin::launch_narrow_fwd(plan_words(plan_dev), h->fwd, h->group, X, wf, bias, y, B, Cin, Cout, st);
+    if (rc != GIN_OK) return fail(rc, "narrow forward launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return GIN_OK;
+  }
   return run_gather_gemm_simt(plan_words(plan_dev), h->fwd, h->group, X, reinterpret_cast<const char*>(packed), B, Cin, Cout, false,
                               bias, y, st, Cin, Cout);
 }
@@ -176,7 +184,8 @@ size_t gin_hexconv_wgrad_ws_bytes(int Cin, int Cout) {
 }
 
 static int wgrad_common(const GinConvPlanHdr* h, const void* plan_dev, const float* x, int64_t sb, int64_t sp, int64_t sc, const void* xb,
-                        const void* dyb, const float* dy, float* dW, float* db, void* ws, int B, int Cin, int Cout, cudaStream_t st) {
+                        const void* dyb, const float* dy, float* dW, float* db, void* ws, int B, int Cin, int Cout, cudaStream_t st,
+                        int impl = GIN_IMPL_SIMT) {
   float* dWp = reinterpret_cast<float*>(ws);
   int rc;
   if (cudaMemsetAsync(dWp, 0, (size_t)28 * Cin * Cout, st) != cudaSuccess) return fail(GIN_ERR_CUDA, "memset failed");
@@ -195,6 +204,12 @@ static int wgrad_common(const GinConvPlanHdr* h, const void* plan_dev, const flo
         if (rc != GIN_OK) return fail(rc, "tcgen05 wgrad launch failed: %s", cudaGetErrorString(cudaGetLastError()));
       }
       g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else if (impl == GIN_IMPL_AUTO && gin::narrow_supported(Cin, Cout, side)) {
+      GinSrcView X{x, (long long)sb, (long long)sp, (long long)sc, side.P_src};
+      rc = gin::launch_narrow_wgrad(plan_words(plan_dev), side, h->group, X, dy, dWp, db, B, Cin, Cout, st);   // db comes with it
+      if (rc != GIN_OK) return fail(rc, "narrow wgrad launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      db = nullptr;
     } else {
       GinSrcView X{x, (long long)sb, (long long)sp, (long long)sc, side.P_src};
       const int nblk = ((Cin + gin::WG_TC - 1) / gin::WG_TC) * ((Cout + gin::WG_TC - 1) / gin::WG_TC);
@@ -230,7 +245,7 @@ int gin_hexconv_wgrad(const void* plan_host, const void* plan_dev, const float* 
   const GinConvPlanHdr* h;
   int rc = conv_hdr(plan_host, plan_dev, &h);
   if (rc) return rc;
-  return wgrad_common(h, plan_dev, x, sb, sp, sc, nullptr, nullptr, dy, dW, db, ws, B, Cin, Cout, (cudaStream_t)stream);
+  return wgrad_common(h, plan_dev, x, sb, sp, sc, nullptr, nullptr, dy, dW, db, ws, B, Cin, Cout, (cudaStream_t)stream, impl);
 }
 
 // ------------------------------------------------------------------ bf16 (tcgen05) entry points
@@ -251,6 +266,27 @@ int gin_cast_bf16(const void* plan_host, const void* plan_dev, int which, const 
   gin::cast_bf16_kernel<<<grid_for(n8, 256, 16), 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(xb), plan_words(plan_dev) + side.ring_off,
                                                                 B, side.P_src, C);
   return check_launch("cast_bf16");
+}
+
+size_t gin_cast_bf16_colsum_ws_bytes(int C) { return C <= 0 ? 0 : (size_t)(4 + (size_t)gin::CAST_COLSUM_MAX_CTAS * C) * 4; }
+
+int gin_cast_bf16_colsum(const void* plan_host, const void* plan_dev, int which, const float* x, void* xb, float* colsum, void* ws, int B, int C,
+                         void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!x || !xb || !colsum || !ws || B < 0 || C <= 0 || (C & 7) || (256 % (C >> 3)) || (which != 0 && which != 1))
+    return fail(GIN_ERR_ARG, "gin_cast_bf16_colsum: bad argument (C/8 must divide 256)");
+  const GinConvPlanHdr* h;
+  int rc = conv_hdr(plan_host, plan_dev, &h);
+  if (rc) return rc;
+  if (B == 0) return cudaMemsetAsync(colsum, 0, (size_t)C * 4, st) == cudaSuccess ? GIN_OK : fail(GIN_ERR_CUDA, "memset failed");
+  const GinSide& side = which == 0 ? h->fwd : h->dg;
+  const long long n8 = (long long)B * side.P_src * (C / 8) + 2LL * B * (C / 8);
+  int ctas = grid_for(n8, 256, 4);
+  if (ctas > gin::CAST_COLSUM_MAX_CTAS) ctas = gin::CAST_COLSUM_MAX_CTAS;
+  if (cudaMemsetAsync(ws, 0, 16, st) != cudaSuccess) return fail(GIN_ERR_CUDA, "memset failed");      // the ticket
+  gin::cast_bf16_colsum_kernel<<<ctas, 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(xb), plan_words(plan_dev) + side.ring_off, B,
+                                                      side.P_src, C, colsum, reinterpret_cast<float*>(ws));
+  return check_launch("cast_bf16_colsum");
 }
 
 int gin_hexconv_fwd_bf16(const void* plan_host, const void* plan_dev, const void* xb, const void* packed, const float* bias, float* y, int B,

@@ -103,6 +103,75 @@ cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, co
   }
 }
 
+// Same cast, plus the per-channel column sums of the fp32 input (the conv BIAS gradient db[c] = sum over pixels of
+// dy[., c], losses.backward -> IcoConvS2S.bias.grad): the tensor is being read anyway, so db costs no extra pass.
+// Needs (C/8) | 256 so that a thread keeps the same 8 channels for all of its grid-stride iterations.  Every CTA writes
+// its partial sums to ws[1 + block][C]; the last CTA to finish (ticket in ws[0], reset for the next call) adds them up
+// in a fixed order, so db is deterministic.
+constexpr int CAST_COLSUM_MAX_CTAS = 148 * 4;
+
+__global__ void __launch_bounds__(256)
+cast_bf16_colsum_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, const int32_t* __restrict__ ring, int B, int P, int C,
+                        float* __restrict__ colsum, float* __restrict__ ws) {
+  __shared__ float part[256][9];
+  __shared__ int is_last;
+  const int C8 = C >> 3;
+  const long long n_main = (long long)B * P * C8, n_all = n_main + 2LL * B * C8;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_all; i += (long long)gridDim.x * blockDim.x) {
+    float4 a, b;
+    if (i < n_main) {
+      a = ld4(x + i * 8);
+      b = ld4(x + i * 8 + 4);
+      s[0] += a.x; s[1] += a.y; s[2] += a.z; s[3] += a.w; s[4] += b.x; s[5] += b.y; s[6] += b.z; s[7] += b.w;
+    } else {
+      const long long j = i - n_main;
+      const int c = (int)(j % C8) * 8;
+      const int sp = (int)(j / C8), sample = sp >> 1, pole = sp & 1;
+      a = make_float4(0.f, 0.f, 0.f, 0.f); b = a;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const float* src = x + ((size_t)sample * P + ring[pole * 5 + k]) * C + c;
+        a = fma4(0.2f, ld4(src), a);
+        b = fma4(0.2f, ld4(src + 4), b);
+      }
+    }
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+    o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+    *reinterpret_cast<uint4*>(xb + i * 8) = o;
+  }
+  // channel group of this thread: (threadIdx.x % C8) because C8 | 256 | grid stride
+#pragma unroll
+  for (int k = 0; k < 8; ++k) part[threadIdx.x][k] = s[k];
+  __syncthreads();
+  float* mine = ws + 4 + (size_t)blockIdx.x * C;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const int g = c >> 3, k = c & 7;
+    float acc = 0.f;
+    for (int t = g; t < 256; t += C8) acc += part[t][k];
+    mine[c] = acc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(ws), 1u);
+    is_last = ticket == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float acc = 0.f;
+      for (unsigned b2 = 0; b2 < gridDim.x; ++b2) acc += __ldcg(ws + 4 + (size_t)b2 * C + c);
+      colsum[c] = acc;
+    }
+    if (threadIdx.x == 0) *reinterpret_cast<unsigned*>(ws) = 0u;      // re-arm the ticket
+  }
+}
+
 // ---------------------------------------------------------------- Philox4x32-10 + Box-Muller
 GIN_DEVINL void philox_round(uint32_t c[4], uint32_t k0, uint32_t k1) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;

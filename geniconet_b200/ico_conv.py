@@ -102,8 +102,9 @@ class _CastCache:
 _cast_cache = _CastCache()
 
 
-def cast_bf16(x_cl, plan, which, level, use_cache=False):
-    """bf16 copy [B*P + 2B, C] of a channels-last fp32 map (pixels, then the per-sample pole means)."""
+def cast_bf16(x_cl, plan, which, level, use_cache=False, colsum=None):
+    """bf16 copy [B*P + 2B, C] of a channels-last fp32 map (pixels, then the per-sample pole means).  `colsum` [C]
+    (optional) receives the per-channel sums over all pixels from the same pass (the conv bias gradient)."""
     B, C = x_cl.shape[0], x_cl.shape[1]
     key = (plan.dev_ptr, which)
     if use_cache:
@@ -111,6 +112,11 @@ def cast_bf16(x_cl, plan, which, level, use_cache=False):
         if hit is not None:
             return hit
     out = torch.empty((_lib.lib.gin_cast_bf16_bytes(B, level, C) // 2,), dtype=torch.bfloat16, device=x_cl.device)
+    if colsum is not None:
+        ws = torch.empty((_lib.lib.gin_cast_bf16_colsum_ws_bytes(C),), dtype=torch.uint8, device=x_cl.device)
+        _lib.check(_lib.lib.gin_cast_bf16_colsum(plan.host_ptr, plan.dev_ptr, which, x_cl.data_ptr(), out.data_ptr(), colsum.data_ptr(),
+                                                 ws.data_ptr(), B, C, _stream()), 'gin_cast_bf16_colsum')
+        return out
     _lib.check(_lib.lib.gin_cast_bf16(plan.host_ptr, plan.dev_ptr, which, x_cl.data_ptr(), out.data_ptr(), B, C, _stream()), 'gin_cast_bf16')
     if use_cache:
         _cast_cache.put(x_cl, key, out)
@@ -144,7 +150,7 @@ class _HexConvFn(torch.autograd.Function):
             xs, sb, sp, sc = pixel_strides(x)
             if B > 0:
                 _lib.check(_lib.lib.gin_hexconv_fwd(plan.host_ptr, plan.dev_ptr, xs.data_ptr(), sb, sp, sc, packed.data_ptr(), bias_ptr,
-                                                    y.data_ptr(), B, mod.in_features, mod.out_features, _lib.IMPL_SIMT, _stream()), 'gin_hexconv_fwd')
+                                                    y.data_ptr(), B, mod.in_features, mod.out_features, mod.impl, _stream()), 'gin_hexconv_fwd')
             ctx.strides = (sb, sp, sc)
             ctx.save_for_backward(xs, packed)
         return y
@@ -171,13 +177,18 @@ class _HexConvFn(torch.autograd.Function):
             dx = _new_map(B, mod.in_features, H, W, dev)
         if ctx.tc:
             level_out = mod.subdivisions - (1 if mod.stride == 2 else 0)
-            dyb = cast_bf16(dy, plan, 1, level_out)                  # one cast serves dgrad and wgrad
+            fuse_db = db is not None and 256 % (mod.out_features // 8) == 0
+            dyb = cast_bf16(dy, plan, 1, level_out, colsum=db if fuse_db else None)   # one cast serves dgrad, wgrad and db
+            if fuse_db:
+                db_arg = None
+            else:
+                db_arg = db
             if dx is not None:
                 _lib.check(_lib.lib.gin_hexconv_dgrad_bf16(plan.host_ptr, plan.dev_ptr, dyb.data_ptr(), packed.data_ptr(), dx.data_ptr(),
                                                            B, mod.in_features, mod.out_features, st), 'gin_hexconv_dgrad_bf16')
             if need_w:
                 _lib.check(_lib.lib.gin_hexconv_wgrad_bf16(plan.host_ptr, plan.dev_ptr, xs.data_ptr(), dyb.data_ptr(), dy.data_ptr(),
-                                                           dW.data_ptr(), db.data_ptr() if db is not None else None, ws.data_ptr(),
+                                                           dW.data_ptr(), db_arg.data_ptr() if db_arg is not None else None, ws.data_ptr(),
                                                            B, mod.in_features, mod.out_features, st), 'gin_hexconv_wgrad_bf16')
         else:
             if dx is not None:
@@ -187,7 +198,7 @@ class _HexConvFn(torch.autograd.Function):
                 sb, sp, sc = ctx.strides
                 _lib.check(_lib.lib.gin_hexconv_wgrad(plan.host_ptr, plan.dev_ptr, xs.data_ptr(), sb, sp, sc, dy.data_ptr(),
                                                       dW.data_ptr(), db.data_ptr() if db is not None else None, ws.data_ptr(),
-                                                      B, mod.in_features, mod.out_features, _lib.IMPL_SIMT, st), 'gin_hexconv_wgrad')
+                                                      B, mod.in_features, mod.out_features, mod.impl, st), 'gin_hexconv_wgrad')
         return dx, dW, db, None
 
 
@@ -221,7 +232,9 @@ class IcoConvS2S(torch.nn.Module):
 
     def _packed_weights(self, weight):
         key = (weight.data_ptr(), weight._version, weight.device)
-        if self._packed is None or self._packed_key != key:
+        # under CUDA-graph capture the packing kernel must be part of the graph: the optimizer updates the weights in place
+        # on every replay and no Python runs then
+        if self._packed is None or self._packed_key != key or torch.cuda.is_current_stream_capturing():
             nbytes = _lib.lib.gin_hexconv_packed_bytes(self.in_features, self.out_features)
             # a fresh buffer per weight version: a pending backward may still hold the previous one
             self._packed = torch.empty((nbytes,), dtype=torch.uint8, device=weight.device)

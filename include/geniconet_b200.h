@@ -22,8 +22,9 @@
  *     gin_hexconv_fwd / gin_hexconv_wgrad may instead use arbitrary element strides
  *     (sb, sp, sc) so the NCHW xyz input of models.py:104 needs no transpose.
  *   - corner_mode: 0 = 'zeros', 1 = 'average' (models.py:11, run.py:683).
- *   - the fp32 entry points gin_hexconv_{fwd,dgrad,wgrad} run the exact-fp32 CUDA-core kernels (impl must be
- *     GIN_IMPL_AUTO or GIN_IMPL_SIMT); the tcgen05 implicit GEMM (bf16 operands, fp32 accumulate in TMEM) is
+ *   - the fp32 entry points gin_hexconv_{fwd,dgrad,wgrad} run the exact-fp32 CUDA-core kernels: with GIN_IMPL_AUTO
+ *     the narrow xyz layer (Cin = 3) takes the warp-level memory-bound kernels (gin_narrow.cuh), anything else and
+ *     GIN_IMPL_SIMT the generic fp32 gather-GEMM; the tcgen05 implicit GEMM (bf16 operands, fp32 accumulate in TMEM) is
  *     gin_cast_bf16 + gin_hexconv_*_bf16 and is what the Python layer uses whenever both channel counts are
  *     multiples of 64.
  */
@@ -100,6 +101,12 @@ int gin_hexconv_wgrad(const void* plan_host, const void* plan_dev, const float* 
  * is fp32 in TMEM, outputs are fp32.  Needs Cin % 64 == 0 and Cout % 64 == 0. */
 size_t gin_cast_bf16_bytes(int B, int level, int C);
 int gin_cast_bf16(const void* plan_host, const void* plan_dev, int which, const float* x, void* xb, int B, int C, void* stream);
+/* Same cast fused with the per-channel sums of x over all B*P pixels: with which = 1 this is the conv bias gradient
+ * (IcoConvS2S.bias.grad = sum of dy over batch and pixels), obtained from the pass that reads dy anyway.
+ * Needs (C/8) | 256.  ws: gin_cast_bf16_colsum_ws_bytes(C) bytes of scratch (contents irrelevant). Deterministic. */
+size_t gin_cast_bf16_colsum_ws_bytes(int C);
+int gin_cast_bf16_colsum(const void* plan_host, const void* plan_dev, int which, const float* x, void* xb, float* colsum, void* ws,
+                         int B, int C, void* stream);
 int gin_hexconv_fwd_bf16(const void* plan_host, const void* plan_dev, const void* xb, const void* packed, const float* bias,
                          float* y, int B, int Cin, int Cout, void* stream);
 int gin_hexconv_dgrad_bf16(const void* plan_host, const void* plan_dev, const void* dyb, const void* packed, float* dx,

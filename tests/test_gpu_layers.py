@@ -69,6 +69,23 @@ def test_hexconv_simt_matches_oracle(case):
     _check_conv(cin, cout, stride, level, cm, B, 'simt', RTOL32, ATOL32, layout)
 
 
+NARROW_CASES = [
+    # the xyz input layer (models.py:104) through the warp-level kernels of gin_narrow.cuh (impl 'auto', Cin == 3)
+    (3, 64, 1, 5, 'average', 3, 'nchw'),
+    (3, 64, 1, 5, 'zeros', 2, 'cl'),
+    (3, 64, 1, 2, 'average', 5, 'nchw'),       # level 2: several samples per tile group, ragged batch
+    (3, 64, 1, 1, 'average', 19, 'nchw'),
+    (3, 128, 1, 3, 'average', 3, 'nchw'),
+    (3, 64, 2, 3, 'average', 4, 'nchw'),       # stride 2 uses the same tables
+]
+
+
+@pytest.mark.parametrize('case', NARROW_CASES)
+def test_hexconv_narrow_matches_oracle(case):
+    cin, cout, stride, level, cm, B, layout = case
+    _check_conv(cin, cout, stride, level, cm, B, 'auto', RTOL32, ATOL32, layout)
+
+
 def test_hexconv_empty_batch():
     from geniconet_b200.ico_conv import IcoConvS2S
     mod = IcoConvS2S(8, 8, 1, True, 2, 'average', impl='simt').cuda()

@@ -146,9 +146,16 @@ def test_cuda_path_reproduces_reference_golden():
         last = crit.get_last_losses()
         for a, b in zip(last, g['last_losses']):
             assert abs(a - b) <= max(tol, 1e-4) * max(1.0, abs(b)), (impl, last, g['last_losses'])
+        # a conv bias that feeds a BatchNorm has a mathematically ZERO gradient (the batch mean absorbs it): its golden
+        # "norm" is fp32 rounding noise (~1e-7), so it is only required to stay noise-sized, not to match
+        noise = 1e-5 * max(g['grad_norms'].values())
         for k, p in mod.named_parameters():
             want = g['grad_norms'][k]
-            assert abs(p.grad.norm().item() - want) <= (1e-2 if impl == 'simt' else 0.25) * want + 1e-9, (impl, k)
+            got = p.grad.norm().item()
+            if want < noise:
+                assert got < (10 if impl == 'simt' else 1e3) * noise, (impl, k, got, want)
+            else:
+                assert abs(got - want) <= (1e-2 if impl == 'simt' else 0.25) * want, (impl, k, got, want)
     # the loss kernels alone, all three terms live (losses.py:71-80)
     g3 = gold['p2p_level3']
     gen = torch.Generator().manual_seed(g3['input_seed'])
