@@ -14,6 +14,7 @@
 #include "gin_gemm_simt.cuh"
 #include "gin_gemm_tc.cuh"
 #include "gin_gemm_tcp.cuh"
+#include "gin_conv2.cuh"
 #include "gin_wgrad_tcp.cuh"
 #include "gin_loss.cuh"
 #include "gin_narrow.cuh"
@@ -61,12 +62,14 @@ int grid_for(long long work_items, int threads, int max_waves = 8) {
   return (int)(blocks < cap ? blocks : cap);
 }
 
-// GIN_TC_MODE=gather forces the gather-mode tcgen05 kernels (A/B experiments); default is patch mode where a plan has it
-bool patch_mode_enabled() {
+// GIN_TC_MODE (A/B experiments): "gather" forces the gather-mode tcgen05 kernels, "patch1" the first-generation patch kernels
+// (three shifted copies); default is the second-generation patch kernels wherever a plan has patch tiles
+int tc_mode() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("GIN_TC_MODE"); v = (e && strcmp(e, "gather") == 0) ? 0 : 1; }
-  return v == 1;
+  if (v < 0) { const char* e = getenv("GIN_TC_MODE"); v = (e && strcmp(e, "gather") == 0) ? 0 : (e && strcmp(e, "patch1") == 0) ? 1 : 2; }
+  return v;
 }
+bool patch_mode_enabled() { return tc_mode() >= 1; }
 
 // fp32 CUDA-core path
 int run_gather_gemm_simt(const int32_t* plan_dev, const GinSide& side, int group, GinSrcView X, const char* packed, int B, int K, int N,
@@ -93,7 +96,8 @@ int run_gemm_tc(const int32_t* plan_dev, const GinConvPlanHdr* h, const void* Xb
   const GinPSide& ps = dgrad ? h->pdg : h->pfwd;
   int rc;
   if (h->stride == 1 && patch_mode_enabled() && gin::tcp_supported(ps, K, N)) {
-    rc = gin::launch_patch_gemm_tc(plan_dev, ps, h->group, side.P_dst, Xb, wb, bias, Y, B, K, N, dgrad ? 1 : 0, st);
+    if (tc_mode() == 2 && gin::cv2_supported(ps, K, N)) rc = gin::launch_patch_conv2(plan_dev, ps, h->group, side.P_dst, 2 << h->level_in, Xb, wb, bias, Y, B, K, N, dgrad ? 1 : 0, st);
+    else rc = gin::launch_patch_gemm_tc(plan_dev, ps, h->group, side.P_dst, Xb, wb, bias, Y, B, K, N, dgrad ? 1 : 0, st);
     if (rc != GIN_OK) return fail(rc, "tcgen05 patch-GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (dgrad && h->dgx.ntiles > 0) {       // cross-seam and pole entries, accumulated on top

@@ -46,6 +46,16 @@ GIN_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
+// true on exactly one (elected) lane of a fully converged warp
+GIN_DEVINL bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 GIN_DEVINL void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 GIN_DEVINL void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 GIN_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -113,6 +123,11 @@ GIN_DEVINL uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7
 // 16-byte asynchronous global -> shared copy (LDGSTS); src_bytes == 0 writes zeros instead of reading
 GIN_DEVINL void cp_async16(uint32_t dst_smem, const void* src, bool valid) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+// same, bypassing L1 (the data is read once; with ~200 KB of the SM's 228 KB configured as shared memory the L1 is too small to hold
+// the lines of the cp.async in flight, and allocating them throttles the whole gather)
+GIN_DEVINL void cp_async16_cg(uint32_t dst_smem, const void* src, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(valid ? 16 : 0) : "memory");
 }
 // the mbarrier receives one (pre-counted) arrival once every cp.async issued so far by this thread has landed
 GIN_DEVINL void cp_async_arrive(uint64_t* bar) {

@@ -33,7 +33,17 @@ def run():
 for _ in range(2): run()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(iters): run()
-e1.record(); torch.cuda.synchronize()
+if iters >= 4:          # GPU time only: replay a captured graph of `iters` calls (the Python/ctypes launch path costs ~20-30 us per call)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        st = side.cuda_stream
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(iters): run()
+    g.replay(); torch.cuda.synchronize()
+    e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+else:
+    e0.record()
+    for _ in range(iters): run()
+    e1.record(); torch.cuda.synchronize()
 print('%s %d->%d s%d L%d B%d: %.1f us/iter' % (which, cin, cout, stride, level, B, e0.elapsed_time(e1) * 1e3 / iters))
