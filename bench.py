@@ -177,8 +177,11 @@ def kernel_table(model, B, level, peaks, steps=5):
         def cast_x():
             _lib.check(_lib.lib.gin_cast_bf16(plan.host_ptr, plan.dev_ptr, 0, x.data_ptr(), xb.data_ptr(), B, Ci, st))
 
-        def cast_dy():
-            _lib.check(_lib.lib.gin_cast_bf16(plan.host_ptr, plan.dev_ptr, 1, dy.data_ptr(), dyb.data_ptr(), B, Co, st))
+        cws = torch.empty(_lib.lib.gin_cast_bf16_colsum_ws_bytes(Co), dtype=torch.uint8, device='cuda')
+
+        def cast_dy():          # as in IcoConvS2S.backward: the cast of dy also yields the bias gradient
+            _lib.check(_lib.lib.gin_cast_bf16_colsum(plan.host_ptr, plan.dev_ptr, 1, dy.data_ptr(), dyb.data_ptr(), db.data_ptr(),
+                                                     cws.data_ptr(), B, Co, st))
 
         def fwd():
             _lib.check(_lib.lib.gin_hexconv_fwd_bf16(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), packed.data_ptr(), m.bias.data_ptr(),
@@ -188,8 +191,8 @@ def kernel_table(model, B, level, peaks, steps=5):
             _lib.check(_lib.lib.gin_hexconv_dgrad_bf16(plan.host_ptr, plan.dev_ptr, dyb.data_ptr(), packed.data_ptr(), dx.data_ptr(), B, Ci, Co, st))
 
         def wgrad():
-            _lib.check(_lib.lib.gin_hexconv_wgrad_bf16(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), dyb.data_ptr(), dy.data_ptr(), dW.data_ptr(),
-                                                       db.data_ptr(), ws.data_ptr(), B, Ci, Co, st))
+            _lib.check(_lib.lib.gin_hexconv_wgrad_bf16(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), dyb.data_ptr(), None, dW.data_ptr(),
+                                                       None, ws.data_ptr(), B, Ci, Co, st))
         cast_x()
         cast_dy()
         flops = 2.0 * 7 * Ci * Co * Pout * B
@@ -199,13 +202,25 @@ def kernel_table(model, B, level, peaks, steps=5):
         for tag, fn in (('fwd', fwd), ('dgrad', dgrad), ('wgrad', wgrad), ('cast_x', cast_x), ('cast_dy', cast_dy)):
             for _ in range(2):
                 fn()
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-            ev[0].record()
-            for i in range(steps):
-                fn()
-                ev[i + 1].record()
             torch.cuda.synchronize()
-            ms = statistics.median(ev[i].elapsed_time(ev[i + 1]) for i in range(steps))
+            # device time only: `steps` back-to-back calls replayed as one CUDA graph (issued from Python a call costs
+            # 20-30 us of host time, more than several of these kernels run)
+            side = torch.cuda.Stream()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                st_saved, st = st, side.cuda_stream
+                with torch.cuda.graph(graph, stream=side):
+                    for _ in range(steps):
+                        fn()
+                st = st_saved
+            graph.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
             ent[tag + '_us'] = ms * 1e3
             ent[tag + '_tflops'] = flops / (ms * 1e-3) / 1e12
             ent[tag + '_gbs'] = act_bytes / (ms * 1e-3) / 1e9

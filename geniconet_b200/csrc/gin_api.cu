@@ -15,6 +15,7 @@
 #include "gin_gemm_tc.cuh"
 #include "gin_gemm_tcp.cuh"
 #include "gin_conv2.cuh"
+#include "gin_wgrad2.cuh"
 #include "gin_wgrad_tcp.cuh"
 #include "gin_loss.cuh"
 #include "gin_narrow.cuh"
@@ -182,9 +183,12 @@ int gin_hexconv_dgrad(const void* plan_host, const void* plan_dev, const float* 
                               nullptr, dx, st, Cin, Cout);
 }
 
+// workspace: [dWp: 7*Cin*Cout fp32][split-K partial sums of the second-generation tcgen05 wgrad]
 size_t gin_hexconv_wgrad_ws_bytes(int Cin, int Cout) {
   if (Cin <= 0 || Cout <= 0) return 0;
-  return (size_t)28 * Cin * Cout;
+  size_t n = (size_t)28 * Cin * Cout;
+  if (gin::tc_supported(Cin, Cout)) n += gin::wg2::partial_bytes(Cin, Cout);
+  return n;
 }
 
 static int wgrad_common(const GinConvPlanHdr* h, const void* plan_dev, const float* x, int64_t sb, int64_t sp, int64_t sc, const void* xb,
@@ -192,6 +196,21 @@ static int wgrad_common(const GinConvPlanHdr* h, const void* plan_dev, const flo
                         int impl = GIN_IMPL_SIMT) {
   float* dWp = reinterpret_cast<float*>(ws);
   int rc;
+  if (xb && B > 0 && h->stride == 1 && tc_mode() == 2 && gin::wg2_supported(h->pfwd, Cin, Cout)) {
+    // second-generation patch wgrad: split-K partials in the workspace, reduced (and laid out as dW[Cout][Cin][7]) by a second kernel
+    rc = gin::launch_wgrad_patch2(plan_words(plan_dev), h->pfwd, h->group, h->fwd.P_dst, xb, dyb, dWp + (size_t)7 * Cin * Cout, dW, B, Cin, Cout, st);
+    if (rc != GIN_OK) return fail(rc, "tcgen05 patch wgrad (v2) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    if (db) {
+      if (cudaMemsetAsync(db, 0, (size_t)4 * Cout, st) != cudaSuccess) return fail(GIN_ERR_CUDA, "memset failed");
+      const long long rows = (long long)B * h->fwd.P_dst;
+      int ctas = (int)((rows + 255) / 256);
+      if (ctas > 148 * 2) ctas = 148 * 2;
+      gin::bias_grad_kernel<<<ctas, 256, 0, st>>>(dy, db, rows, Cout, (int)((rows + ctas - 1) / ctas));
+      if ((rc = check_launch("bias_grad"))) return rc;
+    }
+    return GIN_OK;
+  }
   if (cudaMemsetAsync(dWp, 0, (size_t)28 * Cin * Cout, st) != cudaSuccess) return fail(GIN_ERR_CUDA, "memset failed");
   if (db && cudaMemsetAsync(db, 0, (size_t)4 * Cout, st) != cudaSuccess) return fail(GIN_ERR_CUDA, "memset failed");
   if (B > 0) {
