@@ -102,7 +102,7 @@ int run_gemm_tc(const int32_t* plan_dev, const GinConvPlanHdr* h, const void* Xb
     if (rc != GIN_OK) return fail(rc, "tcgen05 patch-GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (dgrad && h->dgx.ntiles > 0) {       // cross-seam and pole entries, accumulated on top
-      rc = gin::launch_gather_gemm_tc(plan_dev, h->dgx, h->group, Xb, wb, nullptr, Y, B, K, N, groups * h->dgx.ntiles, st, 2);
+      rc = gin::launch_gather_gemm_tc(plan_dev, h->dgx, h->group, Xb, wb, nullptr, Y, B, K, N, groups * h->dgx.ntiles, st, 1);
       if (rc != GIN_OK) return fail(rc, "tcgen05 seam pass launch failed: %s", cudaGetErrorString(cudaGetLastError()));
       g_launches.fetch_add(1, std::memory_order_relaxed);
     }
@@ -291,7 +291,7 @@ int gin_cast_bf16(const void* plan_host, const void* plan_dev, int which, const 
   return check_launch("cast_bf16");
 }
 
-size_t gin_cast_bf16_colsum_ws_bytes(int C) { return C <= 0 ? 0 : (size_t)(4 + (size_t)gin::CAST_COLSUM_MAX_CTAS * C) * 4; }
+size_t gin_cast_bf16_colsum_ws_bytes(int C) { return C <= 0 ? 0 : (size_t)gin::CAST_COLSUM_MAX_CTAS * C * 4; }
 
 int gin_cast_bf16_colsum(const void* plan_host, const void* plan_dev, int which, const float* x, void* xb, float* colsum, void* ws, int B, int C,
                          void* stream) {
@@ -304,12 +304,13 @@ int gin_cast_bf16_colsum(const void* plan_host, const void* plan_dev, int which,
   if (B == 0) return cudaMemsetAsync(colsum, 0, (size_t)C * 4, st) == cudaSuccess ? GIN_OK : fail(GIN_ERR_CUDA, "memset failed");
   const GinSide& side = which == 0 ? h->fwd : h->dg;
   const long long n8 = (long long)B * side.P_src * (C / 8) + 2LL * B * (C / 8);
-  int ctas = grid_for(n8, 256, 4);
+  int ctas = grid_for(n8, 256, 2);
   if (ctas > gin::CAST_COLSUM_MAX_CTAS) ctas = gin::CAST_COLSUM_MAX_CTAS;
-  if (cudaMemsetAsync(ws, 0, 16, st) != cudaSuccess) return fail(GIN_ERR_CUDA, "memset failed");      // the ticket
   gin::cast_bf16_colsum_kernel<<<ctas, 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(xb), plan_words(plan_dev) + side.ring_off, B,
-                                                      side.P_src, C, colsum, reinterpret_cast<float*>(ws));
-  return check_launch("cast_bf16_colsum");
+                                                      side.P_src, C, reinterpret_cast<float*>(ws));
+  if ((rc = check_launch("cast_bf16_colsum"))) return rc;
+  gin::colsum_final_kernel<<<(C + 7) / 8, 256, 0, st>>>(reinterpret_cast<const float*>(ws), colsum, C, ctas);
+  return check_launch("colsum_final");
 }
 
 int gin_hexconv_fwd_bf16(const void* plan_host, const void* plan_dev, const void* xb, const void* packed, const float* bias, float* y, int B,

@@ -323,14 +323,14 @@ bool build_conv(int level, int stride, int corner_mode, std::vector<int32_t>& bl
     };
     emit_p(psrc, ring_in, h.pfwd);
     emit_p(pdsrc, ring_out, h.pdg);
-    // ---- the cross-seam remainder of dgrad: ONE ROW PER ENTRY, rows grouped by tap, so every tile is a plain
-    // single-tap GEMM over gathered dy rows (weights fetched once per tile); rows that share a destination pixel are
-    // combined by the kernel's atomic-add epilogue.
+    // ---- the cross-seam remainder of dgrad: one row per BOUNDARY PIXEL carrying all of its cross-seam / pole entries as
+    // slots (rows sorted by slot signature so a tile needs few slots).  A pixel appears in exactly one row, so the pass adds
+    // into dx with a plain read-modify-write after the in-chart pass -- no atomics.
     SideBuild X;
     std::vector<std::vector<Entry>> only;
     std::vector<int> pix;
     for (int v = 0; v < gi.P; ++v)
-      for (const Entry& e : adjx[v]) { only.push_back({e}); pix.push_back(v); }
+      if (!adjx[v].empty()) { only.push_back(adjx[v]); pix.push_back(v); }
     if (!build_side(only, go.P, (int)only.size(), go.s, group, true, X)) return false;
     // build_side numbered the rows 0..only.size()-1 per sample; translate back to pixels of the full map
     for (auto& r : X.rows)

@@ -56,7 +56,7 @@ GIN_DEVINL void stage_tile(const int32_t* __restrict__ plan, const GinSide& side
 // ------------------------------------------------------------------------------------------------ forward
 // CPL = output channels per lane (Cout = 32 * CPL).  W is wf[7][CIN][Cout] fp32.
 template <int CIN, int CPL>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 4)
 fwd_kernel(const int32_t* __restrict__ plan, GinSide side, GinSrcView X, const float* __restrict__ W, const float* __restrict__ bias,
            float* __restrict__ Y, int group, int B, int total_tiles) {
   extern __shared__ __align__(16) float smem_f[];
@@ -127,7 +127,7 @@ fwd_kernel(const int32_t* __restrict__ plan, GinSide side, GinSrcView X, const f
 // ------------------------------------------------------------------------------------------------ wgrad (+ bias grad)
 // dWp is [7][CIN][COUT] (zeroed by the caller), db [COUT] (zeroed by the caller) or null.
 template <int CIN, int CPL>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, CPL <= 2 ? 3 : 2)
 wgrad_kernel(const int32_t* __restrict__ plan, GinSide side, GinSrcView X, const float* __restrict__ dY, float* __restrict__ dWp,
              float* __restrict__ db, int group, int B, int total_tiles) {
   extern __shared__ __align__(16) float smem_f[];
@@ -257,7 +257,7 @@ inline int launch_narrow_fwd(const int32_t* plan_dev, const GinSide& side, int g
                              int B, int Cin, int Cout, cudaStream_t st) {
   const int groups = (B + group - 1) / group, total = groups * side.ntiles;
   const size_t smem = narrow::fwd_smem(Cin, Cout, side.max_slots);
-  const int grid = total < 148 * 2 ? total : 148 * 2;
+  const int grid = total < 148 * 4 ? total : 148 * 4;      // several CTAs per SM hide the table -> value load chain of a tile
   if (Cout == 64) {
     auto k = narrow::fwd_kernel<3, 2>;
     if (narrow_config(k, smem)) return -3;
@@ -274,7 +274,7 @@ inline int launch_narrow_wgrad(const int32_t* plan_dev, const GinSide& side, int
                                int B, int Cin, int Cout, cudaStream_t st) {
   const int groups = (B + group - 1) / group, total = groups * side.ntiles;
   const size_t smem = narrow::wgrad_smem(Cin, Cout, side.max_slots);
-  const int grid = total < 148 * 2 ? total : 148 * 2;
+  const int grid = total < 148 * 3 ? total : 148 * 3;
   if (Cout == 64) {
     auto k = narrow::wgrad_kernel<3, 2>;
     if (narrow_config(k, smem)) return -3;

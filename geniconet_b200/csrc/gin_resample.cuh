@@ -106,15 +106,14 @@ cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, co
 // Same cast, plus the per-channel column sums of the fp32 input (the conv BIAS gradient db[c] = sum over pixels of
 // dy[., c], losses.backward -> IcoConvS2S.bias.grad): the tensor is being read anyway, so db costs no extra pass.
 // Needs (C/8) | 256 so that a thread keeps the same 8 channels for all of its grid-stride iterations.  Every CTA writes
-// its partial sums to ws[1 + block][C]; the last CTA to finish (ticket in ws[0], reset for the next call) adds them up
-// in a fixed order, so db is deterministic.
-constexpr int CAST_COLSUM_MAX_CTAS = 148 * 4;
+// its partial sums to ws[block][C]; colsum_final_kernel adds them in a fixed order, so db is deterministic.  (A single
+// "last CTA" doing that sum serially cost 40 us of pure load latency; the second kernel does it in ~3.)
+constexpr int CAST_COLSUM_MAX_CTAS = 148 * 2;
 
 __global__ void __launch_bounds__(256)
 cast_bf16_colsum_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, const int32_t* __restrict__ ring, int B, int P, int C,
-                        float* __restrict__ colsum, float* __restrict__ ws) {
+                        float* __restrict__ ws) {
   __shared__ float part[256][9];
-  __shared__ int is_last;
   const int C8 = C >> 3;
   const long long n_main = (long long)B * P * C8, n_all = n_main + 2LL * B * C8;
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -147,28 +146,29 @@ cast_bf16_colsum_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__
 #pragma unroll
   for (int k = 0; k < 8; ++k) part[threadIdx.x][k] = s[k];
   __syncthreads();
-  float* mine = ws + 4 + (size_t)blockIdx.x * C;
+  float* mine = ws + (size_t)blockIdx.x * C;
   for (int c = threadIdx.x; c < C; c += 256) {
     const int g = c >> 3, k = c & 7;
     float acc = 0.f;
     for (int t = g; t < 256; t += C8) acc += part[t][k];
     mine[c] = acc;
   }
-  __threadfence();
+}
+
+// colsum[c] = sum_b ws[b][c]: one CTA per 8 columns, 32 row groups of (nblocks / 32) partials each, fixed summation order
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ ws, float* __restrict__ colsum, int C, int nblocks) {
+  __shared__ float red[32][9];
+  const int c = blockIdx.x * 8 + (threadIdx.x & 7), rg = threadIdx.x >> 3;
+  float acc = 0.f;
+  if (c < C)
+    for (int b = rg; b < nblocks; b += 32) acc += __ldg(ws + (size_t)b * C + c);
+  red[rg][threadIdx.x & 7] = acc;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(ws), 1u);
-    is_last = ticket == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    for (int c = threadIdx.x; c < C; c += 256) {
-      float acc = 0.f;
-      for (unsigned b2 = 0; b2 < gridDim.x; ++b2) acc += __ldcg(ws + 4 + (size_t)b2 * C + c);
-      colsum[c] = acc;
-    }
-    if (threadIdx.x == 0) *reinterpret_cast<unsigned*>(ws) = 0u;      // re-arm the ticket
+  if (threadIdx.x < 8 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) t += red[r][threadIdx.x];
+    colsum[c] = t;
   }
 }
 

@@ -250,11 +250,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_patch_kernel(const Params p
   }
 }
 
-// dW[co][ci][tap] = sum over the slices of a unit, in slice order (deterministic); co runs fastest over the threads
+// dW[co][ci][tap] = sum over the slices of a unit (fixed order: deterministic).  A CTA handles 64 consecutive outputs (co runs
+// fastest, so the partial-sum reads are 256-byte rows); its four warp pairs each take every fourth slice and meet in smem.
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int Cin, int Cout, int n_blk, int slices, int n_cblk) {
-  const long long n = 7LL * Cin * Cout;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+  __shared__ float red[4][64];
+  const long long n = 7LL * Cin * Cout;                 // multiple of 64 (Cout % 64 == 0)
+  const int o = threadIdx.x & 63, sg = threadIdx.x >> 6;
+  for (long long i0 = (long long)blockIdx.x * 64; i0 < n; i0 += (long long)gridDim.x * 64) {
+    const long long i = i0 + o;
     const int co = (int)(i % Cout);
     const long long r = i / Cout;
     const int ci = (int)(r % Cin), tap = (int)(r / Cin);
@@ -263,9 +267,17 @@ wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, i
     const int h = (tap == 5 || tap == 0 || tap == 6) ? 1 : 0;
     const int unit = (ci >> 6) + n_cblk * (co / n_blk);
     const float* src = partial + ((size_t)unit * slices * 4 + pr) * BM * n_blk + (size_t)(h * 64 + (ci & 63)) * n_blk + (co % n_blk);
-    float acc = 0.f;
-    for (int s = 0; s < slices; ++s) acc += __ldg(src + (size_t)s * 4 * BM * n_blk);
-    dW[((size_t)co * Cin + ci) * 7 + tap] = acc;
+    float a0 = 0.f, a1 = 0.f;
+    int s = sg;
+    for (; s + 4 < slices; s += 8) {
+      a0 += __ldg(src + (size_t)s * 4 * BM * n_blk);
+      a1 += __ldg(src + (size_t)(s + 4) * 4 * BM * n_blk);
+    }
+    if (s < slices) a0 += __ldg(src + (size_t)s * 4 * BM * n_blk);
+    red[sg][o] = a0 + a1;
+    __syncthreads();
+    if (sg == 0) dW[((size_t)co * Cin + ci) * 7 + tap] = (red[0][o] + red[1][o]) + (red[2][o] + red[3][o]);
+    __syncthreads();
   }
 }
 
@@ -293,8 +305,8 @@ int launch(Params p, float* dW, cudaStream_t st) {
   kern<<<units * slices, NTHREADS, p.stages * stage_bytes + fixed, st>>>(p);
   if (cudaGetLastError() != cudaSuccess) return -3;
   const long long n = 7LL * p.Cin * p.Cout;
-  int blocks = (int)((n + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  int blocks = (int)(n / 64);
+  if (blocks > 148 * 16) blocks = 148 * 16;
   wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(p.partial, dW, p.Cin, p.Cout, N_BLK, slices, p.n_cblk);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

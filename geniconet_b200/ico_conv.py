@@ -100,6 +100,7 @@ class _CastCache:
 
 
 _cast_cache = _CastCache()
+_upsample_cache = _CastCache(size=2)
 
 
 def cast_bf16(x_cl, plan, which, level, use_cache=False, colsum=None):
@@ -298,7 +299,16 @@ class IcoUpsampleS2S(torch.nn.Module):
         self.in_features, self.subdivisions, self.corner_mode = int(in_features), int(subdivisions), corner_mode
 
     def forward(self, x):
-        return _UpsampleFn.apply(x, self)
+        # The layer has no parameters, so two IcoUpsampleS2S of the same geometry applied to the SAME tensor
+        # (upsample00 / upsample10 of a BasicIcoS2SUpBlock, models.py:59-60) produce the same map: the second call returns
+        # the first one's output (autograd adds the two incoming gradients before the single backward).
+        key = (self.subdivisions, self.corner_mode)
+        hit = _upsample_cache.get(x, key)
+        if hit is not None and hit.requires_grad == (x.requires_grad and torch.is_grad_enabled()):
+            return hit
+        y = _UpsampleFn.apply(x, self)
+        _upsample_cache.put(x, key, y)
+        return y
 
     def extra_repr(self):
         return '%d ch, level %d -> %d, corner_mode=%s' % (self.in_features, self.subdivisions, self.subdivisions + 1, self.corner_mode)
