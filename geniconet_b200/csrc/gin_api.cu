@@ -108,6 +108,20 @@ int run_gemm_tc(const int32_t* plan_dev, const GinConvPlanHdr* h, const void* Xb
     }
     return GIN_OK;
   }
+  if (h->stride == 2 && tc_mode() == 2 && gin::cv2_supported(h->p2, K, N)) {
+    // stride 2 in patch mode on the coarse lattice: four parity planes (gin_plan.h: GinP2Side)
+    const int Pf = h->fwd.P_src, Pc = h->fwd.P_dst;
+    if (!dgrad) rc = gin::launch_patch_conv2_s2_fwd(plan_dev, h->p2, h->group, Pf, Pc, 2 << h->level_out, Xb, wb, bias, Y, B, K, N, st);
+    else rc = gin::launch_patch_conv2_s2_dgrad(plan_dev, h->p2, h->group, Pf, Pc, 2 << h->level_in, Xb, wb, Y, B, K, N, st);
+    if (rc != GIN_OK) return fail(rc, "tcgen05 stride-2 patch launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (dgrad && h->dgx.ntiles > 0) {
+      rc = gin::launch_gather_gemm_tc(plan_dev, h->dgx, h->group, Xb, wb, nullptr, Y, B, K, N, groups * h->dgx.ntiles, st, 1);
+      if (rc != GIN_OK) return fail(rc, "tcgen05 seam pass launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    return GIN_OK;
+  }
   rc = gin::launch_gather_gemm_tc(plan_dev, side, h->group, Xb, wb, bias, Y, B, K, N, groups * side.ntiles, st);
   if (rc != GIN_OK) return fail(rc, "tcgen05 gather-GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -196,9 +210,12 @@ static int wgrad_common(const GinConvPlanHdr* h, const void* plan_dev, const flo
                         int impl = GIN_IMPL_SIMT) {
   float* dWp = reinterpret_cast<float*>(ws);
   int rc;
-  if (xb && B > 0 && h->stride == 1 && tc_mode() == 2 && gin::wg2_supported(h->pfwd, Cin, Cout)) {
+  const bool wg2_s1 = h->stride == 1 && gin::wg2_supported(h->pfwd, Cin, Cout), wg2_s2 = h->stride == 2 && gin::wg2_supported(h->p2, Cin, Cout);
+  if (xb && B > 0 && tc_mode() == 2 && (wg2_s1 || wg2_s2)) {
     // second-generation patch wgrad: split-K partials in the workspace, reduced (and laid out as dW[Cout][Cin][7]) by a second kernel
-    rc = gin::launch_wgrad_patch2(plan_words(plan_dev), h->pfwd, h->group, h->fwd.P_dst, xb, dyb, dWp + (size_t)7 * Cin * Cout, dW, B, Cin, Cout, st);
+    float* partial = dWp + (size_t)7 * Cin * Cout;
+    if (wg2_s1) rc = gin::launch_wgrad_patch2(plan_words(plan_dev), h->pfwd, h->group, h->fwd.P_dst, xb, dyb, partial, dW, B, Cin, Cout, st);
+    else rc = gin::launch_wgrad_patch2_s2(plan_words(plan_dev), h->p2, h->group, h->fwd.P_src, h->fwd.P_dst, xb, dyb, partial, dW, B, Cin, Cout, st);
     if (rc != GIN_OK) return fail(rc, "tcgen05 patch wgrad (v2) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     g_launches.fetch_add(2, std::memory_order_relaxed);
     if (db) {

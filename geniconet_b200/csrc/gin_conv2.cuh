@@ -45,22 +45,33 @@ constexpr int STAGE_PITCH = 144;             // epilogue staging: 32 fp32 + 16 b
 constexpr int STAGE_BYTES = EPI_WARPS * 32 * STAGE_PITCH;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
+// A tile is processed as `nplanes` segments.  Each segment stages ONE image (its own source table) per 64-channel chunk and
+// applies its own short tap list to it.  Stride 1: one segment with all seven taps.  Stride-2 forward: four parity planes of
+// the fine input, 1-2 taps each, all accumulated into one output tile.  Stride-2 dgrad: the four parity classes of the fine
+// output, each its own output tile (flush_each) gathered from the same coarse dy image.  (gin_plan.h: GinPSide / GinP2Side.)
 struct Params {
   const int32_t* plan;
-  GinPSide ps;
-  int group, B, K, N, P, W;   // P = pixels per sample (stride 1: same on both sides), W = 2n pixels per chart row
-  const __nv_bfloat16* X;     // [B*P + 2B][K] bf16 (pixels, then pole-mean rows)
+  int U, Q, ntiles;           // patch rows per image, octets per patch row, tiles per sample group
+  int group, B, K, N;
+  int P_src, P_dst;           // pixels per sample of the gathered / written map
+  const __nv_bfloat16* X;     // [B*P_src + 2B][K] bf16 (pixels, then pole-mean rows)
   const __nv_bfloat16* Wt;    // pre-swizzled bf16 tiles [7][K/64][N][64]
   const float* bias;
-  float* Y;                   // [B*P][N] fp32
-  int mirror;                 // 0 forward: tap (di,dj) reads cell (+di,+dj);  1 dgrad: reads (-di,-dj)
+  float* Y;                   // [B*P_dst][N] fp32
+  int nplanes, flush_each;
+  int ntaps[4];
+  int8_t tap_id[4][8];        // weight index of each tap of a segment
+  int16_t tap_row[4][8];      // its start row inside the image (8-row groups are 10 rows apart)
+  int tab_off, tab_tstride, tab_pstride;      // source table of (tile t, segment pl): plan[tab_off + t*tab_tstride + pl*tab_pstride ...]
+  int base_off, base_tstride, base_qstride;   // first destination pixel of octet column q of tile t
+  int dst_row_stride, dst_px_stride, dst_plane_off[4];
   int total_tiles, n_blocks;  // CTA c owns n-block c % n_blocks and tiles c / n_blocks + k * (gridDim.x / n_blocks)
   int a_stage_bytes, a_stages, b_stages, resident;
   int dbg;                    // GIN_DBG bit mask (experiments only): 1 no epilogue stores, 2 no patch loads, 4 no MMAs
 };
 
-__device__ __constant__ int8_t kDi[7] = {0, -1, 1, 0, 0, -1, 1};
-__device__ __constant__ int8_t kDj[7] = {0, 0, 0, -1, 1, 1, -1};
+constexpr int kDi[7] = {0, -1, 1, 0, 0, -1, 1};
+constexpr int kDj[7] = {0, 0, 0, -1, 1, 1, -1};
 
 GIN_DEVINL uint64_t desc_kmajor(uint32_t smem_addr, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -100,7 +111,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-UNIFORM role index: keeps the issuer loops in uniform registers
-  const int U = p.ps.U, Q = p.ps.Q;
+  const int U = p.U, Q = p.Q, NP = p.nplanes;
   const int AS = p.a_stages, BS = p.b_stages;
   constexpr uint32_t TM_COLS = (2 * N_TILE <= 32) ? 32 : 2 * N_TILE;
   const int nb = blockIdx.x % p.n_blocks, n0 = nb * N_TILE;
@@ -117,8 +128,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
     __syncwarp();
     tmem_alloc(tmem_slot, TM_COLS);
   }
-  for (int i = tid; i < p.ps.ntiles * Q; i += NTHREADS)
-    tile_base[i] = __ldg(p.plan + p.ps.rows_off + (i / Q) * BM + (i % Q) * 8);
+  for (int i = tid; i < p.ntiles * Q; i += NTHREADS)
+    tile_base[i] = __ldg(p.plan + p.base_off + (i / Q) * p.base_tstride + (i % Q) * p.base_qstride);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -130,7 +141,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
     const __nv_bfloat16* __restrict__ Xc = p.X + c8 * 8;
     int s = 0, ts = 0;
     uint32_t ph = 0, tph = 0;
-    for (int T = t_first; T < p.total_tiles; T += t_step) {
+    for (int VT = t_first * NP; VT < p.total_tiles * NP; VT = (VT % NP == NP - 1) ? VT + 1 + (t_step - 1) * NP : VT + 1) {
       int v[MAX_ITEMS];
       mbar_wait(&tab_full[ts], tph);
 #pragma unroll
@@ -160,48 +171,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
     const bool leader = elect_one();
     int s = 0, bs = 0;
     uint32_t ph = 0, bph = 0, wc = 0;
-    uint32_t tap_off[7];
-#pragma unroll
-    for (int tap = 0; tap < 7; ++tap) {
-      int di = kDi[tap], dj = kDj[tap];
-      if (p.mirror) { di = -di; dj = -dj; }
-      tap_off[tap] = (uint32_t)(((1 + di) * Q * 10 + (1 + dj)) * 128);
-    }
     if (RESIDENT) mbar_wait(&b_full[0], 0);          // the whole weight slice, loaded once
-    for (int T = t_first; T < p.total_tiles; T += t_step, ++wc) {
-      const uint32_t ab = wc & 1;
-      mbar_wait(&acc_empty[ab], ((wc >> 1) & 1u) ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + ab * N_TILE;
-      for (int kc = 0; kc < kchunks; ++kc) {
-        mbar_wait(&a_full[s], ph);
-        fence_async_smem();                          // cp.async (generic proxy) writes -> visible to the async proxy
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(a_smem + s * p.a_stage_bytes);
-#pragma unroll
-        for (int tap = 0; tap < 7; ++tap) {
-          uint32_t b_addr;
-          if (RESIDENT) b_addr = smem_u32(b_smem + (size_t)(tap * kchunks + kc) * B_TILE);
-          else {
-            mbar_wait(&b_full[bs], bph);
-            tc_fence_after();
-            b_addr = smem_u32(b_smem + (size_t)bs * B_TILE);
-          }
-          const uint64_t da = desc_kmajor(a_addr + tap_off[tap], 1280), db = desc_kmajor(b_addr, 1024);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            if (leader && !(p.dbg & 4)) umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kc | tap | k) != 0);
-          if (!RESIDENT) {
-            if (leader) umma_commit(&b_empty[bs]);
-            if (++bs == BS) { bs = 0; bph ^= 1u; }
-          }
+    for (int T = t_first; T < p.total_tiles; T += t_step) {
+      uint32_t fresh = 1;                            // the next MMA starts a new accumulation
+      for (int pl = 0; pl < NP; ++pl) {
+        const uint32_t ab = wc & 1;
+        if (fresh) {
+          mbar_wait(&acc_empty[ab], ((wc >> 1) & 1u) ^ 1u);
+          tc_fence_after();
         }
-        if (leader) umma_commit(&a_empty[s]);
-        __syncwarp();
-        if (++s == AS) { s = 0; ph ^= 1u; }
+        const uint32_t d_tmem = tmem_base + ab * N_TILE;
+        const int nt = p.ntaps[pl];
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&a_full[s], ph);
+          fence_async_smem();                        // cp.async (generic proxy) writes -> visible to the async proxy
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(a_smem + s * p.a_stage_bytes);
+          for (int j = 0; j < nt; ++j) {
+            const int tap = p.tap_id[pl][j];
+            uint32_t b_addr;
+            if (RESIDENT) b_addr = smem_u32(b_smem + (size_t)(tap * kchunks + kc) * B_TILE);
+            else {
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+              b_addr = smem_u32(b_smem + (size_t)bs * B_TILE);
+            }
+            const uint64_t da = desc_kmajor(a_addr + (uint32_t)p.tap_row[pl][j] * 128u, 1280), db = desc_kmajor(b_addr, 1024);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              if (leader && !(p.dbg & 4)) umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, fresh ^ 1u);
+              fresh = 0;
+            }
+            if (!RESIDENT) {
+              if (leader) umma_commit(&b_empty[bs]);
+              if (++bs == BS) { bs = 0; bph ^= 1u; }
+            }
+          }
+          if (leader) umma_commit(&a_empty[s]);
+          __syncwarp();
+          if (++s == AS) { s = 0; ph ^= 1u; }
+        }
+        if (p.flush_each || pl == NP - 1) {
+          if (leader) umma_commit(&acc_full[ab]);
+          __syncwarp();
+          ++wc;
+          fresh = 1;
+        }
       }
-      if (leader) umma_commit(&acc_full[ab]);
-      __syncwarp();
     }
   } else if (warp == W_WEIGHT) {
     // =========================================================== weight tiles
@@ -214,45 +230,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
         int bs = 0;
         uint32_t bph = 0;
         for (int T = t_first; T < p.total_tiles; T += t_step)
-          for (int kc = 0; kc < kchunks; ++kc)
-            for (int tap = 0; tap < 7; ++tap) {
-              mbar_wait(&b_empty[bs], bph ^ 1u);
-              mbar_arrive_expect_tx(&b_full[bs], B_TILE);
-              bulk_g2s(b_smem + (size_t)bs * B_TILE, p.Wt + (((size_t)tap * kchunks + kc) * p.N + n0) * BK, B_TILE, &b_full[bs]);
-              if (++bs == BS) { bs = 0; bph ^= 1u; }
-            }
+          for (int pl = 0; pl < NP; ++pl)
+            for (int kc = 0; kc < kchunks; ++kc)
+              for (int j = 0; j < p.ntaps[pl]; ++j) {
+                const int tap = p.tap_id[pl][j];
+                mbar_wait(&b_empty[bs], bph ^ 1u);
+                mbar_arrive_expect_tx(&b_full[bs], B_TILE);
+                bulk_g2s(b_smem + (size_t)bs * B_TILE, p.Wt + (((size_t)tap * kchunks + kc) * p.N + n0) * BK, B_TILE, &b_full[bs]);
+                if (++bs == BS) { bs = 0; bph ^= 1u; }
+              }
       }
     }
     __syncwarp();
   } else if (warp == W_TABLE) {
-    // =========================================================== gather tables, resolved TAB_BATCH tiles at a time, up to 8 ahead
-    const long long total_pix = (long long)p.B * p.P;
+    // =========================================================== gather tables, resolved TAB_BATCH segments at a time, up to 8 ahead
+    const long long total_src = (long long)p.B * p.P_src;
     int ts = 0;
     uint32_t tph = 0;
-    for (int T0 = t_first; T0 < p.total_tiles; T0 += TAB_BATCH * t_step) {
-      int code[TAB_BATCH][MAX_ITEMS];
+    const int vt_end = p.total_tiles * NP;
+    auto next_vt = [&](int vt) { return (vt % NP == NP - 1) ? vt + 1 + (t_step - 1) * NP : vt + 1; };
+    for (int VT0 = t_first * NP; VT0 < vt_end;) {
+      int code[TAB_BATCH][MAX_ITEMS], vts[TAB_BATCH];
+      int vt = VT0;
 #pragma unroll
       for (int j = 0; j < TAB_BATCH; ++j) {
-        const int T = T0 + j * t_step;
-        if (T < p.total_tiles) {
-          const int32_t* __restrict__ src_tab = p.plan + p.ps.src_off + (size_t)(T % p.ps.ntiles) * U;
+        vts[j] = vt;
+        if (vt < vt_end) {
+          const int T = vt / NP, pl = vt - T * NP;
+          const int32_t* __restrict__ src_tab = p.plan + p.tab_off + (size_t)(T % p.ntiles) * p.tab_tstride + (size_t)pl * p.tab_pstride;
 #pragma unroll
           for (int it = 0; it < MAX_ITEMS; ++it) {
             const int u = it * 32 + lane;
             code[j][it] = (u < U) ? __ldg(src_tab + u) : GIN_SRC_ZERO;
           }
+          vt = next_vt(vt);
         }
       }
+      VT0 = vt;
 #pragma unroll
       for (int j = 0; j < TAB_BATCH; ++j) {
-        const int T = T0 + j * t_step;
-        if (T < p.total_tiles) {
-          const int G = T / p.ps.ntiles;
-          const long long base = (long long)G * p.group * p.P;
+        if (vts[j] < vt_end) {
+          const int G = (vts[j] / NP) / p.ntiles;
+          const long long base = (long long)G * p.group * p.P_src;
           mbar_wait(&tab_empty[ts], tph ^ 1u);
 #pragma unroll
           for (int it = 0; it < MAX_ITEMS; ++it)
-            tab[ts * TAB_ROWS + it * 32 + lane] = resolve_row(code[j][it], base, total_pix, G * p.group, p.B);
+            tab[ts * TAB_ROWS + it * 32 + lane] = resolve_row(code[j][it], base, total_src, G * p.group, p.B);
           __syncwarp();
           if (lane == 0) mbar_arrive(&tab_full[ts]);
           if (++ts == TAB_SLOTS) { ts = 0; tph ^= 1u; }
@@ -266,14 +289,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
     const int hslab = e >> 2;                         // which of the two warps of this quarter: takes 32-column slabs hslab, hslab+2, ...
     const int row = q * 32 + lane;                    // tile row of this thread: group g = row / 8 = r * Q + oq, pixel px = row % 8
     const int g = row >> 3, r_in = g / Q, oq = g - r_in * Q;
-    const int row_off = r_in * p.W + (row & 7);
+    const int row_off = r_in * p.dst_row_stride + (row & 7) * p.dst_px_stride;
     uint8_t* my_stage = stage_smem + (size_t)e * 32 * STAGE_PITCH;
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;  // store phase: one instruction = four whole 128-byte row segments
-    const long long total_pix = (long long)p.B * p.P;
+    const long long total_pix = (long long)p.B * p.P_dst;
     uint32_t wc = 0;
-    for (int T = t_first; T < p.total_tiles; T += t_step, ++wc) {
-      const int G = T / p.ps.ntiles, t = T - G * p.ps.ntiles;
-      const long long gdl = (long long)G * p.group * p.P + tile_base[t * Q + oq] + row_off;
+    const int nflush = p.flush_each ? NP : 1;
+    for (int T = t_first; T < p.total_tiles; T += t_step)
+    for (int fl = 0; fl < nflush; ++fl, ++wc) {
+      const int G = T / p.ntiles, t = T - G * p.ntiles;
+      const long long gdl = (long long)G * p.group * p.P_dst + tile_base[t * Q + oq] + row_off + p.dst_plane_off[fl];
       const int gd = gdl < total_pix ? (int)gdl : -1; // B*P < 2^31 is checked by the launcher
       const uint32_t ab = wc & 1;
       mbar_wait(&acc_full[ab], (wc >> 1) & 1u);
@@ -315,10 +340,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
 }
 
 // shared-memory plan for one launch; returns false when nothing fits
-inline bool plan_smem(int n_tile, int K, const GinPSide& ps, Params& p, int& total) {
+inline bool plan_smem(int n_tile, int K, int U, int ntiles, int Q, Params& p, int& total) {
   const int b_tile = n_tile * 128, kchunks = K / 64;
-  p.a_stage_bytes = ((ps.U * 128 + 1023) / 1024) * 1024;
-  const int fixed = STAGE_BYTES + TAB_SLOTS * TAB_ROWS * 4 + BAR_BYTES + ps.ntiles * ps.Q * 4 + 16;
+  p.a_stage_bytes = ((U * 128 + 1023) / 1024) * 1024;
+  const int fixed = STAGE_BYTES + TAB_SLOTS * TAB_ROWS * 4 + BAR_BYTES + ntiles * Q * 4 + 16;
   const int budget = SMEM_LIMIT - 1024 - fixed;
   const int resident_bytes = 7 * kchunks * b_tile;
   p.resident = resident_bytes <= 114688 && resident_bytes + 2 * p.a_stage_bytes <= budget;
@@ -340,7 +365,7 @@ inline bool plan_smem(int n_tile, int K, const GinPSide& ps, Params& p, int& tot
 template <int N_TILE>
 int launch(Params p, cudaStream_t st) {
   int smem_total = 0;
-  if (!plan_smem(N_TILE, p.K, p.ps, p, smem_total)) return -4;
+  if (!plan_smem(N_TILE, p.K, p.U, p.ntiles, p.Q, p, smem_total)) return -4;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(patch_conv_kernel<N_TILE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
@@ -359,11 +384,13 @@ int launch(Params p, cudaStream_t st) {
 
 }  // namespace cv2
 
-inline bool cv2_supported(const GinPSide& ps, int K, int N) {
+inline bool cv2_supported(int U, int ntiles, int Q, int K, int N) {
   cv2::Params tmp;
   int total;
-  return ps.ntiles > 0 && ps.U <= cv2::TAB_ROWS && tc_supported(K, N) && cv2::plan_smem(64, K, ps, tmp, total);
+  return ntiles > 0 && U <= cv2::TAB_ROWS && tc_supported(K, N) && cv2::plan_smem(64, K, U, ntiles, Q, tmp, total);
 }
+inline bool cv2_supported(const GinPSide& ps, int K, int N) { return cv2_supported(ps.U, ps.ntiles, ps.Q, K, N); }
+inline bool cv2_supported(const GinP2Side& ps, int K, int N) { return cv2_supported(ps.U, ps.ntiles, ps.Q, K, N); }
 
 // N tile: minimise (rounds of 148 CTAs) x (MMA time per item); a 64-wide tile is shared-memory-bandwidth bound (A 128 B/clk +
 // B 64 B/clk against 128 B/clk), hence the 1.5 penalty
@@ -383,20 +410,78 @@ inline int cv2_pick_ntile(long long tiles, int N) {
   return best;
 }
 
-inline int launch_patch_conv2(const int32_t* plan_dev, const GinPSide& ps, int group, int P, int W, const void* Xb, const void* Wb,
-                              const float* bias, float* Y, int B, int K, int N, int mirror, cudaStream_t st) {
-  cv2::Params p;
-  p.plan = plan_dev; p.ps = ps; p.group = group; p.B = B; p.K = K; p.N = N; p.P = P; p.W = W;
-  p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.Wt = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = bias; p.Y = Y; p.mirror = mirror;
-  if ((long long)B * P + 2LL * B >= 0x7fffffffLL) return -4;
-  const int groups = (B + group - 1) / group;
-  p.total_tiles = groups * ps.ntiles;
+inline int cv2_dispatch(cv2::Params& p, int max_ntile, cudaStream_t st) {
+  if ((long long)p.B * (p.P_src > p.P_dst ? p.P_src : p.P_dst) + 2LL * p.B >= 0x7fffffffLL) return -4;
+  const int groups = (p.B + p.group - 1) / p.group;
+  p.total_tiles = groups * p.ntiles;
   { const char* e = getenv("GIN_DBG"); p.dbg = e ? atoi(e) : 0; }
-  switch (cv2_pick_ntile(p.total_tiles, N)) {
+  int nt = cv2_pick_ntile(p.total_tiles, p.N);
+  while (nt > max_ntile) nt /= 2;
+  switch (nt) {
     case 256: return cv2::launch<256>(p, st);
     case 128: return cv2::launch<128>(p, st);
     default: return cv2::launch<64>(p, st);
   }
+}
+
+// stride 1: forward (mirror 0) / in-chart dgrad (mirror 1: tap (di,dj) reads cell (-di,-dj)); W = 2n pixels per chart row
+inline int launch_patch_conv2(const int32_t* plan_dev, const GinPSide& ps, int group, int P, int W, const void* Xb, const void* Wb,
+                              const float* bias, float* Y, int B, int K, int N, int mirror, cudaStream_t st) {
+  cv2::Params p{};
+  p.plan = plan_dev; p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P; p.P_dst = P;
+  p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.Wt = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = bias; p.Y = Y;
+  p.nplanes = 1; p.flush_each = 0; p.ntaps[0] = 7;
+  for (int t = 0; t < 7; ++t) {
+    const int di = mirror ? -cv2::kDi[t] : cv2::kDi[t], dj = mirror ? -cv2::kDj[t] : cv2::kDj[t];
+    p.tap_id[0][t] = (int8_t)t;
+    p.tap_row[0][t] = (int16_t)((1 + di) * ps.Q * 10 + (1 + dj));
+  }
+  p.tab_off = ps.src_off; p.tab_tstride = ps.U; p.tab_pstride = 0;
+  p.base_off = ps.rows_off; p.base_tstride = GIN_TILE_M; p.base_qstride = 8;
+  p.dst_row_stride = W; p.dst_px_stride = 1;
+  return cv2_dispatch(p, 256, st);
+}
+
+// forward tap -> (parity plane, coarse offset a, b) of a stride-2 convolution (gin_plan.h: GinP2Side)
+constexpr int kS2Plane[7] = {2, 0, 0, 3, 3, 1, 1};
+constexpr int kS2A[7] = {0, 0, 1, 0, 0, 0, 1};
+constexpr int kS2B[7] = {0, 0, 0, -1, 0, 0, -1};
+
+// stride 2 forward: X is the FINE map (P_f pixels per sample), Y the coarse one; Wc = 2n of the coarse level
+inline int launch_patch_conv2_s2_fwd(const int32_t* plan_dev, const GinP2Side& ps, int group, int P_f, int P_c, int Wc, const void* Xb,
+                                     const void* Wb, const float* bias, float* Y, int B, int K, int N, cudaStream_t st) {
+  cv2::Params p{};
+  p.plan = plan_dev; p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P_f; p.P_dst = P_c;
+  p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.Wt = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = bias; p.Y = Y;
+  p.nplanes = 4; p.flush_each = 0;
+  for (int t = 0; t < 7; ++t) {
+    const int pl = kS2Plane[t], j = p.ntaps[pl]++;
+    p.tap_id[pl][j] = (int8_t)t;
+    p.tap_row[pl][j] = (int16_t)((1 + kS2A[t]) * ps.Q * 10 + (1 + kS2B[t]));
+  }
+  p.tab_off = ps.src_off; p.tab_tstride = 4 * ps.U; p.tab_pstride = ps.U;
+  p.base_off = ps.rows_off; p.base_tstride = GIN_TILE_M; p.base_qstride = 8;
+  p.dst_row_stride = Wc; p.dst_px_stride = 1;
+  return cv2_dispatch(p, 256, st);
+}
+
+// stride 2 dgrad, in-chart part: X is the coarse dy (K = Cout channels), Y the fine dx; Wf = 2n of the fine level
+inline int launch_patch_conv2_s2_dgrad(const int32_t* plan_dev, const GinP2Side& ps, int group, int P_f, int P_c, int Wf, const void* dYb,
+                                       const void* Wb, float* dX, int B, int K, int N, cudaStream_t st) {
+  cv2::Params p{};
+  p.plan = plan_dev; p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P_c; p.P_dst = P_f;
+  p.X = reinterpret_cast<const __nv_bfloat16*>(dYb); p.Wt = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = nullptr; p.Y = dX;
+  p.nplanes = 4; p.flush_each = 1;
+  for (int t = 0; t < 7; ++t) {
+    const int pl = kS2Plane[t], j = p.ntaps[pl]++;
+    p.tap_id[pl][j] = (int8_t)t;
+    p.tap_row[pl][j] = (int16_t)((1 - kS2A[t]) * ps.Q * 10 + (1 - kS2B[t]));
+  }
+  p.tab_off = ps.dsrc_off; p.tab_tstride = ps.U; p.tab_pstride = 0;
+  p.base_off = ps.frows_off; p.base_tstride = ps.Q; p.base_qstride = 1;
+  p.dst_row_stride = 2 * Wf; p.dst_px_stride = 2;
+  for (int pl = 0; pl < 4; ++pl) p.dst_plane_off[pl] = (pl >> 1) * Wf + (pl & 1);
+  return cv2_dispatch(p, 256, st);     // two accumulators of N_TILE columns, as everywhere
 }
 
 }  // namespace gin

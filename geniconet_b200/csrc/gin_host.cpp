@@ -323,6 +323,8 @@ bool build_conv(int level, int stride, int corner_mode, std::vector<int32_t>& bl
     };
     emit_p(psrc, ring_in, h.pfwd);
     emit_p(pdsrc, ring_out, h.pdg);
+  }
+  if (level >= 2 && (stride == 1 || go.s >= 2)) {
     // ---- the cross-seam remainder of dgrad: one row per BOUNDARY PIXEL carrying all of its cross-seam / pole entries as
     // slots (rows sorted by slot signature so a tile needs few slots).  A pixel appears in exactly one row, so the pass adds
     // into dx with a plain read-modify-write after the in-chart pass -- no atomics.
@@ -337,6 +339,58 @@ bool build_conv(int level, int stride, int corner_mode, std::vector<int32_t>& bl
       if (r >= 0) { const int sg = r / (int)only.size(), idx = r % (int)only.size(); r = sg * gi.P + pix[idx]; }
     X.P_dst = gi.P;
     emit_side(X, ring_out, h.dgx);
+  }
+  if (stride == 2 && go.s >= 2) {
+    // ---- stride-2 patch tiles on the coarse lattice (see GinP2Side)
+    const int R = (go.s >= 3) ? 8 : 4, Q = 16 / R, octs = go.W / 8, rblocks = go.n / R;
+    struct OctCol { int sg, k, i0, j0; };
+    std::vector<OctCol> cols;
+    for (int sg = 0; sg < group; ++sg)
+      for (int k = 0; k < 5; ++k)
+        for (int bi = 0; bi < rblocks; ++bi)
+          for (int jo = 0; jo < octs; ++jo) cols.push_back({sg, k, bi * R, jo * 8});
+    if (cols.size() % Q) { gin_set_error("hexconv plan: stride-2 octet columns do not tile"); return false; }
+    const int ntiles = (int)cols.size() / Q, U = (R + 2) * Q * 10;
+    std::vector<int32_t> src((size_t)ntiles * 4 * U, GIN_SRC_ZERO), dsrc((size_t)ntiles * U, GIN_SRC_ZERO);
+    std::vector<int32_t> rows((size_t)ntiles * GIN_TILE_M), frows((size_t)ntiles * Q);
+    for (int t = 0; t < ntiles; ++t)
+      for (int q = 0; q < Q; ++q) {
+        const OctCol& oc = cols[(size_t)t * Q + q];
+        for (int ip = 0; ip < R + 2; ++ip)
+          for (int c = 0; c < 10; ++c) {
+            const int I = oc.i0 - 1 + ip, J = oc.j0 - 1 + c;
+            const size_t cell = ((size_t)ip * Q + q) * 10 + c;
+            for (int pl = 0; pl < 4; ++pl) {
+              const int pr = pl >> 1, pc = pl & 1;
+              // cells some forward tap of this plane reads: rows I0 .. I0+R-1 (+1 more for the even-row planes), columns J0 .. J0+7
+              // (-1 more for the odd-column planes)
+              const bool used = ip >= 1 && ip <= (pr == 0 ? R + 1 : R) && c >= (pc == 1 ? 0 : 1) && c <= 8;
+              if (!used) continue;
+              const int fi = 2 * I + pr, fj = 2 * J + pc;
+              if (fi < -1 || fi > gi.n || fj < -1 || fj > gi.W) continue;
+              const int v = gi.source(oc.k, fi, fj);
+              int code = GIN_SRC_ZERO;
+              if (v >= 0 && v < gi.P) code = oc.sg * gi.P + v;
+              else if (v >= gi.P && corner_mode == GIN_CORNER_AVERAGE) code = -2 - (2 * oc.sg + (v - gi.P));
+              src[((size_t)t * 4 + pl) * U + cell] = code;
+            }
+            if (I >= 0 && I < go.n && J >= 0 && J < go.W) dsrc[(size_t)t * U + cell] = oc.sg * go.P + go.vid(oc.k, I, J);
+          }
+        for (int r = 0; r < R; ++r)
+          for (int px = 0; px < 8; ++px)
+            rows[(size_t)t * GIN_TILE_M + ((size_t)r * Q + q) * 8 + px] = oc.sg * go.P + go.vid(oc.k, oc.i0 + r, oc.j0 + px);
+        frows[(size_t)t * Q + q] = oc.sg * gi.P + gi.vid(oc.k, 2 * oc.i0, 2 * oc.j0);
+      }
+    GinP2Side& p2 = h.p2;
+    p2.R = R; p2.Q = Q; p2.U = U; p2.ntiles = ntiles;
+    p2.src_off = (int)blob.size();
+    blob.insert(blob.end(), src.begin(), src.end());
+    p2.dsrc_off = (int)blob.size();
+    blob.insert(blob.end(), dsrc.begin(), dsrc.end());
+    p2.rows_off = (int)blob.size();
+    blob.insert(blob.end(), rows.begin(), rows.end());
+    p2.frows_off = (int)blob.size();
+    blob.insert(blob.end(), frows.begin(), frows.end());
   }
   h.magic = GIN_MAGIC; h.kind = GIN_PLAN_HEXCONV; h.level_in = level; h.level_out = go.s; h.stride = stride;
   h.corner_mode = corner_mode; h.group = group; h.total_words = (int)blob.size();

@@ -43,13 +43,31 @@ struct GinPSide {
   int32_t ring_off, pad_;
 };
 
+// Patch tiles for STRIDE-2 convolutions.  Tiles live on the COARSE (output) lattice: R coarse rows x Q octets, R*Q = 16, and the
+// cells of the coarse padded patch are numbered exactly as in GinPSide (cell (i', q, c) -> row (i'*Q + q)*10 + c).  The fine
+// input is seen as four PARITY PLANES pl = 2*pr + pc: plane pl at coarse cell (I', J') is the fine padded cell (2I'+pr, 2J'+pc).
+// A forward tap (di, dj) reads fine cell (2I+1+di, 2J+dj) = plane ((1+di)&1, dj&1) at coarse offset (a, b):
+//     tap 0 (0,0): plane 2 (0,0)     tap 1 (-1,0): plane 0 (0,0)    tap 2 (1,0): plane 0 (+1,0)    tap 3 (0,-1): plane 3 (0,-1)
+//     tap 4 (0,1): plane 3 (0,0)     tap 5 (-1,1): plane 1 (0,0)    tap 6 (1,-1): plane 1 (+1,-1)
+// so per plane the conv is a 1-2 tap patch conv over one staged image (forward: the planes extend K; wgrad: one tap pair per
+// plane).  dgrad runs the adjoint per plane: the fine pixels of plane pl gather the SAME coarse dy image with offsets (-a, -b).
+struct GinP2Side {
+  int32_t R, Q, U;            // U = (R+2)*Q*10
+  int32_t ntiles;             // per sample group (0 = not available)
+  int32_t src_off;            // int32 src[ntiles][4][U]: fine source code of (plane, cell); GIN_SRC_ZERO where no tap reads it
+  int32_t dsrc_off;           // int32 dsrc[ntiles][U]: coarse dy pixel of the cell, GIN_SRC_ZERO outside the chart (in-chart part of dgrad)
+  int32_t rows_off;           // int32 rows[ntiles][128]: coarse pixel of tile row (r*Q + q)*8 + px
+  int32_t frows_off;          // int32 frows[ntiles][Q]: fine pixel (2*I0, 2*J0_q) of each octet column
+};
+
 struct GinConvPlanHdr {
   int32_t magic, kind, level_in, level_out, stride, corner_mode, group, total_words;
   GinSide fwd;                // y rows gathered from x   (also drives wgrad)
   GinSide dg;                 // dx rows gathered from dy (adjoint of pad o conv)
   GinPSide pfwd;              // stride 1 only: forward in patch mode (halo cells come through the chart stitching)
   GinPSide pdg;               // stride 1 only: in-chart part of dgrad in patch mode (halo cells are zero) ...
-  GinSide dgx;                // ... plus the cross-seam / pole entries, ACCUMULATED on top by a gather-mode pass
+  GinSide dgx;                // ... plus the cross-seam / pole entries, ACCUMULATED on top by a gather-mode pass (both strides)
+  GinP2Side p2;               // stride 2 only: forward / wgrad / in-chart dgrad in patch mode
 };
 
 struct GinUpPlanHdr {

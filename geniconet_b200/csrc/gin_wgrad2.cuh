@@ -32,20 +32,26 @@ constexpr int ATOM = BM * 128;               // one 64-channel atom of the dY ti
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int MAX_CTAS = 148;
 
+// A tile is `nplanes` stages (gin_conv2.cuh: Params): stride 1 has one image and four tap pairs, stride 2 has one image per
+// parity plane of the fine input and ONE tap pair per plane (taps {1,2} {5,6} {0,0} {3,4}); either way four accumulators.
 struct Params {
   const int32_t* plan;
-  GinPSide ps;
-  int group, B, Cin, Cout, P;
-  const __nv_bfloat16* X;      // [B*P + 2B][Cin] bf16
-  const __nv_bfloat16* dY;     // [B*P (+2B)][Cout] bf16
+  int U, Q, ntiles;
+  int group, B, Cin, Cout;
+  int P_src, P_dst;            // pixels per sample of the x map / of the dy map
+  const __nv_bfloat16* X;      // [B*P_src + 2B][Cin] bf16
+  const __nv_bfloat16* dY;     // [B*P_dst (+2B)][Cout] bf16
   float* partial;              // [gridDim.x][4][128][N_BLK] fp32
+  int nplanes;
+  int npairs[4];
+  int16_t pair_row[4][4];      // start row of the pair's first tap inside the image
+  int16_t pair_lbo[4][4];      // rows from the first to the second tap (>= 0: the descriptor's leading byte offset is unsigned)
+  int8_t pair_acc[4][4];       // accumulator (0..3) of the pair
+  int8_t tap_acc[8], tap_half[8];   // where tap t ends up: accumulator and half (rows 0-63 / 64-127)
+  int tab_off, tab_tstride, tab_pstride, rows_off;
   int total_tiles, tiles_per_cta, slices, n_cblk;   // unit = blockIdx.x / slices: ci-block = unit % n_cblk, co-block = unit / n_cblk
   int a_bytes, stages;
 };
-
-// taps sorted by start row inside the single-copy patch (1, 2, 10Q, 10Q+1, 10Q+2, 20Q, 20Q+1 for taps 1 5 3 0 4 6 2) and paired so
-// that the second tap of a pair never starts before the first (the leading byte offset is unsigned): (1,5) (3,0) (4,6) (2,2)
-__device__ __constant__ int8_t kPairTap[4][2] = {{1, 5}, {3, 0}, {4, 6}, {2, 2}};
 
 GIN_DEVINL uint64_t desc_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -81,7 +87,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_patch_kernel(const Params p
   const int unit = blockIdx.x / p.slices, slice = blockIdx.x % p.slices;
   const int ci0 = (unit % p.n_cblk) * 64, co0 = (unit / p.n_cblk) * N_BLK;
   const int T0 = slice * p.tiles_per_cta, T1 = min(T0 + p.tiles_per_cta, p.total_tiles);
-  const int Q = p.ps.Q, U = p.ps.U, NS = p.stages;
+  const int U = p.U, NS = p.stages, NP = p.nplanes;
   constexpr uint32_t TM_COLS = (4 * N_BLK <= 256) ? 256 : 512;
 
   if (warp == W_MMA) {
@@ -106,7 +112,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_patch_kernel(const Params p
     const __nv_bfloat16* __restrict__ Yc = p.dY + co0 + c8 * 8;
     int s = 0, ts = 0;
     uint32_t ph = 0, tph = 0;
-    for (int T = T0; T < T1; ++T) {
+    for (int VT = T0 * NP; VT < T1 * NP; ++VT) {
       int v[MAX_ITEMS], dv[4];
       mbar_wait(&tab_full[ts], tph);
 #pragma unroll
@@ -168,50 +174,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_patch_kernel(const Params p
     // =========================================================== MMA issuer (warp-uniform loop, one elected lane issues)
     constexpr uint32_t idesc = make_idesc_bf16(N_BLK, 1, 1);
     const bool leader = elect_one();
-    uint32_t ta[4], lbo[4];
-#pragma unroll
-    for (int pr = 0; pr < 4; ++pr) {
-      const int a = kPairTap[pr][0], b = kPairTap[pr][1];
-      ta[pr] = (uint32_t)(((1 + cv2::kDi[a]) * Q * 10 + (1 + cv2::kDj[a])) * 128);
-      const uint32_t tb = (uint32_t)(((1 + cv2::kDi[b]) * Q * 10 + (1 + cv2::kDj[b])) * 128);
-      lbo[pr] = tb - ta[pr];
-    }
     int s = 0;
     uint32_t ph = 0;
-    for (int T = T0; T < T1; ++T) {
-      mbar_wait(&full_bar[s], ph);
-      fence_async_smem();
-      tc_fence_after();
-      const uint32_t a_addr = smem_u32(smem + s * stage_bytes), b_addr = a_addr + p.a_bytes;
+    for (int T = T0; T < T1; ++T)
+      for (int pl = 0; pl < NP; ++pl) {
+        mbar_wait(&full_bar[s], ph);
+        fence_async_smem();
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * stage_bytes), b_addr = a_addr + p.a_bytes;
+        const int np = p.npairs[pl];
+        for (int j = 0; j < np; ++j) {
+          const uint32_t ta = (uint32_t)p.pair_row[pl][j] * 128u, lbo = (uint32_t)p.pair_lbo[pl][j] * 128u;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(p.pair_acc[pl][j] * N_BLK);
 #pragma unroll
-      for (int pr = 0; pr < 4; ++pr) {
-#pragma unroll
-        for (int k = 0; k < BM / 16; ++k) {          // 16 pixel rows per MMA = two 8-row groups, 1280 bytes apart in the patch
-          const uint64_t da = desc_mnmajor(a_addr + ta[pr] + k * 2560, lbo[pr], 1280);
-          const uint64_t db = desc_mnmajor(b_addr + k * 2048, ATOM, 1024);
-          if (leader) umma_bf16(tmem_base + (uint32_t)(pr * N_BLK), da, db, idesc, (T > T0) || (k != 0));
+          for (int k = 0; k < BM / 16; ++k) {        // 16 pixel rows per MMA = two 8-row groups, 1280 bytes apart in the patch
+            const uint64_t da = desc_mnmajor(a_addr + ta + k * 2560, lbo, 1280);
+            const uint64_t db = desc_mnmajor(b_addr + k * 2048, ATOM, 1024);
+            if (leader) umma_bf16(d_tmem, da, db, idesc, (T > T0) || (k != 0));
+          }
         }
+        if (leader) umma_commit(&empty_bar[s]);
+        __syncwarp();
+        if (++s == NS) { s = 0; ph ^= 1u; }
       }
-      if (leader) umma_commit(&empty_bar[s]);
-      __syncwarp();
-      if (++s == NS) { s = 0; ph ^= 1u; }
-    }
     if (leader && T1 > T0) umma_commit(accum_bar);
     __syncwarp();
   } else {
-    // =========================================================== gather tables (source rows + dY rows), several tiles ahead
-    const long long total_pix = (long long)p.B * p.P;
+    // =========================================================== gather tables (source rows + dY rows), several stages ahead
+    const long long total_src = (long long)p.B * p.P_src, total_dst = (long long)p.B * p.P_dst;
     int ts = 0;
     uint32_t tph = 0;
-    for (int Tb = T0; Tb < T1; Tb += TAB_BATCH) {
+    for (int Vb = T0 * NP; Vb < T1 * NP; Vb += TAB_BATCH) {
       int code[TAB_BATCH][MAX_ITEMS], rowc[TAB_BATCH][4];
 #pragma unroll
       for (int j = 0; j < TAB_BATCH; ++j) {
-        const int T = Tb + j;
-        if (T < T1) {
-          const int t = T % p.ps.ntiles;
-          const int32_t* __restrict__ src_tab = p.plan + p.ps.src_off + (size_t)t * U;
-          const int32_t* __restrict__ row_tab = p.plan + p.ps.rows_off + t * BM;
+        const int VT = Vb + j;
+        if (VT < T1 * NP) {
+          const int T = VT / NP, pl = VT - T * NP, t = T % p.ntiles;
+          const int32_t* __restrict__ src_tab = p.plan + p.tab_off + (size_t)t * p.tab_tstride + (size_t)pl * p.tab_pstride;
+          const int32_t* __restrict__ row_tab = p.plan + p.rows_off + t * BM;
 #pragma unroll
           for (int it = 0; it < MAX_ITEMS; ++it) {
             const int u = it * 32 + lane;
@@ -223,18 +224,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_patch_kernel(const Params p
       }
 #pragma unroll
       for (int j = 0; j < TAB_BATCH; ++j) {
-        const int T = Tb + j;
-        if (T < T1) {
-          const int G = T / p.ps.ntiles;
-          const long long base = (long long)G * p.group * p.P;
+        const int VT = Vb + j;
+        if (VT < T1 * NP) {
+          const int G = (VT / NP) / p.ntiles;
+          const long long base_s = (long long)G * p.group * p.P_src, base_d = (long long)G * p.group * p.P_dst;
           mbar_wait(&tab_empty[ts], tph ^ 1u);
 #pragma unroll
           for (int it = 0; it < MAX_ITEMS; ++it)
-            tab[ts * TAB_ROWS + it * 32 + lane] = resolve_row(code[j][it], base, total_pix, G * p.group, p.B);
+            tab[ts * TAB_ROWS + it * 32 + lane] = resolve_row(code[j][it], base_s, total_src, G * p.group, p.B);
 #pragma unroll
           for (int ps = 0; ps < 4; ++ps) {
-            const long long gd = base + rowc[j][ps];
-            tab[ts * TAB_ROWS + TAB_SRC + ps * 32 + lane] = (rowc[j][ps] >= 0 && gd < total_pix) ? (int)gd : -1;
+            const long long gd = base_d + rowc[j][ps];
+            tab[ts * TAB_ROWS + TAB_SRC + ps * 32 + lane] = (rowc[j][ps] >= 0 && gd < total_dst) ? (int)gd : -1;
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&tab_full[ts]);
@@ -250,34 +251,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_patch_kernel(const Params p
   }
 }
 
-// dW[co][ci][tap] = sum over the slices of a unit (fixed order: deterministic).  A CTA handles 64 consecutive outputs (co runs
-// fastest, so the partial-sum reads are 256-byte rows); its four warp pairs each take every fourth slice and meet in smem.
+struct TapMap { int8_t acc[8], half[8]; };
+
+// dW[co][ci][tap] = sum over the slices of a unit (fixed order: deterministic); one thread per output, co runs fastest so the
+// partial-sum reads are coalesced rows.  (Splitting the slice loop over several lanes measured slower: the kernel is bound by
+// the 20-40 MB of partials it streams from L2, not by latency.)
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int Cin, int Cout, int n_blk, int slices, int n_cblk) {
-  __shared__ float red[4][64];
-  const long long n = 7LL * Cin * Cout;                 // multiple of 64 (Cout % 64 == 0)
-  const int o = threadIdx.x & 63, sg = threadIdx.x >> 6;
-  for (long long i0 = (long long)blockIdx.x * 64; i0 < n; i0 += (long long)gridDim.x * 64) {
-    const long long i = i0 + o;
+wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int Cin, int Cout, int n_blk, int slices, int n_cblk, TapMap tm) {
+  const long long n = 7LL * Cin * Cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int co = (int)(i % Cout);
     const long long r = i / Cout;
     const int ci = (int)(r % Cin), tap = (int)(r / Cin);
-    // inverse of kPairTap
-    const int pr = (tap == 1 || tap == 5) ? 0 : (tap == 3 || tap == 0) ? 1 : (tap == 4 || tap == 6) ? 2 : 3;
-    const int h = (tap == 5 || tap == 0 || tap == 6) ? 1 : 0;
+    const int pr = tm.acc[tap], h = tm.half[tap];
     const int unit = (ci >> 6) + n_cblk * (co / n_blk);
     const float* src = partial + ((size_t)unit * slices * 4 + pr) * BM * n_blk + (size_t)(h * 64 + (ci & 63)) * n_blk + (co % n_blk);
     float a0 = 0.f, a1 = 0.f;
-    int s = sg;
-    for (; s + 4 < slices; s += 8) {
+    int s = 0;
+    for (; s + 1 < slices; s += 2) {
       a0 += __ldg(src + (size_t)s * 4 * BM * n_blk);
-      a1 += __ldg(src + (size_t)(s + 4) * 4 * BM * n_blk);
+      a1 += __ldg(src + (size_t)(s + 1) * 4 * BM * n_blk);
     }
     if (s < slices) a0 += __ldg(src + (size_t)s * 4 * BM * n_blk);
-    red[sg][o] = a0 + a1;
-    __syncthreads();
-    if (sg == 0) dW[((size_t)co * Cin + ci) * 7 + tap] = (red[0][o] + red[1][o]) + (red[2][o] + red[3][o]);
-    __syncthreads();
+    dW[((size_t)co * Cin + ci) * 7 + tap] = a0 + a1;
   }
 }
 
@@ -289,7 +285,7 @@ int launch(Params p, float* dW, cudaStream_t st) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -3;
     configured = true;
   }
-  p.a_bytes = ((p.ps.U * 128 + 1023) / 1024) * 1024;
+  p.a_bytes = ((p.U * 128 + 1023) / 1024) * 1024;
   const int stage_bytes = p.a_bytes + (N_BLK / 64) * ATOM;
   const int fixed = TAB_SLOTS * TAB_ROWS * 4 + BAR_BYTES + 1024;
   p.stages = (SMEM_LIMIT - fixed) / stage_bytes;
@@ -305,9 +301,11 @@ int launch(Params p, float* dW, cudaStream_t st) {
   kern<<<units * slices, NTHREADS, p.stages * stage_bytes + fixed, st>>>(p);
   if (cudaGetLastError() != cudaSuccess) return -3;
   const long long n = 7LL * p.Cin * p.Cout;
-  int blocks = (int)(n / 64);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(p.partial, dW, p.Cin, p.Cout, N_BLK, slices, p.n_cblk);
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  TapMap tm;
+  for (int t = 0; t < 8; ++t) { tm.acc[t] = p.tap_acc[t]; tm.half[t] = p.tap_half[t]; }
+  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(p.partial, dW, p.Cin, p.Cout, N_BLK, slices, p.n_cblk, tm);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
@@ -321,21 +319,57 @@ inline size_t partial_bytes(int Cin, int Cout) {
 
 }  // namespace wg2
 
-inline bool wg2_supported(const GinPSide& ps, int Cin, int Cout) {
-  return ps.ntiles > 0 && ps.U <= wg2::TAB_SRC && tc_supported(Cin, Cout);
+inline bool wg2_supported(const GinPSide& ps, int Cin, int Cout) { return ps.ntiles > 0 && ps.U <= wg2::TAB_SRC && tc_supported(Cin, Cout); }
+inline bool wg2_supported(const GinP2Side& ps, int Cin, int Cout) { return ps.ntiles > 0 && ps.U <= wg2::TAB_SRC && tc_supported(Cin, Cout); }
+
+inline int wg2_dispatch(wg2::Params& p, float* dW, cudaStream_t st) {
+  const int groups = (p.B + p.group - 1) / p.group;
+  p.total_tiles = groups * p.ntiles;
+  if ((long long)p.B * (p.P_src > p.P_dst ? p.P_src : p.P_dst) + 2LL * p.B >= 0x7fffffffLL) return -4;
+  if (wg2::pick_nblk(p.Cout) == 128) return wg2::launch<128>(p, dW, st);
+  return wg2::launch<64>(p, dW, st);
 }
 
-// writes dW[Cout][Cin][7] directly; `partial` needs wg2::partial_bytes(Cin, Cout) bytes
+// stride 1.  Taps sorted by start row inside the single-copy patch (1, 2, 10Q, 10Q+1, 10Q+2, 20Q, 20Q+1 for taps 1 5 3 0 4 6 2) and
+// paired so that the second tap of a pair never starts before the first: (1,5) (3,0) (4,6) (2,2).
+// Writes dW[Cout][Cin][7] directly; `partial` needs wg2::partial_bytes(Cin, Cout) bytes.
 inline int launch_wgrad_patch2(const int32_t* plan_dev, const GinPSide& ps, int group, int P, const void* Xb, const void* dYb, float* partial,
                                float* dW, int B, int Cin, int Cout, cudaStream_t st) {
-  wg2::Params p;
-  p.plan = plan_dev; p.ps = ps; p.group = group; p.B = B; p.Cin = Cin; p.Cout = Cout; p.P = P;
+  static const int pairs[4][2] = {{1, 5}, {3, 0}, {4, 6}, {2, 2}};
+  wg2::Params p{};
+  p.plan = plan_dev; p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.Cin = Cin; p.Cout = Cout; p.P_src = P; p.P_dst = P;
   p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.dY = reinterpret_cast<const __nv_bfloat16*>(dYb); p.partial = partial;
-  const int groups = (B + group - 1) / group;
-  p.total_tiles = groups * ps.ntiles;
-  if ((long long)B * P + 2LL * B >= 0x7fffffffLL) return -4;
-  if (wg2::pick_nblk(Cout) == 128) return wg2::launch<128>(p, dW, st);
-  return wg2::launch<64>(p, dW, st);
+  p.nplanes = 1; p.npairs[0] = 4;
+  for (int j = 0; j < 4; ++j) {
+    const int a = pairs[j][0], b = pairs[j][1];
+    const int ra = (1 + cv2::kDi[a]) * ps.Q * 10 + (1 + cv2::kDj[a]), rb = (1 + cv2::kDi[b]) * ps.Q * 10 + (1 + cv2::kDj[b]);
+    p.pair_row[0][j] = (int16_t)ra; p.pair_lbo[0][j] = (int16_t)(rb - ra); p.pair_acc[0][j] = (int8_t)j;
+    p.tap_acc[a] = (int8_t)j; p.tap_half[a] = 0;
+    if (b != a) { p.tap_acc[b] = (int8_t)j; p.tap_half[b] = 1; }
+  }
+  p.tab_off = ps.src_off; p.tab_tstride = ps.U; p.tab_pstride = 0; p.rows_off = ps.rows_off;
+  return wg2_dispatch(p, dW, st);
+}
+
+// stride 2: one tap pair per parity plane of the fine input: plane 0 (1,2), plane 1 (5,6), plane 2 (0,0), plane 3 (3,4)
+inline int launch_wgrad_patch2_s2(const int32_t* plan_dev, const GinP2Side& ps, int group, int P_f, int P_c, const void* Xb, const void* dYb,
+                                  float* partial, float* dW, int B, int Cin, int Cout, cudaStream_t st) {
+  static const int pairs[4][2] = {{1, 2}, {5, 6}, {0, 0}, {3, 4}};
+  wg2::Params p{};
+  p.plan = plan_dev; p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.Cin = Cin; p.Cout = Cout; p.P_src = P_f; p.P_dst = P_c;
+  p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.dY = reinterpret_cast<const __nv_bfloat16*>(dYb); p.partial = partial;
+  p.nplanes = 4;
+  for (int pl = 0; pl < 4; ++pl) {
+    const int a = pairs[pl][0], b = pairs[pl][1];
+    const int ra = (1 + kS2A[a]) * ps.Q * 10 + (1 + kS2B[a]), rb = (1 + kS2A[b]) * ps.Q * 10 + (1 + kS2B[b]);
+    if (rb < ra) return -4;
+    p.npairs[pl] = 1;
+    p.pair_row[pl][0] = (int16_t)ra; p.pair_lbo[pl][0] = (int16_t)(rb - ra); p.pair_acc[pl][0] = (int8_t)pl;
+    p.tap_acc[a] = (int8_t)pl; p.tap_half[a] = 0;
+    if (b != a) { p.tap_acc[b] = (int8_t)pl; p.tap_half[b] = 1; }
+  }
+  p.tab_off = ps.src_off; p.tab_tstride = 4 * ps.U; p.tab_pstride = ps.U; p.rows_off = ps.rows_off;
+  return wg2_dispatch(p, dW, st);
 }
 
 }  // namespace gin

@@ -202,3 +202,151 @@ def run_side_accumulate(blob, side, group, x, W, y):
                     if gd < B * side['P_dst']:
                         yf[gd] += acc[r]
     return y
+
+
+# ---------------------------------------------------------------- second-generation patch kernels (gin_conv2.cuh, gin_wgrad2.cuh)
+def image_rows(start, group_rows=10):
+    """Rows of the single-copy patch image read by the 128 tile rows for a tap that starts at `start`."""
+    m = np.arange(TILE)
+    return start + (m // 8) * group_rows + (m % 8)
+
+
+def tap_start(Q, a, b):
+    return (1 + a) * Q * 10 + (1 + b)
+
+
+def run_patch2(blob, ps, group, x, W, mirror, bias=None):
+    """Stride-1 forward (mirror=0) / in-chart dgrad (mirror=1) as gin_conv2.cuh computes it: ONE image per tile in plan order,
+    tap (di,dj) = the rows start + (m/8)*10 + m%8."""
+    B, P, K = x.shape
+    N = W.shape[2]
+    Q, U = ps['Q'], ps['U']
+    y = np.full((B, P, N), np.nan, dtype=x.dtype)
+    yf = y.reshape(B * P, N)
+    ring = blob[ps['ring_off']:ps['ring_off'] + 10]
+    for G in range((B + group - 1) // group):
+        for t in range(ps['ntiles']):
+            img = gather_rows(x, blob[ps['src_off'] + t * U: ps['src_off'] + (t + 1) * U], G * group, ring, P)
+            acc = np.zeros((TILE, N), dtype=x.dtype)
+            for tap, (di, dj) in enumerate(TAPS):
+                if mirror:
+                    di, dj = -di, -dj
+                acc += img[image_rows(tap_start(Q, di, dj))] @ W[tap]
+            # destination rows the way the epilogue computes them: per-octet base pixel + r*W + px
+            base = blob[ps['rows_off'] + t * TILE: ps['rows_off'] + (t + 1) * TILE]
+            n2 = int(round((P / 10) ** 0.5)) * 2
+            for m in range(TILE):
+                g, px = divmod(m, 8)
+                r, q = divmod(g, Q)
+                gd = G * group * P + int(base[q * 8]) + r * n2 + px
+                assert int(base[m]) == int(base[q * 8]) + r * n2 + px
+                if gd < B * P:
+                    yf[gd] = acc[m] + (bias if bias is not None else 0)
+    return y
+
+
+def run_wgrad2(blob, ps, group, x, dy):
+    """gin_wgrad2.cuh: dW[tap] += image[tap rows]^T @ dY tile."""
+    B, P, K = x.shape
+    N = dy.shape[2]
+    Q, U = ps['Q'], ps['U']
+    dW = np.zeros((7, K, N), dtype=x.dtype)
+    dyf = dy.reshape(B * P, N)
+    ring = blob[ps['ring_off']:ps['ring_off'] + 10]
+    for G in range((B + group - 1) // group):
+        for t in range(ps['ntiles']):
+            img = gather_rows(x, blob[ps['src_off'] + t * U: ps['src_off'] + (t + 1) * U], G * group, ring, P)
+            rows = blob[ps['rows_off'] + t * TILE: ps['rows_off'] + (t + 1) * TILE]
+            g = np.zeros((TILE, N), dtype=x.dtype)
+            for m, d in enumerate(rows):
+                if G * group * P + int(d) < B * P:
+                    g[m] = dyf[G * group * P + int(d)]
+            for tap, (di, dj) in enumerate(TAPS):
+                dW[tap] += img[image_rows(tap_start(Q, di, dj))].T @ g
+    return dW
+
+
+# stride 2 (GinP2Side): forward tap -> (parity plane, coarse offset)
+S2_TAP = {0: (2, 0, 0), 1: (0, 0, 0), 2: (0, 1, 0), 3: (3, 0, -1), 4: (3, 0, 0), 5: (1, 0, 0), 6: (1, 1, -1)}
+
+
+def parse_p2(blob):
+    names = ['R', 'Q', 'U', 'ntiles', 'src_off', 'dsrc_off', 'rows_off', 'frows_off']
+    return dict(zip(names, [int(v) for v in blob[48:56]]))
+
+
+def run_p2_fwd(blob, h, p2, x, W, bias=None):
+    """Stride-2 forward: per plane an image gathered from the FINE map, 1-2 taps each, one accumulator."""
+    B, Pf, K = x.shape
+    N = W.shape[2]
+    Pc, group, Q, U = h['fwd']['P_dst'], h['group'], p2['Q'], p2['U']
+    ring = blob[h['fwd']['ring_off']:h['fwd']['ring_off'] + 10]
+    y = np.full((B, Pc, N), np.nan, dtype=x.dtype)
+    yf = y.reshape(B * Pc, N)
+    for G in range((B + group - 1) // group):
+        for t in range(p2['ntiles']):
+            acc = np.zeros((TILE, N), dtype=x.dtype)
+            for pl in range(4):
+                off = p2['src_off'] + (t * 4 + pl) * U
+                img = gather_rows(x, blob[off:off + U], G * group, ring, Pf)
+                for tap, (tpl, a, b) in S2_TAP.items():
+                    if tpl == pl:
+                        acc += img[image_rows(tap_start(Q, a, b))] @ W[tap]
+            rows = blob[p2['rows_off'] + t * TILE: p2['rows_off'] + (t + 1) * TILE]
+            for m, d in enumerate(rows):
+                gd = G * group * Pc + int(d)
+                if gd < B * Pc:
+                    yf[gd] = acc[m] + (bias if bias is not None else 0)
+    return y
+
+
+def run_p2_wgrad(blob, h, p2, x, dy):
+    B, Pf, K = x.shape
+    N = dy.shape[2]
+    Pc, group, Q, U = h['fwd']['P_dst'], h['group'], p2['Q'], p2['U']
+    ring = blob[h['fwd']['ring_off']:h['fwd']['ring_off'] + 10]
+    dW = np.zeros((7, K, N), dtype=x.dtype)
+    dyf = dy.reshape(B * Pc, N)
+    for G in range((B + group - 1) // group):
+        for t in range(p2['ntiles']):
+            rows = blob[p2['rows_off'] + t * TILE: p2['rows_off'] + (t + 1) * TILE]
+            g = np.zeros((TILE, N), dtype=x.dtype)
+            for m, d in enumerate(rows):
+                if G * group * Pc + int(d) < B * Pc:
+                    g[m] = dyf[G * group * Pc + int(d)]
+            for pl in range(4):
+                off = p2['src_off'] + (t * 4 + pl) * U
+                img = gather_rows(x, blob[off:off + U], G * group, ring, Pf)
+                for tap, (tpl, a, b) in S2_TAP.items():
+                    if tpl == pl:
+                        dW[tap] += img[image_rows(tap_start(Q, a, b))].T @ g
+    return dW
+
+
+def run_p2_dgrad(blob, h, p2, dy, Wd):
+    """In-chart part of the stride-2 dgrad: the fine pixels of plane pl gather the coarse dy image with offsets (-a, -b);
+    destination = frows[t][q] + r*2*Wf + 2*px + pr*Wf + pc.  Wd is [7][Cout][Cin]."""
+    B, Pc, K = dy.shape
+    N = Wd.shape[2]
+    Pf, group, Q, U = h['fwd']['P_src'], h['group'], p2['Q'], p2['U']
+    Wf = int(round((Pf / 10) ** 0.5)) * 2
+    dx = np.full((B, Pf, N), np.nan, dtype=dy.dtype)
+    dxf = dx.reshape(B * Pf, N)
+    ring = np.zeros(10, dtype=np.int64)
+    for G in range((B + group - 1) // group):
+        for t in range(p2['ntiles']):
+            img = gather_rows(dy, blob[p2['dsrc_off'] + t * U: p2['dsrc_off'] + (t + 1) * U], G * group, ring, Pc)
+            fr = blob[p2['frows_off'] + t * Q: p2['frows_off'] + (t + 1) * Q]
+            for pl in range(4):
+                pr, pc = pl >> 1, pl & 1
+                acc = np.zeros((TILE, N), dtype=dy.dtype)
+                for tap, (tpl, a, b) in S2_TAP.items():
+                    if tpl == pl:
+                        acc += img[image_rows(tap_start(Q, -a, -b))] @ Wd[tap]
+                for m in range(TILE):
+                    g, px = divmod(m, 8)
+                    r, q = divmod(g, Q)
+                    gd = G * group * Pf + int(fr[q]) + r * 2 * Wf + 2 * px + pr * Wf + pc
+                    if gd < B * Pf:
+                        dxf[gd] = acc[m]
+    return dx

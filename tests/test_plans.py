@@ -38,6 +38,53 @@ def test_hexconv_plan_reproduces_oracle(case):
     assert np.abs(dWe - m.weight.grad.permute(2, 1, 0).numpy()).max() < 1e-10
 
 
+PATCH_CASES = [  # level, stride, corner_mode, B, Cin, Cout
+    (2, 1, 'average', 5, 3, 4), (3, 1, 'average', 2, 3, 2), (3, 1, 'zeros', 1, 2, 3), (4, 1, 'average', 1, 2, 2),
+    (3, 2, 'average', 5, 3, 2), (4, 2, 'average', 2, 2, 3), (4, 2, 'zeros', 1, 2, 2), (5, 2, 'average', 1, 1, 2),
+]
+
+
+@pytest.mark.parametrize('case', PATCH_CASES)
+def test_patch_plan_reproduces_oracle(case):
+    """The patch-mode tables (single-copy image, taps = start rows; stride 2 = four parity planes on the coarse lattice)
+    interpreted as gin_conv2.cuh / gin_wgrad2.cuh interpret them."""
+    lvl, stride, cm, B, Cin, Cout = case
+    torch.manual_seed(1)
+    blob = _lib.plan_blob(_lib.PLAN_HEXCONV, lvl, stride, cm)
+    h = pe.parse_conv_full(blob)
+    m = icocnn_ref.IcoConvS2S(Cin, Cout, stride, True, lvl, cm).double()
+    x = torch.randn(B, Cin, 5 * 2 ** lvl, 2 * 2 ** lvl, dtype=torch.double, requires_grad=True)
+    y = m(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xn = x.detach().permute(0, 2, 3, 1).reshape(B, -1, Cin).numpy()
+    W = m.weight.detach().permute(2, 1, 0).numpy()                      # [7][Cin][Cout]
+    Wd = np.ascontiguousarray(W.transpose(0, 2, 1))                     # [7][Cout][Cin]
+    yn = y.detach().permute(0, 2, 3, 1).reshape(B, -1, Cout).numpy()
+    gyn = gy.permute(0, 2, 3, 1).reshape(B, -1, Cout).numpy()
+    dxn = x.grad.permute(0, 2, 3, 1).reshape(B, -1, Cin).numpy()
+    dWn = m.weight.grad.permute(2, 1, 0).numpy()
+    if stride == 1:
+        ye = pe.run_patch2(blob, h['pfwd'], h['group'], xn, W, 0, m.bias.detach().numpy())
+        dxe = pe.run_patch2(blob, h['pdg'], h['group'], gyn, Wd, 1)
+        dWe = pe.run_wgrad2(blob, h['pfwd'], h['group'], xn, gyn)
+    else:
+        p2 = pe.parse_p2(blob)
+        assert p2['ntiles'] > 0
+        ye = pe.run_p2_fwd(blob, h, p2, xn, W, m.bias.detach().numpy())
+        dxe = pe.run_p2_dgrad(blob, h, p2, gyn, Wd)
+        dWe = pe.run_p2_wgrad(blob, h, p2, xn, gyn)
+    assert np.abs(ye - yn).max() < 1e-12
+    assert not np.isnan(dxe).any()                                      # the in-chart pass writes every input pixel once
+    dxe = pe.run_side_accumulate(blob, h['dgx'], h['group'], gyn, Wd, dxe)   # + cross-seam / pole remainder
+    assert np.abs(dxe - dxn).max() < 1e-12
+    assert np.abs(dWe - dWn).max() < 1e-10
+    # one boundary pixel per seam row: the seam pass may add without atomics
+    rows = blob[h['dgx']['rows_off']:h['dgx']['rows_off'] + h['dgx']['ntiles'] * 128]
+    valid = rows[rows >= 0]
+    assert len(set(valid.tolist())) == len(valid)
+
+
 @pytest.mark.parametrize('lvl', [2, 3, 4, 5])
 def test_dgrad_plan_shape(lvl):
     """Interior rows form pure 7-slot tiles (sorted first); seam rows carry the extra slots; stride 2 needs <= 4."""
