@@ -19,6 +19,7 @@
 #include "gin_wgrad_tcp.cuh"
 #include "gin_loss.cuh"
 #include "gin_narrow.cuh"
+#include "gin_bn.cuh"
 #include "gin_resample.cuh"
 
 static thread_local char g_err[512] = "";
@@ -426,6 +427,71 @@ int gin_kld_bwd(const float* mu, const float* logvar, const float* dout, float s
   gin::kld_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(mu, logvar, dout, scale * (float)(-0.5 / (double)n), dmu,
                                                                          dlogvar, n);
   return check_launch("kld_bwd");
+}
+
+// ------------------------------------------------------------------ fused BatchNorm + activation + operand cast
+size_t gin_bn_ws_bytes(int C) { return C <= 0 ? 0 : (size_t)gin::bn::MAX_CTAS * 2 * C * 4; }
+
+static bool bn_shape_ok(int C) { return C > 0 && (C & 7) == 0 && 256 % (C >> 3) == 0; }
+
+int gin_bn_stats(const float* y, int64_t ld, int64_t rows, int C, const float* gamma, const float* beta, float eps, float momentum,
+                 float* running_mean, float* running_var, float* stat, void* ws, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!y || !stat || !ws || rows <= 0 || !bn_shape_ok(C) || ld < C || (ld & 3)) return fail(GIN_ERR_ARG, "gin_bn_stats: bad argument (C/8 must divide 256)");
+  const int ctas = gin::bn::grid_for_rows(rows * (C >> 3));
+  gin::bn::stats_kernel<<<ctas, 256, 0, st>>>(gin::bn::Src{y, (long long)ld}, rows, C, reinterpret_cast<float*>(ws));
+  int rc = check_launch("bn_stats");
+  if (rc) return rc;
+  gin::bn::stats_final_kernel<<<C / 8, 256, 0, st>>>(reinterpret_cast<const float*>(ws), ctas, rows, C, gamma, beta, eps, momentum, running_mean,
+                                                     running_var, stat);
+  return check_launch("bn_stats_final");
+}
+
+int gin_bn_act_fwd(const float* y1, int64_t ld1, const float* stat1, const float* y2, int64_t ld2, const float* stat2, int relu, void* out_b,
+                   float* out_f, int B, int level, int C, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!y1 || !stat1 || (y2 && !stat2) || (!out_b && !out_f) || B <= 0 || level < 0 || level > 9 || !bn_shape_ok(C))
+    return fail(GIN_ERR_ARG, "gin_bn_act_fwd: bad argument");
+  const int n = 1 << level, P = 10 << (2 * level);
+  const int ctas = gin::bn::grid_for_rows(((long long)B * P + 2LL * B) * (C >> 3));
+  const gin::bn::Src s1{y1, (long long)ld1}, s2{y2, (long long)ld2};
+  if (y2) gin::bn::act_fwd_kernel<true><<<ctas, 256, 0, st>>>(s1, stat1, s2, stat2, relu, reinterpret_cast<__nv_bfloat16*>(out_b), out_f, n, B, P, C);
+  else gin::bn::act_fwd_kernel<false><<<ctas, 256, 0, st>>>(s1, stat1, s2, stat2, relu, reinterpret_cast<__nv_bfloat16*>(out_b), out_f, n, B, P, C);
+  return check_launch("bn_act_fwd");
+}
+
+int gin_bn_act_bwd(const float* dout, int64_t ldg, const void* mask_b, const float* y, int64_t ld, const float* stat, float* bstat, void* dy_b,
+                   int64_t ldo, float* dy_f, int64_t ldf, void* ws, int B, int level, int C, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!dout || !y || !stat || !bstat || !ws || (!dy_b && !dy_f) || B <= 0 || level < 0 || level > 9 || !bn_shape_ok(C))
+    return fail(GIN_ERR_ARG, "gin_bn_act_bwd: bad argument");
+  const int n = 1 << level, P = 10 << (2 * level);
+  const long long rows = (long long)B * P;
+  const gin::bn::Src sy{y, (long long)ld};
+  const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(mask_b);
+  const int ctas = gin::bn::grid_for_rows(rows * (C >> 3));
+  gin::bn::bwd_reduce_kernel<<<ctas, 256, 0, st>>>(dout, ldg, mask, sy, stat, rows, C, reinterpret_cast<float*>(ws));
+  int rc = check_launch("bn_bwd_reduce");
+  if (rc) return rc;
+  gin::bn::bwd_final_kernel<<<C / 8, 256, 0, st>>>(reinterpret_cast<const float*>(ws), ctas, rows, C, bstat);
+  if ((rc = check_launch("bn_bwd_final"))) return rc;
+  gin::bn::bwd_apply_kernel<<<ctas, 256, 0, st>>>(dout, ldg, mask, sy, stat, bstat, reinterpret_cast<__nv_bfloat16*>(dy_b), ldo, dy_f, ldf, n, B, P, C);
+  return check_launch("bn_bwd_apply");
+}
+
+static int up_hdr(const void* plan_host, const void* plan_dev, const GinUpPlanHdr** out);
+
+int gin_upsample_bf16(const void* plan_host, const void* plan_dev, const void* in, int in_is_f32, void* out_b, int B, int C, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!in || !out_b || B <= 0 || C <= 0 || (C & 7)) return fail(GIN_ERR_ARG, "gin_upsample_bf16: bad argument (C must be a multiple of 8)");
+  const GinUpPlanHdr* h;
+  int rc = up_hdr(plan_host, plan_dev, &h);
+  if (rc) return rc;
+  const int ctas = gin::bn::grid_for_rows(((long long)B * h->Pf + 2LL * B) * (C >> 3));
+  const int grid = ctas * 4 > 148 * 8 ? 148 * 8 : ctas * 4;
+  if (in_is_f32) gin::bn::upsample_bf16_kernel<true><<<grid, 256, 0, st>>>(plan_words(plan_dev), in, reinterpret_cast<__nv_bfloat16*>(out_b), 2 << h->level, B, C);
+  else gin::bn::upsample_bf16_kernel<false><<<grid, 256, 0, st>>>(plan_words(plan_dev), in, reinterpret_cast<__nv_bfloat16*>(out_b), 2 << h->level, B, C);
+  return check_launch("upsample_bf16");
 }
 
 static int loss_hdr(const void* plan_host, const void* plan_dev, const GinLossPlanHdr** out) {

@@ -1,0 +1,344 @@
+// Fused BatchNorm(training) + ReLU + residual add + bf16 operand cast around the hex-convs -- SURVEY 8f rank 1.
+//
+// models.py:37-39 / 59-61 evaluate  relu(bn(conv(x)))  and  relu(bn01(conv01(.)) + bn10(conv10(.)))  with stock torch modules:
+// per conv output that is a BatchNorm statistics pass, a normalise pass, a ReLU pass, an add pass and finally the bf16 cast the
+// next tcgen05 conv needs -- about 26 bytes of HBM traffic per element forward and twice that backward.  Here a conv output y
+// (fp32, written once by the conv epilogue) is read by
+//     bn_stats      sum y, sum y^2 per channel                  (4 B / element)
+//     bn_act_fwd    out = relu(y*scale + shift [+ y2*scale2 + shift2]) written ONLY as the bf16 operand copy
+//                   [B*P + 2B][C] (pixels + pole-mean rows) that the next conv gathers from      (4-8 B read, 2 B written)
+// and backward
+//     bn_bwd_reduce sum g, sum g*yhat with g = dout * (out > 0)  (mask from the bf16 copy)       (10 B / element)
+//     bn_bwd_apply  dy = scale * (g - mean(g) - yhat * mean(g*yhat)) written as the bf16 copy dgrad / wgrad read
+// All reductions are two-stage (per-CTA partials, then a fixed-order fp64 final), hence deterministic.
+// Thread layout everywhere: one thread = 8 consecutive channels of one row; (C/8) | 256 so a thread keeps its channels
+// for every grid-stride iteration.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "gin_common.cuh"
+#include "gin_resample.cuh"
+
+namespace gin {
+namespace bn {
+
+constexpr int MAX_CTAS = 148 * 2;
+
+struct Src {               // a [rows][C] fp32 view inside a wider row-major matrix
+  const float* p;
+  long long ld;            // row stride in floats
+};
+
+// pixel e (0..4) of the ring of `pole` on a level with n = 2^level: chart e, first pixel of row 0 / last pixel of row n-1
+GIN_DEVINL int ring_pixel(int n, int pole, int e) { return e * n * 2 * n + (pole ? (n - 1) * 2 * n + 2 * n - 1 : 0); }
+
+GIN_DEVINL void ld8(const float* p, float v[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+GIN_DEVINL void ld8_bf16(const __nv_bfloat16* p, float v[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+GIN_DEVINL void st8_bf16(__nv_bfloat16* p, const float v[8]) {
+  __nv_bfloat162 h[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<uint4*>(h);
+}
+GIN_DEVINL void st8(float* p, const float v[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// block-level: partial[blockIdx][k][C] = sum over this CTA's threads of s_k[8]  (k = 0, 1)
+GIN_DEVINL void block_partials(const float s0[8], const float s1[8], int C, float* __restrict__ partial) {
+  __shared__ float part[2][256][9];
+  const int C8 = C >> 3;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { part[0][threadIdx.x][k] = s0[k]; part[1][threadIdx.x][k] = s1[k]; }
+  __syncthreads();
+  float* mine = partial + (size_t)blockIdx.x * 2 * C;
+  for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    const int w = i / C, c = i - w * C, g = c >> 3, k = c & 7;
+    float acc = 0.f;
+    for (int t = g; t < 256; t += C8) acc += part[w][t][k];
+    mine[i] = acc;
+  }
+}
+
+// final[k][c] (double) = sum_b partial[b][k][c] for the 8 channels of this CTA; returned to threads 0..7 (k = 0) and 8..15 (k = 1)
+GIN_DEVINL double final_sum(const float* __restrict__ partial, int nblocks, int C) {
+  __shared__ double red[16][17];
+  const int j = threadIdx.x & 15, rg = threadIdx.x >> 4;       // j: (k, channel-in-8), rg: 16 row groups
+  const int k = j >> 3, c = blockIdx.x * 8 + (j & 7);
+  double acc = 0.0;
+  if (c < C)
+    for (int b = rg; b < nblocks; b += 16) acc += (double)__ldg(partial + ((size_t)b * 2 + k) * C + c);
+  red[rg][j] = acc;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x < 16)
+#pragma unroll
+    for (int r = 0; r < 16; ++r) t += red[r][threadIdx.x];
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------ forward statistics
+__global__ void __launch_bounds__(256) stats_kernel(Src y, long long rows, int C, float* __restrict__ partial) {
+  const int C8 = C >> 3;
+  const long long n = rows * C8;
+  float s0[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, s1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+    const long long r = i / C8;
+    const int c = (int)(i - r * C8) * 8;
+    float v[8];
+    ld8(y.p + r * y.ld + c, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s0[k] += v[k]; s1[k] = fmaf(v[k], v[k], s1[k]); }
+  }
+  block_partials(s0, s1, C, partial);
+}
+
+// stat[0..3][C] = mean, invstd, scale = gamma*invstd, shift = beta - mean*scale; running statistics updated as torch does
+// (momentum, unbiased variance).  grid = C/8, block = 256.
+__global__ void __launch_bounds__(256)
+stats_final_kernel(const float* __restrict__ partial, int nblocks, long long rows, int C, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                   float* __restrict__ stat) {
+  __shared__ double sums[16];
+  const double t = final_sum(partial, nblocks, C);
+  if (threadIdx.x < 16) sums[threadIdx.x] = t;
+  __syncthreads();
+  const int c = blockIdx.x * 8 + threadIdx.x;
+  if (threadIdx.x < 8 && c < C) {
+    const double mean = sums[threadIdx.x] / (double)rows;
+    double var = sums[8 + threadIdx.x] / (double)rows - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    const float scale = g * invstd;
+    stat[c] = (float)mean; stat[C + c] = invstd; stat[2 * C + c] = scale; stat[3 * C + c] = b - (float)mean * scale;
+    if (running_mean) {
+      const double unbiased = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ forward apply
+// out[row, :] = act(y1*scale1 + shift1 [+ y2*scale2 + shift2]) -> bf16 rows [0, rows) of out_b, per-sample pole means
+// (mean over the pole's five ring pixels of the fp32 values) in rows [rows, rows + 2B), optional fp32 copy out_f.
+template <bool TWO>
+GIN_DEVINL void apply_row(const Src& y1, const Src& y2, long long r, int c, const float sc1[8], const float sh1[8], const float sc2[8],
+                          const float sh2[8], int relu, float o[8]) {
+  float v[8];
+  ld8(y1.p + r * y1.ld + c, v);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) o[k] = fmaf(v[k], sc1[k], sh1[k]);
+  if (TWO) {
+    ld8(y2.p + r * y2.ld + c, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] += fmaf(v[k], sc2[k], sh2[k]);
+  }
+  if (relu) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k], 0.f);
+  }
+}
+
+template <bool TWO>
+__global__ void __launch_bounds__(256)
+act_fwd_kernel(Src y1, const float* __restrict__ stat1, Src y2, const float* __restrict__ stat2, int relu, __nv_bfloat16* __restrict__ out_b,
+               float* __restrict__ out_f, int nlat, int B, int P, int C) {
+  const int C8 = C >> 3;
+  const long long rows = (long long)B * P, n_main = rows * C8, n_all = n_main + 2LL * B * C8;
+  const int c = (int)(threadIdx.x % C8) * 8;            // fixed for this thread: C8 | 256 | grid stride
+  float sc1[8], sh1[8], sc2[8], sh2[8];
+  ld8(stat1 + 2 * C + c, sc1); ld8(stat1 + 3 * C + c, sh1);
+  if (TWO) { ld8(stat2 + 2 * C + c, sc2); ld8(stat2 + 3 * C + c, sh2); }
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n_all; i += gridDim.x * 256LL) {
+    float o[8];
+    if (i < n_main) {
+      const long long r = i / C8;
+      apply_row<TWO>(y1, y2, r, c, sc1, sh1, sc2, sh2, relu, o);
+      if (out_f) st8(out_f + r * C + c, o);
+    } else {
+      const long long j = (i - n_main) / C8;
+      const int sample = (int)(j >> 1), pole = (int)(j & 1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = 0.f;
+      for (int e = 0; e < 5; ++e) {
+        float t[8];
+        apply_row<TWO>(y1, y2, (long long)sample * P + ring_pixel(nlat, pole, e), c, sc1, sh1, sc2, sh2, relu, t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = fmaf(0.2f, t[k], o[k]);
+      }
+    }
+    if (out_b) st8_bf16(out_b + (i / C8) * C + c, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// g = dout * (out > 0) (mask read from the bf16 activation copy; mask == null: no ReLU), yhat = (y - mean) * invstd
+GIN_DEVINL void grad_row(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, const Src& y, long long r, int c,
+                         int C, const float mean[8], const float invstd[8], float g[8], float yh[8]) {
+  ld8(dout + r * ldg + c, g);
+  if (mask) {
+    float m[8];
+    ld8_bf16(mask + r * C + c, m);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] = m[k] > 0.f ? g[k] : 0.f;
+  }
+  float v[8];
+  ld8(y.p + r * y.ld + c, v);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) yh[k] = (v[k] - mean[k]) * invstd[k];
+}
+
+__global__ void __launch_bounds__(256)
+bwd_reduce_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, Src y, const float* __restrict__ stat,
+                  long long rows, int C, float* __restrict__ partial) {
+  const int C8 = C >> 3;
+  const long long n = rows * C8;
+  const int c = (int)(threadIdx.x % C8) * 8;
+  float mean[8], invstd[8];
+  ld8(stat + c, mean); ld8(stat + C + c, invstd);
+  float s0[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, s1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+    float g[8], yh[8];
+    grad_row(dout, ldg, mask, y, i / C8, c, C, mean, invstd, g, yh);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s0[k] += g[k]; s1[k] = fmaf(g[k], yh[k], s1[k]); }
+  }
+  block_partials(s0, s1, C, partial);
+}
+
+// bstat[0..3][C] = dbeta = sum g, dgamma = sum g*yhat, c1 = mean(g), c2 = mean(g*yhat).  grid = C/8.
+__global__ void __launch_bounds__(256)
+bwd_final_kernel(const float* __restrict__ partial, int nblocks, long long rows, int C, float* __restrict__ bstat) {
+  const double t = final_sum(partial, nblocks, C);
+  if (threadIdx.x < 16) {
+    const int k = threadIdx.x >> 3, c = blockIdx.x * 8 + (threadIdx.x & 7);
+    if (c < C) { bstat[k * C + c] = (float)t; bstat[(2 + k) * C + c] = (float)(t / (double)rows); }
+  }
+}
+
+// dy = scale * (g - c1 - yhat*c2) -> bf16 copy (rows + per-sample pole means of dy, row stride ldo) and/or fp32 (row stride ldf)
+__global__ void __launch_bounds__(256)
+bwd_apply_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, Src y, const float* __restrict__ stat,
+                 const float* __restrict__ bstat, __nv_bfloat16* __restrict__ dy_b, long long ldo, float* __restrict__ dy_f, long long ldf,
+                 int nlat, int B, int P, int C) {
+  const int C8 = C >> 3;
+  const long long rows = (long long)B * P, n_main = rows * C8, n_all = n_main + (dy_b ? 2LL * B * C8 : 0);
+  const int c = (int)(threadIdx.x % C8) * 8;
+  float mean[8], invstd[8], scale[8], c1[8], c2[8];
+  ld8(stat + c, mean); ld8(stat + C + c, invstd); ld8(stat + 2 * C + c, scale); ld8(bstat + 2 * C + c, c1); ld8(bstat + 3 * C + c, c2);
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n_all; i += gridDim.x * 256LL) {
+    float o[8];
+    if (i < n_main) {
+      const long long r = i / C8;
+      float g[8], yh[8];
+      grad_row(dout, ldg, mask, y, r, c, C, mean, invstd, g, yh);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = scale[k] * (g[k] - c1[k] - yh[k] * c2[k]);
+      if (dy_f) st8(dy_f + r * ldf + c, o);
+    } else {
+      const long long j = (i - n_main) / C8;
+      const int sample = (int)(j >> 1), pole = (int)(j & 1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = 0.f;
+      for (int e = 0; e < 5; ++e) {
+        float g[8], yh[8];
+        grad_row(dout, ldg, mask, y, (long long)sample * P + ring_pixel(nlat, pole, e), c, C, mean, invstd, g, yh);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = fmaf(0.2f * scale[k], g[k] - c1[k] - yh[k] * c2[k], o[k]);
+      }
+    }
+    if (dy_b) st8_bf16(dy_b + (i / C8) * ldo + c, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ upsample into the operand copy
+// IcoUpsampleS2S whose output exists only as the next convolution's bf16 operand copy [B*Pf + 2B][C] (fine pixels + fine pole
+// means).  The source is the fp32 coarse map [B*Pc][C] (F32 = true: one rounding, like the module-wise path) or its bf16
+// operand copy [B*Pc + 2B][C] (coarse pole means taken from its pole rows).
+template <bool F32>
+GIN_DEVINL void up_fetch_any(const void* __restrict__ xin, const int32_t* __restrict__ cring, long long sample, int B, int Pc, int code, int C, int c,
+                             float v[8]) {
+  if (code == GIN_SRC_ZERO) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = 0.f;
+    return;
+  }
+  if (F32) {
+    const float* x = reinterpret_cast<const float*>(xin) + (size_t)sample * Pc * C + c;
+    if (code >= 0) { ld8(x + (size_t)code * C, v); return; }
+    const int pole = (-2 - code) & 1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = 0.f;
+    for (int e = 0; e < 5; ++e) {
+      float t[8];
+      ld8(x + (size_t)cring[pole * 5 + e] * C, t);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaf(0.2f, t[k], v[k]);
+    }
+  } else {
+    const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(xin);
+    if (code >= 0) ld8_bf16(x + ((size_t)sample * Pc + code) * C + c, v);
+    else ld8_bf16(x + ((size_t)B * Pc + 2 * sample + ((-2 - code) & 1)) * C + c, v);     // the coarse pole-mean row
+  }
+}
+template <bool F32>
+GIN_DEVINL void up_pixel(const int32_t* __restrict__ src, const void* __restrict__ xin, const int32_t* __restrict__ cring, long long sample, int B,
+                         int Pc, int f, int C, int c, float o[8]) {
+  const int s0 = src[2 * f], s1 = src[2 * f + 1];
+  up_fetch_any<F32>(xin, cring, sample, B, Pc, s0, C, c, o);
+  if (s0 != s1) {
+    float t[8];
+    up_fetch_any<F32>(xin, cring, sample, B, Pc, s1, C, c, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = 0.5f * (o[k] + t[k]);
+  }
+}
+template <bool F32>
+__global__ void __launch_bounds__(256)
+upsample_bf16_kernel(const int32_t* __restrict__ plan, const void* __restrict__ xin, __nv_bfloat16* __restrict__ out, int nfine, int B, int C) {
+  const GinUpPlanHdr* h = reinterpret_cast<const GinUpPlanHdr*>(plan);
+  const int Pc = h->Pc, Pf = h->Pf, C8 = C >> 3;
+  const int32_t* src = plan + h->fwd_off;
+  const int32_t* cring = plan + h->ring_off;
+  const long long n_main = (long long)B * Pf * C8, n_all = n_main + 2LL * B * C8;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n_all; i += gridDim.x * 256LL) {
+    const int c = (int)(i % C8) * 8;
+    const long long row = i / C8;
+    float o[8];
+    if (i < n_main) {
+      up_pixel<F32>(src, xin, cring, row / Pf, B, Pc, (int)(row % Pf), C, c, o);
+    } else {
+      const long long j = row - (long long)B * Pf;
+      const int pole = (int)(j & 1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = 0.f;
+      for (int e = 0; e < 5; ++e) {
+        float t[8];
+        up_pixel<F32>(src, xin, cring, j >> 1, B, Pc, ring_pixel(nfine, pole, e), C, c, t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = fmaf(0.2f, t[k], o[k]);
+      }
+    }
+    st8_bf16(out + row * C + c, o);
+  }
+}
+
+inline int grid_for_rows(long long n_threads) {
+  long long b = (n_threads + 255) / 256;
+  if (b < 1) b = 1;
+  return (int)(b < MAX_CTAS ? b : MAX_CTAS);
+}
+
+}  // namespace bn
+}  // namespace gin

@@ -1,0 +1,278 @@
+"""Fused execution of the residual encoder / decoder bodies of models.py.
+
+The module-by-module path (ico_conv.py + torch BatchNorm2d / ReLU / add, exactly what the unmodified models.py runs) moves every
+conv output through five torch kernels before the next conv sees it.  Here a whole chain of
+
+    stem   IcoConvS2S(3 -> C) + BatchNorm2d + ReLU                                   (models.py:104-111)
+    block  BasicIcoS2SDownBlock / BasicIcoS2SUpBlock                                 (models.py:22-62)
+
+runs inside ONE autograd Function whose internal activations exist only as the bf16 operand copies the tcgen05 kernels gather
+from (plus the fp32 conv outputs BatchNorm needs):
+
+  * the two sibling convolutions of a block (conv00 / conv10 read the same input) are one GEMM with concatenated output
+    channels -- forward, wgrad and (concatenated along K, which also adds the two input gradients for free) dgrad;
+  * BatchNorm statistics, normalise + ReLU + residual add + bf16 cast are gin_bn_stats / gin_bn_act_fwd, their backward
+    gin_bn_act_bwd writes the bf16 gradient copy dgrad and wgrad read (include/geniconet_b200.h);
+  * an Up block upsamples once (upsample00 / upsample10 are the same parameter-free map), from the fp32 coarse map straight
+    into the bf16 operand copy of the fine level.
+
+Parameters stay where models.py puts them (conv00.weight, icobn00.weight, ...), so state dicts are unchanged; BatchNorm running
+statistics are updated as torch does.  Training mode only (batch statistics); in eval mode the modules run one by one.
+A conv bias that feeds a BatchNorm has a mathematically zero gradient; the fused path returns exactly zero for it.
+"""
+import torch
+
+from . import _lib
+from .ico_conv import IcoConvS2S, IcoUpsampleS2S, get_plan, _stream, pixel_strides
+
+L = _lib.lib
+
+
+def _P(level):
+    return 10 * 4 ** level
+
+
+def _is_block(m):
+    return hasattr(m, 'conv00') and hasattr(m, 'icobn10')
+
+
+def chain_supported(mods):
+    """True when `mods` is [IcoConvS2S(3->C), BatchNorm2d, ReLU]? + residual blocks with tensor-core channel widths."""
+    mods = list(mods)
+    i = 0
+    if len(mods) >= 3 and isinstance(mods[0], IcoConvS2S) and isinstance(mods[1], torch.nn.BatchNorm2d) and isinstance(mods[2], torch.nn.ReLU):
+        if mods[0].in_features != 3 or mods[0].stride != 1 or mods[0].out_features % 64 or mods[0].bias is None:
+            return False
+        i = 3
+    if i == len(mods):
+        return False
+    if i == 3 and _is_block(mods[3]) and not mods[3]._down:
+        return False                                  # an Up block needs the fp32 map of its input, the stem keeps only the bf16 copy
+    for m in mods[i:]:
+        if not _is_block(m):
+            return False
+        for c in (m.conv00, m.conv01, m.conv10):
+            if c.in_features % 64 or c.out_features % 64 or c.bias is None or 256 % (c.out_features // 8):
+                return False
+        for b in (m.icobn00, m.icobn01, m.icobn10):
+            if not isinstance(b, torch.nn.BatchNorm2d) or not b.affine or not b.track_running_stats or b.momentum is None:
+                return False
+    return True
+
+
+def chain_params(mods):
+    out = []
+    for m in mods:
+        if isinstance(m, IcoConvS2S):
+            out += [m.weight, m.bias]
+        elif isinstance(m, torch.nn.BatchNorm2d):
+            out += [m.weight, m.bias]
+        elif _is_block(m):
+            for c, b in ((m.conv00, m.icobn00), (m.conv01, m.icobn01), (m.conv10, m.icobn10)):
+                out += [c.weight, c.bias, b.weight, b.bias]
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ thin wrappers over the C ABI
+def _empty(n, dtype, dev):
+    return torch.empty(n, dtype=dtype, device=dev)
+
+
+def _pack(w, cin, cout):
+    packed = _empty(L.gin_hexconv_packed_bytes(cin, cout), torch.uint8, w.device)
+    _lib.check(L.gin_hexconv_pack_weights(w.data_ptr(), packed.data_ptr(), cin, cout, _stream()), 'gin_hexconv_pack_weights')
+    return packed
+
+
+def _conv_fwd(plan, xb, packed, bias, B, cin, cout, p_out):
+    y = _empty((B * p_out, cout), torch.float32, xb.device)
+    _lib.check(L.gin_hexconv_fwd_bf16(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), packed.data_ptr(), bias.data_ptr(), y.data_ptr(), B, cin, cout,
+                                      _stream()), 'gin_hexconv_fwd_bf16')
+    return y
+
+
+def _conv_dgrad(plan, dyb, packed, B, cin, cout, p_in):
+    dx = _empty((B * p_in, cin), torch.float32, dyb.device)
+    _lib.check(L.gin_hexconv_dgrad_bf16(plan.host_ptr, plan.dev_ptr, dyb.data_ptr(), packed.data_ptr(), dx.data_ptr(), B, cin, cout, _stream()),
+               'gin_hexconv_dgrad_bf16')
+    return dx
+
+
+def _conv_wgrad(plan, xb, dyb, B, cin, cout):
+    dW = _empty((cout, cin, 7), torch.float32, xb.device)
+    ws = _empty(L.gin_hexconv_wgrad_ws_bytes(cin, cout), torch.uint8, xb.device)
+    _lib.check(L.gin_hexconv_wgrad_bf16(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), dyb.data_ptr(), None, dW.data_ptr(), None, ws.data_ptr(),
+                                        B, cin, cout, _stream()), 'gin_hexconv_wgrad_bf16')
+    return dW
+
+
+def _bn_stats(y, col0, ld, rows, C, bn):
+    stat = _empty(4 * C, torch.float32, y.device)
+    ws = _empty(L.gin_bn_ws_bytes(C), torch.uint8, y.device)
+    _lib.check(L.gin_bn_stats(y.data_ptr() + 4 * col0, ld, rows, C, bn.weight.data_ptr(), bn.bias.data_ptr(), float(bn.eps), float(bn.momentum),
+                              bn.running_mean.data_ptr(), bn.running_var.data_ptr(), stat.data_ptr(), ws.data_ptr(), _stream()), 'gin_bn_stats')
+    bn.num_batches_tracked.add_(1)
+    return stat
+
+
+def _bn_act(y1, col1, ld1, stat1, y2, col2, ld2, stat2, B, level, C, want_b=True, want_f=False):
+    dev = y1.device
+    out_b = _empty(((B * _P(level) + 2 * B), C), torch.bfloat16, dev) if want_b else None
+    out_f = _empty((B * _P(level), C), torch.float32, dev) if want_f else None
+    _lib.check(L.gin_bn_act_fwd(y1.data_ptr() + 4 * col1, ld1, stat1.data_ptr(),
+                                (y2.data_ptr() + 4 * col2) if y2 is not None else None, ld2, stat2.data_ptr() if stat2 is not None else None, 1,
+                                out_b.data_ptr() if want_b else None, out_f.data_ptr() if want_f else None, B, level, C, _stream()), 'gin_bn_act_fwd')
+    return out_b, out_f
+
+
+def _bn_bwd(dout, mask_b, y, col0, ld, stat, B, level, C, dy_b=None, dy_b_col=0, ldo=0, want_f=False):
+    """Returns (bstat [4C]: dbeta, dgamma, ..., dy_f or None); writes the bf16 gradient copy into dy_b[:, dy_b_col:dy_b_col+C]."""
+    dev = dout.device
+    bstat = _empty(4 * C, torch.float32, dev)
+    ws = _empty(L.gin_bn_ws_bytes(C), torch.uint8, dev)
+    dy_f = _empty((B * _P(level), C), torch.float32, dev) if want_f else None
+    _lib.check(L.gin_bn_act_bwd(dout.data_ptr(), C, mask_b.data_ptr() if mask_b is not None else None, y.data_ptr() + 4 * col0, ld,
+                                stat.data_ptr(), bstat.data_ptr(), (dy_b.data_ptr() + 2 * dy_b_col) if dy_b is not None else None, ldo,
+                                dy_f.data_ptr() if want_f else None, C, ws.data_ptr(), B, level, C, _stream()), 'gin_bn_act_bwd')
+    return bstat, dy_f
+
+
+# ------------------------------------------------------------------------------------------------ the chain
+class _Chain(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mods, *params):
+        dev = x.device
+        B = x.shape[0]
+        saved = []                # per stage: dict of what backward needs
+        i = 0
+        act_b, level, C = None, None, None
+        ctx.x_needs_grad = x.requires_grad
+        if isinstance(mods[0], IcoConvS2S):                                  # ---- stem: xyz conv (fp32, warp-level kernels) + BN + ReLU
+            conv, bn = mods[0], mods[1]
+            level, C = conv.subdivisions, conv.out_features
+            plan = get_plan(_lib.PLAN_HEXCONV, level, 1, conv.corner_mode, dev)
+            packed = _pack(conv.weight.detach().contiguous(), 3, C)
+            xs, sb, sp, sc = pixel_strides(x)
+            y = _empty((B * _P(level), C), torch.float32, dev)
+            _lib.check(L.gin_hexconv_fwd(plan.host_ptr, plan.dev_ptr, xs.data_ptr(), sb, sp, sc, packed.data_ptr(), conv.bias.data_ptr(),
+                                         y.data_ptr(), B, 3, C, _lib.IMPL_AUTO, _stream()), 'gin_hexconv_fwd')
+            stat = _bn_stats(y, 0, C, B * _P(level), C, bn)
+            act_b, _ = _bn_act(y, 0, C, stat, None, 0, 0, None, B, level, C)
+            saved.append(dict(kind='stem', plan=plan, xs=xs, strides=(sb, sp, sc), y=y, stat=stat, out_b=act_b, C=C, level=level))
+            i = 3
+        else:                                                                # ---- chain starts on an fp32 map: make the operand copy
+            blk = mods[0]
+            level, C = blk.conv00.subdivisions - (0 if blk._down else 1), blk.conv00.in_features
+            plan = get_plan(_lib.PLAN_HEXCONV, level, 1, blk.conv00.corner_mode, dev)
+            from .ico_conv import as_channels_last, cast_bf16
+            act_b = cast_bf16(as_channels_last(x), plan, 0, level)
+            saved.append(dict(kind='input', level=level, C=C))
+        ctx.in_shape = tuple(x.shape)
+        act_f = None
+        if saved[0]['kind'] == 'input':
+            from .ico_conv import as_channels_last as _acl
+            act_f = _acl(x).permute(0, 2, 3, 1).reshape(-1, C)
+        last = len(mods) - 1
+        out_f = None
+        for j in range(i, len(mods)):
+            blk = mods[j]
+            cm = blk.conv00.corner_mode
+            cin, cout = blk.conv00.in_features, blk.conv00.out_features
+            st = dict(kind='down' if blk._down else 'up', cin=cin, cout=cout, in_level=level)
+            if blk._down:
+                lvl = level - 1
+                plan_a = get_plan(_lib.PLAN_HEXCONV, level, 2, cm, dev)
+                a_b = act_b
+            else:
+                lvl = level + 1
+                up_plan = get_plan(_lib.PLAN_UPSAMPLE, level, 1, blk.upsample00.corner_mode, dev)
+                plan_a = get_plan(_lib.PLAN_HEXCONV, lvl, 1, cm, dev)
+                # upsample straight into the operand copy of the fine level, from the fp32 coarse map (one rounding)
+                a_b = _empty((B * _P(lvl) + 2 * B, cin), torch.bfloat16, dev)
+                _lib.check(L.gin_upsample_bf16(up_plan.host_ptr, up_plan.dev_ptr, act_f.data_ptr(), 1, a_b.data_ptr(), B, cin, _stream()), 'gin_upsample_bf16')
+                st['up_plan'] = up_plan
+            plan_b = get_plan(_lib.PLAN_HEXCONV, lvl, 1, cm, dev)
+            rows = B * _P(lvl)
+            wcat = torch.cat((blk.conv00.weight.detach(), blk.conv10.weight.detach()), 0).contiguous()
+            bcat = torch.cat((blk.conv00.bias.detach(), blk.conv10.bias.detach()), 0)
+            pk_cat = _pack(wcat, cin, 2 * cout)
+            ycat = _conv_fwd(plan_a, a_b, pk_cat, bcat, B, cin, 2 * cout, _P(lvl))          # [rows][conv00 | conv10]
+            stat00 = _bn_stats(ycat, 0, 2 * cout, rows, cout, blk.icobn00)
+            stat10 = _bn_stats(ycat, cout, 2 * cout, rows, cout, blk.icobn10)
+            h_b, _ = _bn_act(ycat, 0, 2 * cout, stat00, None, 0, 0, None, B, lvl, cout)
+            pk01 = _pack(blk.conv01.weight.detach().contiguous(), cout, cout)
+            y01 = _conv_fwd(plan_b, h_b, pk01, blk.conv01.bias.detach(), B, cout, cout, _P(lvl))
+            stat01 = _bn_stats(y01, 0, cout, rows, cout, blk.icobn01)
+            is_last = j == last
+            keep_f = is_last or not mods[j + 1]._down         # an Up block upsamples from the fp32 map (one rounding instead of two)
+            # the bf16 copy of the block output is the ReLU mask of the backward, so it is always produced
+            out_b, out_f = _bn_act(y01, 0, cout, stat01, ycat, cout, 2 * cout, stat10, B, lvl, cout, want_b=True, want_f=keep_f)
+            act_f = out_f
+            st.update(plan_a=plan_a, plan_b=plan_b, a_b=a_b, pk_cat=pk_cat, pk01=pk01, ycat=ycat, y01=y01, h_b=h_b, out_b=out_b,
+                      stat00=stat00, stat01=stat01, stat10=stat10, level=lvl)
+            saved.append(st)
+            act_b, level, C = out_b, lvl, cout
+        ctx.saved, ctx.B, ctx.nparams = saved, B, len(params)
+        n = 2 ** level
+        return out_f.view(B, 5 * n, 2 * n, C).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        B = ctx.B
+        saved = ctx.saved
+        from .ico_conv import as_channels_last
+        d = as_channels_last(d_out).permute(0, 2, 3, 1).reshape(-1, d_out.shape[1])          # fp32 [rows][C], no copy when channels-last
+        if not d.is_contiguous():
+            d = d.contiguous()
+        grads = []                # filled back to front, reversed at the end
+        dx = None
+        for st in reversed(saved):
+            if st['kind'] in ('down', 'up'):
+                cin, cout, lvl = st['cin'], st['cout'], st['level']
+                dev = d.device
+                dycat_b = torch.empty((B * _P(lvl) + 2 * B, 2 * cout), dtype=torch.bfloat16, device=dev)
+                dy01_b = torch.empty((B * _P(lvl) + 2 * B, cout), dtype=torch.bfloat16, device=dev)
+                bs01, _ = _bn_bwd(d, st['out_b'], st['y01'], 0, cout, st['stat01'], B, lvl, cout, dy01_b, 0, cout)
+                bs10, _ = _bn_bwd(d, st['out_b'], st['ycat'], cout, 2 * cout, st['stat10'], B, lvl, cout, dycat_b, cout, 2 * cout)
+                dW01 = _conv_wgrad(st['plan_b'], st['h_b'], dy01_b, B, cout, cout)
+                d_h = _conv_dgrad(st['plan_b'], dy01_b, st['pk01'], B, cout, cout, _P(lvl))
+                bs00, _ = _bn_bwd(d_h, st['h_b'], st['ycat'], 0, 2 * cout, st['stat00'], B, lvl, cout, dycat_b, 0, 2 * cout)
+                dWcat = _conv_wgrad(st['plan_a'], st['a_b'], dycat_b, B, cin, 2 * cout)
+                p_in = _P(lvl + 1) if st['kind'] == 'down' else _P(lvl)
+                d_in = _conv_dgrad(st['plan_a'], dycat_b, st['pk_cat'], B, cin, 2 * cout, p_in)
+                if st['kind'] == 'up':
+                    upp = st['up_plan']
+                    d_prev = torch.empty((B * _P(st['in_level']), cin), dtype=torch.float32, device=dev)
+                    _lib.check(L.gin_upsample_bwd(upp.host_ptr, upp.dev_ptr, d_in.data_ptr(), d_prev.data_ptr(), B, cin, _stream()), 'gin_upsample_bwd')
+                    d_in = d_prev
+                zero_b = torch.zeros(cout, dtype=torch.float32, device=dev)
+                # parameter order of chain_params: conv00 (w, b, gamma, beta), conv01 (...), conv10 (...); appended reversed
+                grads += [bs10[:cout], bs10[cout:2 * cout], zero_b, dWcat[cout:],
+                          bs01[:cout], bs01[cout:2 * cout], zero_b, dW01,
+                          bs00[:cout], bs00[cout:2 * cout], zero_b, dWcat[:cout]]
+                d = d_in
+            elif st['kind'] == 'stem':
+                C, lvl = st['C'], st['level']
+                bs, dy_f = _bn_bwd(d, st['out_b'], st['y'], 0, C, st['stat'], B, lvl, C, want_f=True)
+                plan = st['plan']
+                dW = torch.empty((C, 3, 7), dtype=torch.float32, device=d.device)
+                db = torch.empty((C,), dtype=torch.float32, device=d.device)
+                ws = torch.empty(L.gin_hexconv_wgrad_ws_bytes(3, C), dtype=torch.uint8, device=d.device)
+                sb, sp, sc = st['strides']
+                _lib.check(L.gin_hexconv_wgrad(plan.host_ptr, plan.dev_ptr, st['xs'].data_ptr(), sb, sp, sc, dy_f.data_ptr(), dW.data_ptr(), db.data_ptr(),
+                                               ws.data_ptr(), B, 3, C, _lib.IMPL_AUTO, _stream()), 'gin_hexconv_wgrad')
+                grads += [bs[:C], bs[C:2 * C], db, dW]
+                if ctx.x_needs_grad:
+                    raise RuntimeError('fused chain: gradient with respect to the xyz input is not provided (train with requires_grad=False inputs)')
+            else:   # 'input': gradient of the fp32 map the chain started from
+                n = 2 ** st['level']
+                dx = d.view(B, 5 * n, 2 * n, st['C']).permute(0, 3, 1, 2)
+        grads.reverse()
+        assert len(grads) == ctx.nparams
+        return (dx, None) + tuple(grads)
+
+
+def run_chain(x, mods):
+    """Forward of the module list `mods` (see chain_supported) on the fused path; x fp32 CUDA, returns the fp32 output map."""
+    mods = list(mods)
+    return _Chain.apply(x, mods, *chain_params(mods))

@@ -15,8 +15,32 @@ The unmodified reference file also runs on these layers (through the `icocnn` sh
 """
 import torch
 
+import os
+
+from . import fused as _fused
 from .ico_conv import IcoConvS2S, IcoUpsampleS2S
 from .reparam import reparameterize as _reparameterize
+
+# Fused execution of the encoder / decoder bodies (geniconet_b200/fused.py) in training mode; GIN_FUSED=0 or
+# set_fused(False) runs every module on its own, exactly as the unmodified reference models.py does.
+_FUSED = os.environ.get('GIN_FUSED', '1') != '0'
+
+
+def set_fused(flag):
+    global _FUSED
+    _FUSED = bool(flag)
+
+
+def _run(mods, x):
+    """nn.Sequential semantics over the module list, through the fused chain when possible."""
+    mods = list(mods)
+    if (_FUSED and x.is_cuda and x.dtype == torch.float32 and torch.is_grad_enabled() and all(m.training for m in mods)
+            and all(getattr(c, 'impl', 0) == 0 for m in mods for c in m.modules() if isinstance(c, IcoConvS2S))
+            and _fused.chain_supported(mods)):
+        return _fused.run_chain(x, mods)
+    for m in mods:
+        x = m(x)
+    return x
 
 BatchNorm2d = torch.nn.BatchNorm2d
 
@@ -167,7 +191,9 @@ class ico2ico(torch.nn.Module):
         self.decoder, self.enc2icoConv = createenc2ico(params['ico']['corner_mode'], params['ico2ico']['model'], self.subdivisions)
 
     def forward(self, x):
-        return self.enc2icoConv(self.decoder(self.enc(self.encoder(x))))
+        if isinstance(self.enc, torch.nn.Identity) and not self.enc._forward_hooks:
+            return self.enc2icoConv(_run(list(self.encoder) + list(self.decoder), x))       # one fused chain through both halves
+        return self.enc2icoConv(_run(self.decoder, self.enc(_run(self.encoder, x))))
 
 
 class ico2enc(torch.nn.Module):
@@ -216,11 +242,11 @@ class ico2ico_vae(VAE):
         return _latent_head(self.params, _top(self.params) - 2)
 
     def encode(self, input):
-        h = self.encoder(input)
+        h = _run(self.encoder, input)
         return self.mu_hook(self.mu(h)), self.logvar_hook(self.logvar(h))
 
     def decode(self, z):
-        return self.final_layer(self.decoder(self.reparameterize_hook(z)))
+        return self.final_layer(_run(self.decoder, self.reparameterize_hook(z)))
 
 
 class ico2enc_vae(VAE):

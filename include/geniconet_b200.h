@@ -120,6 +120,29 @@ int gin_hexconv_wgrad_bf16(const void* plan_host, const void* plan_dev, const vo
 int gin_upsample_fwd(const void* plan_host, const void* plan_dev, const float* x, float* y, int B, int C, void* stream);
 int gin_upsample_bwd(const void* plan_host, const void* plan_dev, const float* dy, float* dx, int B, int C, void* stream);
 
+/* ------------------------------------------------------------------ device: fused BN ---- */
+/* torch.nn.BatchNorm2d (training) + ReLU + residual add of models.py:37-39,59-61 fused with the bf16
+ * operand cast of the next convolution.  All maps are pixel-major; `ld` = row stride in elements, so a column slice of a wider
+ * matrix (the concatenated output of two sibling convolutions) is addressed without a copy.  Needs (C/8) | 256.
+ * ws: gin_bn_ws_bytes(C) bytes of scratch.  Deterministic (two-stage reductions, fp64 finals).
+ * gin_bn_stats: stat[4][C] = batch mean, invstd (biased variance, eps), scale = gamma*invstd, shift = beta - mean*scale;
+ *   running_mean / running_var (may be NULL) get torch's momentum update with the unbiased variance. */
+size_t gin_bn_ws_bytes(int C);
+int gin_bn_stats(const float* y, int64_t ld, int64_t rows, int C, const float* gamma, const float* beta, float eps, float momentum,
+                 float* running_mean, float* running_var, float* stat, void* ws, void* stream);
+/* out = act(y1*scale1 + shift1 [+ y2*scale2 + shift2]) at level `level`: out_b (may be NULL) = bf16 [B*P + 2B][C] (pixels, then the
+ * per-sample pole means) -- exactly what gin_cast_bf16 would produce from out; out_f (may be NULL) = fp32 [B*P][C]. */
+int gin_bn_act_fwd(const float* y1, int64_t ld1, const float* stat1, const float* y2 /* may be NULL */, int64_t ld2, const float* stat2,
+                   int relu, void* out_b, float* out_f, int B, int level, int C, void* stream);
+/* backward of out = act(bn(y) [+ ...]) with respect to y: g = dout * (mask_b > 0) (mask_b = the bf16 copy of out; NULL: no ReLU),
+ * bstat[4][C] = dbeta, dgamma, mean(g), mean(g*yhat);  dy = scale*(g - mean(g) - yhat*mean(g*yhat)) is written as the bf16
+ * copy dy_b [B*P + 2B][.] with row stride ldo (pole-mean rows included) and / or as fp32 dy_f with row stride ldf. */
+int gin_bn_act_bwd(const float* dout, int64_t ldg, const void* mask_b, const float* y, int64_t ld, const float* stat, float* bstat,
+                   void* dy_b, int64_t ldo, float* dy_f, int64_t ldf, void* ws, int B, int level, int C, void* stream);
+/* IcoUpsampleS2S.forward whose result exists only as the next convolution's operand copy out_b = bf16 [B*Pf + 2B][C]
+ * (upsample plan).  in: the fp32 coarse map [B*Pc][C] (in_is_f32 = 1) or its bf16 operand copy [B*Pc + 2B][C] (0). */
+int gin_upsample_bf16(const void* plan_host, const void* plan_dev, const void* in, int in_is_f32, void* out_b, int B, int C, void* stream);
+
 /* ------------------------------------------------------------------ device: VAE ------ */
 /* VAE.reparameterize (models.py:89-92), row a6: eps ~ N(0,1) from Philox4x32-10
  * (seed, offset), z = eps*exp(0.5*logvar)+mu; eps is written out for the backward. */
