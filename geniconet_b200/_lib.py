@@ -47,6 +47,7 @@ _SIGS = {
     'gin_plan_build': (_i, [_i, _i, _i, _i, _vp, _sz]),
     'gin_hexconv_packed_bytes': (_sz, [_i, _i]),
     'gin_hexconv_pack_weights': (_i, [_vp, _vp, _i, _i, _vp]),
+    'gin_hexconv_pack_weights_bf16': (_i, [_vp, _i, _vp, _i, _vp, _i, _vp]),
     'gin_hexconv_fwd': (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'gin_hexconv_dgrad': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'gin_hexconv_wgrad_ws_bytes': (_sz, [_i, _i]),
@@ -59,7 +60,7 @@ _SIGS = {
     'gin_hexconv_dgrad_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'gin_hexconv_wgrad_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'gin_bn_ws_bytes': (_sz, [_i]),
-    'gin_bn_stats': (_i, [_vp, _i64, _i64, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    'gin_bn_stats': (_i, [_vp, _i64, _i64, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     'gin_bn_act_fwd': (_i, [_vp, _i64, _vp, _vp, _i64, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
     'gin_bn_act_bwd': (_i, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _vp]),
     'gin_upsample_bf16': (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp]),

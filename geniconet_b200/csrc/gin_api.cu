@@ -153,6 +153,18 @@ int gin_hexconv_pack_weights(const float* weight, void* packed, int Cin, int Cou
   return check_launch("pack_weights");
 }
 
+int gin_hexconv_pack_weights_bf16(const float* w0, int Cout0, const float* w1, int Cout1, void* packed, int Cin, void* stream) {
+  const int Cout = Cout0 + Cout1;
+  if (!w0 || Cout0 <= 0 || Cout1 < 0 || (Cout1 > 0 && !w1) || !packed || Cin <= 0 || (Cin & 63) || (Cout & 63))
+    return fail(GIN_ERR_ARG, "gin_hexconv_pack_weights_bf16: bad argument (channel counts must be multiples of 64)");
+  char* pk = reinterpret_cast<char*>(packed);
+  const long long n = 7LL * Cin * Cout;
+  gin::pack_weights_bf16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      w0, Cout0, w1, reinterpret_cast<unsigned short*>(pk + packed_off_bf(Cin, Cout)), reinterpret_cast<unsigned short*>(pk + packed_off_bd(Cin, Cout)),
+      Cin, Cout);
+  return check_launch("pack_weights_bf16");
+}
+
 static int conv_hdr(const void* plan_host, const void* plan_dev, const GinConvPlanHdr** out) {
   if (!plan_dev) return fail(GIN_ERR_ARG, "null plan");
   const int32_t* w = plan_header(plan_host);
@@ -435,7 +447,7 @@ size_t gin_bn_ws_bytes(int C) { return C <= 0 ? 0 : (size_t)gin::bn::MAX_CTAS * 
 static bool bn_shape_ok(int C) { return C > 0 && (C & 7) == 0 && 256 % (C >> 3) == 0; }
 
 int gin_bn_stats(const float* y, int64_t ld, int64_t rows, int C, const float* gamma, const float* beta, float eps, float momentum,
-                 float* running_mean, float* running_var, float* stat, void* ws, void* stream) {
+                 float* running_mean, float* running_var, int64_t* num_batches_tracked, float* stat, void* ws, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (!y || !stat || !ws || rows <= 0 || !bn_shape_ok(C) || ld < C || (ld & 3)) return fail(GIN_ERR_ARG, "gin_bn_stats: bad argument (C/8 must divide 256)");
   const int ctas = gin::bn::grid_for_rows(rows * (C >> 3));
@@ -443,7 +455,7 @@ int gin_bn_stats(const float* y, int64_t ld, int64_t rows, int C, const float* g
   int rc = check_launch("bn_stats");
   if (rc) return rc;
   gin::bn::stats_final_kernel<<<C / 8, 256, 0, st>>>(reinterpret_cast<const float*>(ws), ctas, rows, C, gamma, beta, eps, momentum, running_mean,
-                                                     running_var, stat);
+                                                     running_var, reinterpret_cast<long long*>(num_batches_tracked), stat);
   return check_launch("bn_stats_final");
 }
 

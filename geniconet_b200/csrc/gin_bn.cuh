@@ -75,8 +75,17 @@ GIN_DEVINL double final_sum(const float* __restrict__ partial, int nblocks, int 
   const int j = threadIdx.x & 15, rg = threadIdx.x >> 4;       // j: (k, channel-in-8), rg: 16 row groups
   const int k = j >> 3, c = blockIdx.x * 8 + (j & 7);
   double acc = 0.0;
-  if (c < C)
-    for (int b = rg; b < nblocks; b += 16) acc += (double)__ldg(partial + ((size_t)b * 2 + k) * C + c);
+  if (c < C) {
+    // every load of this thread is issued before the first add (the kernel is pure load latency otherwise)
+    float v[(MAX_CTAS + 15) / 16];
+#pragma unroll
+    for (int i = 0; i < (MAX_CTAS + 15) / 16; ++i) {
+      const int b = rg + 16 * i;
+      v[i] = b < nblocks ? __ldg(partial + ((size_t)b * 2 + k) * C + c) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < (MAX_CTAS + 15) / 16; ++i) acc += (double)v[i];
+  }
   red[rg][j] = acc;
   __syncthreads();
   double t = 0.0;
@@ -107,12 +116,13 @@ __global__ void __launch_bounds__(256) stats_kernel(Src y, long long rows, int C
 __global__ void __launch_bounds__(256)
 stats_final_kernel(const float* __restrict__ partial, int nblocks, long long rows, int C, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
-                   float* __restrict__ stat) {
+                   long long* __restrict__ num_batches_tracked, float* __restrict__ stat) {
   __shared__ double sums[16];
   const double t = final_sum(partial, nblocks, C);
   if (threadIdx.x < 16) sums[threadIdx.x] = t;
   __syncthreads();
   const int c = blockIdx.x * 8 + threadIdx.x;
+  if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;
   if (threadIdx.x < 8 && c < C) {
     const double mean = sums[threadIdx.x] / (double)rows;
     double var = sums[8 + threadIdx.x] / (double)rows - mean * mean;

@@ -305,6 +305,29 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
   }
 }
 
+// Only the tcgen05 tile images (see pack_weights_kernel) of the weight [w0; w1] concatenated along Cout -- what the fused
+// chains need: two sibling convolutions become one GEMM without materialising the concatenation.
+__global__ void pack_weights_bf16_kernel(const float* __restrict__ w0, int Cout0, const float* __restrict__ w1, unsigned short* __restrict__ bf,
+                                         unsigned short* __restrict__ bd, int Cin, int Cout) {
+  const long long n = (long long)Cin * Cout * 7;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % 7);
+    const long long r = i / 7;
+    const int ci = (int)(r % Cin), co = (int)(r / Cin);
+    const float v = co < Cout0 ? w0[i] : w1[i - (long long)Cout0 * Cin * 7];
+    const unsigned int u = __float_as_uint(v);
+    const unsigned short h = (unsigned short)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
+    {
+      const int kc = ci >> 6, c = (ci >> 3) & 7, e = ci & 7;
+      bf[((((size_t)t * (Cin >> 6) + kc) * Cout + co) << 6) + (((c ^ (co & 7)) << 3) | e)] = h;
+    }
+    {
+      const int kc = co >> 6, c = (co >> 3) & 7, e = co & 7;
+      bd[((((size_t)t * (Cout >> 6) + kc) * Cin + ci) << 6) + (((c ^ (ci & 7)) << 3) | e)] = h;
+    }
+  }
+}
+
 // dWp[7][Cin][Cout] -> dW[Cout][Cin][7]
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dWp, float* __restrict__ dW, int Cin, int Cout) {
   const long long n = (long long)Cin * Cout * 7;

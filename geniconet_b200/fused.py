@@ -84,6 +84,15 @@ def _pack(w, cin, cout):
     return packed
 
 
+def _pack_bf16(w0, w1, cin):
+    """bf16 tile images of [w0; w1] (concatenated output channels) without materialising the concatenation."""
+    c0, c1 = w0.shape[0], (w1.shape[0] if w1 is not None else 0)
+    packed = _empty(L.gin_hexconv_packed_bytes(cin, c0 + c1), torch.uint8, w0.device)
+    _lib.check(L.gin_hexconv_pack_weights_bf16(w0.data_ptr(), c0, w1.data_ptr() if w1 is not None else None, c1, packed.data_ptr(), cin, _stream()),
+               'gin_hexconv_pack_weights_bf16')
+    return packed
+
+
 def _conv_fwd(plan, xb, packed, bias, B, cin, cout, p_out):
     y = _empty((B * p_out, cout), torch.float32, xb.device)
     _lib.check(L.gin_hexconv_fwd_bf16(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), packed.data_ptr(), bias.data_ptr(), y.data_ptr(), B, cin, cout,
@@ -110,8 +119,8 @@ def _bn_stats(y, col0, ld, rows, C, bn):
     stat = _empty(4 * C, torch.float32, y.device)
     ws = _empty(L.gin_bn_ws_bytes(C), torch.uint8, y.device)
     _lib.check(L.gin_bn_stats(y.data_ptr() + 4 * col0, ld, rows, C, bn.weight.data_ptr(), bn.bias.data_ptr(), float(bn.eps), float(bn.momentum),
-                              bn.running_mean.data_ptr(), bn.running_var.data_ptr(), stat.data_ptr(), ws.data_ptr(), _stream()), 'gin_bn_stats')
-    bn.num_batches_tracked.add_(1)
+                              bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), stat.data_ptr(), ws.data_ptr(),
+                              _stream()), 'gin_bn_stats')
     return stat
 
 
@@ -193,14 +202,13 @@ class _Chain(torch.autograd.Function):
                 st['up_plan'] = up_plan
             plan_b = get_plan(_lib.PLAN_HEXCONV, lvl, 1, cm, dev)
             rows = B * _P(lvl)
-            wcat = torch.cat((blk.conv00.weight.detach(), blk.conv10.weight.detach()), 0).contiguous()
             bcat = torch.cat((blk.conv00.bias.detach(), blk.conv10.bias.detach()), 0)
-            pk_cat = _pack(wcat, cin, 2 * cout)
+            pk_cat = _pack_bf16(blk.conv00.weight.detach().contiguous(), blk.conv10.weight.detach().contiguous(), cin)
             ycat = _conv_fwd(plan_a, a_b, pk_cat, bcat, B, cin, 2 * cout, _P(lvl))          # [rows][conv00 | conv10]
             stat00 = _bn_stats(ycat, 0, 2 * cout, rows, cout, blk.icobn00)
             stat10 = _bn_stats(ycat, cout, 2 * cout, rows, cout, blk.icobn10)
             h_b, _ = _bn_act(ycat, 0, 2 * cout, stat00, None, 0, 0, None, B, lvl, cout)
-            pk01 = _pack(blk.conv01.weight.detach().contiguous(), cout, cout)
+            pk01 = _pack_bf16(blk.conv01.weight.detach().contiguous(), None, cout)
             y01 = _conv_fwd(plan_b, h_b, pk01, blk.conv01.bias.detach(), B, cout, cout, _P(lvl))
             stat01 = _bn_stats(y01, 0, cout, rows, cout, blk.icobn01)
             is_last = j == last

@@ -80,6 +80,11 @@ int gin_plan_build(int kind, int level, int stride, int corner_mode, void* host_
 size_t gin_hexconv_packed_bytes(int Cin, int Cout);
 int gin_hexconv_pack_weights(const float* weight, void* packed, int Cin, int Cout, void* stream);
 
+/* Only the bf16 tcgen05 tile images, of the weight [w0; w1] concatenated along Cout (w1 may be NULL with Cout1 = 0): the
+ * fused chains run the two sibling convolutions of a residual block (models.py:25-33, 45-55) as one GEMM.  Channel counts
+ * must be multiples of 64; `packed` has gin_hexconv_packed_bytes(Cin, Cout0 + Cout1) bytes (the fp32 parts stay unwritten). */
+int gin_hexconv_pack_weights_bf16(const float* w0, int Cout0, const float* w1, int Cout1, void* packed, int Cin, void* stream);
+
 /* IcoConvS2S.forward (models.py:14,25-33,45-55,104,165,269,279): rows a1+a2+a3.
  * y[b,p,:] = bias + sum_t W_t^T x~[b, p+t, :] with the padding fused into the gather. */
 int gin_hexconv_fwd(const void* plan_host, const void* plan_dev, const float* x, int64_t sb, int64_t sp, int64_t sc,
@@ -129,7 +134,8 @@ int gin_upsample_bwd(const void* plan_host, const void* plan_dev, const float* d
  *   running_mean / running_var (may be NULL) get torch's momentum update with the unbiased variance. */
 size_t gin_bn_ws_bytes(int C);
 int gin_bn_stats(const float* y, int64_t ld, int64_t rows, int C, const float* gamma, const float* beta, float eps, float momentum,
-                 float* running_mean, float* running_var, float* stat, void* ws, void* stream);
+                 float* running_mean, float* running_var, int64_t* num_batches_tracked /* may be NULL; += 1 */, float* stat, void* ws,
+                 void* stream);
 /* out = act(y1*scale1 + shift1 [+ y2*scale2 + shift2]) at level `level`: out_b (may be NULL) = bf16 [B*P + 2B][C] (pixels, then the
  * per-sample pole means) -- exactly what gin_cast_bf16 would produce from out; out_f (may be NULL) = fp32 [B*P][C]. */
 int gin_bn_act_fwd(const float* y1, int64_t ld1, const float* stat1, const float* y2 /* may be NULL */, int64_t ld2, const float* stat2,
