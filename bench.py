@@ -394,8 +394,14 @@ def run_ours(args):
                 json.dump(table, fh, indent=1)
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Leave without tearing the communicator down: destroying an NCCL communicator whose collectives live in a captured
+        # CUDA graph hung at exit (N = 2, r01).  Every rank has finished its work once the barrier returns.
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':
