@@ -239,6 +239,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device -- geniconet_b200 has no CPU path')
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    os.environ.setdefault('NCCL_DEBUG', 'WARN')          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
     if world > 1:
