@@ -137,69 +137,79 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------- ours
-def kernel_table(model, B, level, peaks, steps=5):
-    """Per-layer CUDA-event timings of the hex-conv kernels through the C ABI on activations of the real shapes.
+def conv_calls(model, fused):
+    """The distinct tcgen05 hex-conv problems one training step launches: (name, Cin, Cout, stride, level, corner_mode, count).
+    On the fused path the two sibling convolutions of a residual block are ONE problem with concatenated output channels."""
+    from geniconet_b200.ico_conv import IcoConvS2S
+    calls = {}
 
-    Every timed launch works on tensors far larger than nothing-in-L2 can explain only when
-    input+output > L2 (126 MB); the `l2` column says which layers that holds for.
-    """
+    def add(name, ci, co, stride, lvl, cm):
+        key = (ci, co, stride, lvl)
+        if key in calls:
+            calls[key][-1] += 1
+        else:
+            calls[key] = [name, ci, co, stride, lvl, cm, 1]
+    if fused:
+        for name, m in model.named_modules():
+            if hasattr(m, 'conv00') and hasattr(m, 'icobn10'):
+                c0, c1 = m.conv00, m.conv01
+                add(name + '.conv00|conv10', c0.in_features, 2 * c0.out_features, c0.stride, c0.subdivisions, c0.corner_mode)
+                add(name + '.conv01', c1.in_features, c1.out_features, 1, c1.subdivisions, c1.corner_mode)
+            elif isinstance(m, IcoConvS2S) and name.split('.')[-1] not in ('conv00', 'conv01', 'conv10') and m.in_features % 64 == 0:
+                add(name, m.in_features, m.out_features, m.stride, m.subdivisions, m.corner_mode)
+    else:
+        for name, m in model.named_modules():
+            if isinstance(m, IcoConvS2S) and m.in_features % 64 == 0 and m.out_features % 64 == 0:
+                add(name, m.in_features, m.out_features, m.stride, m.subdivisions, m.corner_mode)
+    return list(calls.values())
+
+
+def kernel_table(model, B, level, peaks, steps=5, fused=True):
+    """Per-problem CUDA-event timings of the hex-conv kernels through the C ABI on activations of the real shapes (the problems
+    of conv_calls).  The `l2` column says for which of them input + output exceed the 126 MB L2 (back-to-back launches of the
+    others are L2-resident, as they largely are inside the real step)."""
     import torch
     from geniconet_b200 import _lib
-    from geniconet_b200.ico_conv import IcoConvS2S, get_plan
+    from geniconet_b200.ico_conv import get_plan
+    L = _lib.lib
     rows = []
-    seen = {}
-    for name, m in model.named_modules():
-        if not isinstance(m, IcoConvS2S) or m.in_features % 64 or m.out_features % 64:
-            continue
-        key = (m.in_features, m.out_features, m.stride, m.subdivisions)
-        if key in seen:
-            seen[key]['count'] += 1
-            continue
-        n = 2 ** m.subdivisions
-        Pin, Pout = 10 * 4 ** m.subdivisions, 10 * 4 ** m.subdivisions // (m.stride ** 2)
-        x = torch.randn(B, 5 * n, 2 * n, m.in_features, device='cuda').permute(0, 3, 1, 2)
-        dy = torch.randn(B, 5 * n // m.stride, 2 * n // m.stride, m.out_features, device='cuda').permute(0, 3, 1, 2)
+    for name, Ci, Co, stride, lvl, cm, count in conv_calls(model, fused):
+        n = 2 ** lvl
+        Pin, Pout = 10 * 4 ** lvl, 10 * 4 ** lvl // (stride ** 2)
+        lvl_out = lvl - (1 if stride == 2 else 0)
+        x = torch.randn(B, 5 * n, 2 * n, Ci, device='cuda').permute(0, 3, 1, 2)
+        dy = torch.randn(B, 5 * n // stride, 2 * n // stride, Co, device='cuda').permute(0, 3, 1, 2)
+        w = torch.randn(Co, Ci, 7, device='cuda') * 0.05
+        bias = torch.zeros(Co, device='cuda')
         y = torch.empty_like(dy)
         dx = torch.empty_like(x)
-        dW = torch.empty(m.out_features, m.in_features, 7, device='cuda')
-        db = torch.empty(m.out_features, device='cuda')
-        ws = torch.empty(_lib.lib.gin_hexconv_wgrad_ws_bytes(m.in_features, m.out_features), dtype=torch.uint8, device='cuda')
-        plan = get_plan(_lib.PLAN_HEXCONV, m.subdivisions, m.stride, m.corner_mode, 'cuda')
-        packed = m._packed_weights(m.weight)
+        dW = torch.empty(Co, Ci, 7, device='cuda')
+        ws = torch.empty(L.gin_hexconv_wgrad_ws_bytes(Ci, Co), dtype=torch.uint8, device='cuda')
+        plan = get_plan(_lib.PLAN_HEXCONV, lvl, stride, cm, 'cuda')
+        packed = torch.empty(L.gin_hexconv_packed_bytes(Ci, Co), dtype=torch.uint8, device='cuda')
         st = torch.cuda.current_stream().cuda_stream
-        Ci, Co = m.in_features, m.out_features
-        sb, sp, sc = Pin * Ci, Ci, 1
-
-        lvl_out = m.subdivisions - (1 if m.stride == 2 else 0)
-        xb = torch.empty(_lib.lib.gin_cast_bf16_bytes(B, m.subdivisions, Ci) // 2, dtype=torch.bfloat16, device='cuda')
-        dyb = torch.empty(_lib.lib.gin_cast_bf16_bytes(B, lvl_out, Co) // 2, dtype=torch.bfloat16, device='cuda')
-
-        def cast_x():
-            _lib.check(_lib.lib.gin_cast_bf16(plan.host_ptr, plan.dev_ptr, 0, x.data_ptr(), xb.data_ptr(), B, Ci, st))
-
-        cws = torch.empty(_lib.lib.gin_cast_bf16_colsum_ws_bytes(Co), dtype=torch.uint8, device='cuda')
-
-        def cast_dy():          # as in IcoConvS2S.backward: the cast of dy also yields the bias gradient
-            _lib.check(_lib.lib.gin_cast_bf16_colsum(plan.host_ptr, plan.dev_ptr, 1, dy.data_ptr(), dyb.data_ptr(), db.data_ptr(),
-                                                     cws.data_ptr(), B, Co, st))
+        _lib.check(L.gin_hexconv_pack_weights(w.data_ptr(), packed.data_ptr(), Ci, Co, st))
+        xb = torch.empty(L.gin_cast_bf16_bytes(B, lvl, Ci) // 2, dtype=torch.bfloat16, device='cuda')
+        dyb = torch.empty(L.gin_cast_bf16_bytes(B, lvl_out, Co) // 2, dtype=torch.bfloat16, device='cuda')
+        _lib.check(L.gin_cast_bf16(plan.host_ptr, plan.dev_ptr, 0, x.data_ptr(), xb.data_ptr(), B, Ci, st))
+        _lib.check(L.gin_cast_bf16(plan.host_ptr, plan.dev_ptr, 1, dy.data_ptr(), dyb.data_ptr(), B, Co, st))
 
         def fwd():
-            _lib.check(_lib.lib.gin_hexconv_fwd_bf16(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), packed.data_ptr(), m.bias.data_ptr(),
-                                                     y.data_ptr(), B, Ci, Co, st))
+            _lib.check(L.gin_hexconv_fwd_bf16(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), packed.data_ptr(), bias.data_ptr(), y.data_ptr(), B, Ci, Co, st))
 
         def dgrad():
-            _lib.check(_lib.lib.gin_hexconv_dgrad_bf16(plan.host_ptr, plan.dev_ptr, dyb.data_ptr(), packed.data_ptr(), dx.data_ptr(), B, Ci, Co, st))
+            _lib.check(L.gin_hexconv_dgrad_bf16(plan.host_ptr, plan.dev_ptr, dyb.data_ptr(), packed.data_ptr(), dx.data_ptr(), B, Ci, Co, st))
 
         def wgrad():
-            _lib.check(_lib.lib.gin_hexconv_wgrad_bf16(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), dyb.data_ptr(), None, dW.data_ptr(),
-                                                       None, ws.data_ptr(), B, Ci, Co, st))
-        cast_x()
-        cast_dy()
+            _lib.check(L.gin_hexconv_wgrad_bf16(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), dyb.data_ptr(), None, dW.data_ptr(), None, ws.data_ptr(),
+                                                B, Ci, Co, st))
         flops = 2.0 * 7 * Ci * Co * Pout * B
-        act_bytes = 4.0 * B * (Ci * Pin + Co * Pout)
-        ent = {'layer': name, 'cin': Ci, 'cout': Co, 'stride': m.stride, 'level': m.subdivisions, 'count': 1,
-               'gflop': flops / 1e9, 'mbytes': act_bytes / 1e6, 'l2': 'exceeds' if act_bytes > 126e6 else 'fits'}
-        for tag, fn in (('fwd', fwd), ('dgrad', dgrad), ('wgrad', wgrad), ('cast_x', cast_x), ('cast_dy', cast_dy)):
+        # algorithmic bytes of one pass: bf16 operand copy read once + fp32 result written once (fwd, dgrad); both copies read (wgrad)
+        by = {'fwd': B * (2.0 * Ci * Pin + 4.0 * Co * Pout), 'dgrad': B * (2.0 * Co * Pout + 4.0 * Ci * Pin),
+              'wgrad': B * (2.0 * Ci * Pin + 2.0 * Co * Pout) + 28.0 * Ci * Co}
+        ent = {'layer': name, 'cin': Ci, 'cout': Co, 'stride': stride, 'level': lvl, 'count': count, 'gflop': flops / 1e9,
+               'l2': 'exceeds' if by['fwd'] > 126e6 else 'fits'}
+        for tag, fn in (('fwd', fwd), ('dgrad', dgrad), ('wgrad', wgrad)):
             for _ in range(2):
                 fn()
             torch.cuda.synchronize()
@@ -223,8 +233,8 @@ def kernel_table(model, B, level, peaks, steps=5):
             ms = e0.elapsed_time(e1) / steps
             ent[tag + '_us'] = ms * 1e3
             ent[tag + '_tflops'] = flops / (ms * 1e-3) / 1e12
-            ent[tag + '_gbs'] = act_bytes / (ms * 1e-3) / 1e9
-        seen[key] = ent
+            ent[tag + '_mbytes'] = by[tag] / 1e6
+            ent[tag + '_gbs'] = by[tag] / (ms * 1e-3) / 1e9
         rows.append(ent)
     return rows
 
@@ -345,7 +355,8 @@ def run_ours(args):
         tf_burst = peaks.get('bf16_tflops', 1590.0)
         src = 'measured' if peaks else 'fallback'
         if not args.no_kernel_table:
-            table = kernel_table(model, B, args.level, peaks)
+            from geniconet_b200 import models as _gm
+            table = kernel_table(model, B, args.level, peaks, fused=_gm._FUSED)
             # dominant kernel = largest share of the step among (layer, pass) entries
             best = None
             for r in table:
@@ -355,17 +366,19 @@ def run_ours(args):
                         best = (share, r, tag)
             _, r, tag = best
             t_s = r[tag + '_us'] * 1e-6
-            ai = r['gflop'] * 1e9 / (r['mbytes'] * 1e6)
+            mb = r[tag + '_mbytes']
+            ai = r['gflop'] * 1e9 / (mb * 1e6)
             ridge = tf_burst * 1e12 / (hbm * 1e9)
             if ai >= ridge:
                 roof = {'bound': 'tensor', 'achieved': r['gflop'] / 1e3 / t_s, 'peak': tf_burst, 'unit': 'TFLOP/s'}
             else:
-                roof = {'bound': 'hbm', 'achieved': r['mbytes'] / 1e3 / t_s, 'peak': hbm, 'unit': 'GB/s'}
+                roof = {'bound': 'hbm', 'achieved': mb / 1e3 / t_s, 'peak': hbm, 'unit': 'GB/s'}
             roof['frac'] = roof['achieved'] / roof['peak']
             roof['traffic'] = None
             roof['kernel'] = 'hexconv %s %d->%d stride %d level %d (x%d per step)' % (tag, r['cin'], r['cout'], r['stride'], r['level'], r['count'])
             roof['peak_source'] = src + ' (MEASURED_PEAKS.json burst figure: kernel timed alone)' if peaks else 'fallback 6650 GB/s / 1590 TFLOP/s'
-            roof['algorithmic'] = {'gflop_per_launch': r['gflop'], 'mbytes_per_launch': r['mbytes'], 'us_per_launch': r[tag + '_us']}
+            roof['algorithmic'] = {'gflop_per_launch': r['gflop'], 'mbytes_per_launch': mb, 'us_per_launch': r[tag + '_us'],
+                                   'arithmetic_intensity': ai, 'ridge': ridge}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libgeniconet_b200.so')
+LIB_PATH = os.environ.get('GIN_LIB') or os.path.join(_HERE, 'libgeniconet_b200.so')      # GIN_LIB: diagnostics builds (-DGIN_PROF)
 
 PLAN_HEXCONV, PLAN_UPSAMPLE, PLAN_LOSS = 1, 2, 3
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
@@ -67,6 +67,7 @@ _SIGS = {
     'gin_upsample_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     'gin_upsample_bwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     'gin_reparam_fwd': (_i, [_vp, _vp, _vp, _vp, _i64, _u64, _u64, _vp]),
+    'gin_reparam_fwd_step': (_i, [_vp, _vp, _vp, _vp, _i64, _u64, _u64, _vp, _vp]),
     'gin_reparam_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     'gin_kld_fwd': (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
     'gin_kld_bwd': (_i, [_vp, _vp, _vp, _f, _vp, _vp, _i64, _vp]),

@@ -406,13 +406,27 @@ int gin_upsample_bwd(const void* plan_host, const void* plan_dev, const float* d
   return check_launch("upsample_bwd");
 }
 
-int gin_reparam_fwd(const float* mu, const float* logvar, float* eps, float* z, int64_t n, uint64_t seed, uint64_t offset,
-                    void* stream) {
+static int reparam_fwd_impl(const float* mu, const float* logvar, float* eps, float* z, int64_t n, uint64_t seed, uint64_t offset,
+                            uint64_t* step, void* stream) {
   if (!mu || !logvar || !eps || !z || n < 0) return fail(GIN_ERR_ARG, "gin_reparam_fwd: bad argument");
   if (n == 0) return GIN_OK;
   if (((uintptr_t)mu | (uintptr_t)logvar | (uintptr_t)eps | (uintptr_t)z) % 16) return fail(GIN_ERR_ARG, "gin_reparam_fwd: pointers must be 16-byte aligned");
-  gin::reparam_fwd_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(mu, logvar, eps, z, n, seed, offset);
-  return check_launch("reparam_fwd");
+  gin::reparam_fwd_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(mu, logvar, eps, z, n, seed, offset,
+                                                                                        reinterpret_cast<const unsigned long long*>(step));
+  int rc = check_launch("reparam_fwd");
+  if (rc || !step) return rc;
+  gin::counter_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(step));
+  return check_launch("counter_inc");
+}
+
+int gin_reparam_fwd(const float* mu, const float* logvar, float* eps, float* z, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
+  return reparam_fwd_impl(mu, logvar, eps, z, n, seed, offset, nullptr, stream);
+}
+
+int gin_reparam_fwd_step(const float* mu, const float* logvar, float* eps, float* z, int64_t n, uint64_t seed, uint64_t offset, uint64_t* step,
+                         void* stream) {
+  if (!step) return fail(GIN_ERR_ARG, "gin_reparam_fwd_step: null step counter");
+  return reparam_fwd_impl(mu, logvar, eps, z, n, seed, offset, step, stream);
 }
 
 int gin_reparam_bwd(const float* dz, const float* logvar, const float* eps, float* dmu, float* dlogvar, int64_t n, void* stream) {

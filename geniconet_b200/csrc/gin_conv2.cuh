@@ -86,6 +86,15 @@ GIN_DEVINL uint64_t desc_kmajor(uint32_t smem_addr, uint32_t sbo_bytes) {
 constexpr int NBARS = 2 * MAX_A_STAGES + 2 * MAX_B_STAGES + 4 + 2 * TAB_SLOTS;
 constexpr int BAR_BYTES = NBARS * 8 + 16;
 
+// -DGIN_PROF: per-role cycle counters (time blocked on each barrier, time per phase) printed by CTA 0; diagnostics only
+#ifdef GIN_PROF
+#define PROF_T0() const long long _t0 = clock64()
+#define PROF_ADD(acc) (acc) += clock64() - _t0
+#else
+#define PROF_T0()
+#define PROF_ADD(acc)
+#endif
+
 template <int N_TILE, bool RESIDENT>
 __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -134,6 +143,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#ifdef GIN_PROF
+  long long pw[6] = {0, 0, 0, 0, 0, 0};
+  const long long t_begin = clock64();
+#endif
 
   if (warp < PROD_WARPS) {
     // =========================================================== producers: asynchronous patch gather (one copy)
@@ -143,13 +156,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
     uint32_t ph = 0, tph = 0;
     for (int VT = t_first * NP; VT < p.total_tiles * NP; VT = (VT % NP == NP - 1) ? VT + 1 + (t_step - 1) * NP : VT + 1) {
       int v[MAX_ITEMS];
-      mbar_wait(&tab_full[ts], tph);
+      { PROF_T0(); mbar_wait(&tab_full[ts], tph); PROF_ADD(pw[0]); }
 #pragma unroll
       for (int it = 0; it < MAX_ITEMS; ++it) v[it] = tab[ts * TAB_ROWS + it * 32 + warp * 4 + sub];
       mbar_arrive(&tab_empty[ts]);                   // the row ids are in registers now
       if (++ts == TAB_SLOTS) { ts = 0; tph ^= 1u; }
       for (int kc = 0; kc < kchunks; ++kc) {
-        mbar_wait(&a_empty[s], ph ^ 1u);
+        { PROF_T0(); mbar_wait(&a_empty[s], ph ^ 1u); PROF_ADD(pw[1]); }
         const uint32_t st = smem_u32(a_smem + s * p.a_stage_bytes);
 #pragma unroll
         for (int it = 0; it < MAX_ITEMS; ++it) {
@@ -163,6 +176,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
         if (++s == AS) { s = 0; ph ^= 1u; }
       }
     }
+#ifdef GIN_PROF
+    if (blockIdx.x == 0 && tid == 0) printf("producer: total %lld wait_tab %lld wait_a_empty %lld\n", clock64() - t_begin, pw[0], pw[1]);
+#endif
   } else if (warp == W_MMA) {
     // =========================================================== MMA issuer
     // The whole warp runs this loop in lock step (addresses, descriptors and counters stay in uniform registers);
@@ -172,46 +188,77 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
     int s = 0, bs = 0;
     uint32_t ph = 0, bph = 0, wc = 0;
     if (RESIDENT) mbar_wait(&b_full[0], 0);          // the whole weight slice, loaded once
+    // The tensor pipe only holds a few MMAs in its queue: whenever this warp stops issuing for longer than they take (an
+    // mbarrier try_wait alone is 60-90 clk, a proxy fence more) the pipe runs dry.  So just before the LAST tap group of a chunk
+    // is issued -- while the earlier tap groups still execute -- the barriers that open the NEXT chunk are tested WITHOUT
+    // blocking (its a_full + proxy fence, and the accumulator hand-back when it starts a new output); whatever is already
+    // complete then costs nothing at the chunk boundary.
+    bool a_ready = false, acc_ready = false;
     for (int T = t_first; T < p.total_tiles; T += t_step) {
       uint32_t fresh = 1;                            // the next MMA starts a new accumulation
       for (int pl = 0; pl < NP; ++pl) {
         const uint32_t ab = wc & 1;
-        if (fresh) {
+        if (fresh && !acc_ready) {
+          PROF_T0();
           mbar_wait(&acc_empty[ab], ((wc >> 1) & 1u) ^ 1u);
+          PROF_ADD(pw[0]);
           tc_fence_after();
         }
+        acc_ready = false;
         const uint32_t d_tmem = tmem_base + ab * N_TILE;
         const int nt = p.ntaps[pl];
+        const bool flush = p.flush_each || pl == NP - 1;
         for (int kc = 0; kc < kchunks; ++kc) {
-          mbar_wait(&a_full[s], ph);
-          fence_async_smem();                        // cp.async (generic proxy) writes -> visible to the async proxy
-          tc_fence_after();
+          if (!a_ready) {
+            { PROF_T0(); mbar_wait(&a_full[s], ph); PROF_ADD(pw[1]); }
+            { PROF_T0(); fence_async_smem(); tc_fence_after(); PROF_ADD(pw[3]); }
+          }
+          a_ready = false;
           const uint32_t a_addr = smem_u32(a_smem + s * p.a_stage_bytes);
+          const bool last_chunk_of_cta = kc == kchunks - 1 && pl == NP - 1 && T + t_step >= p.total_tiles;
           for (int j = 0; j < nt; ++j) {
+            if (j == nt - 1 && !last_chunk_of_cta) {  // open the next chunk while the earlier tap groups execute
+              const int sn = (s + 1 == AS) ? 0 : s + 1;
+              const uint32_t phn = (s + 1 == AS) ? ph ^ 1u : ph;
+              if (mbar_test(&a_full[sn], phn)) {
+                PROF_T0(); fence_async_smem(); tc_fence_after(); PROF_ADD(pw[3]);
+                a_ready = true;
+              }
+              if (kc == kchunks - 1 && flush) {       // ... and it starts a new output tile: is its accumulator back already?
+                const uint32_t wn = wc + 1;
+                if (mbar_test(&acc_empty[wn & 1], ((wn >> 1) & 1u) ^ 1u)) {
+                  tc_fence_after();
+                  acc_ready = true;
+                }
+              }
+            }
             const int tap = p.tap_id[pl][j];
             uint32_t b_addr;
             if (RESIDENT) b_addr = smem_u32(b_smem + (size_t)(tap * kchunks + kc) * B_TILE);
             else {
-              mbar_wait(&b_full[bs], bph);
+              { PROF_T0(); mbar_wait(&b_full[bs], bph); PROF_ADD(pw[2]); }
               tc_fence_after();
               b_addr = smem_u32(b_smem + (size_t)bs * B_TILE);
             }
             const uint64_t da = desc_kmajor(a_addr + (uint32_t)p.tap_row[pl][j] * 128u, 1280), db = desc_kmajor(b_addr, 1024);
+            {
+              PROF_T0();
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              if (leader && !(p.dbg & 4)) umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, fresh ^ 1u);
-              fresh = 0;
+              for (int k = 0; k < BK / 16; ++k) {
+                if (leader && !(p.dbg & 4)) umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, fresh ^ 1u);
+                fresh = 0;
+              }
+              PROF_ADD(pw[4]);
             }
             if (!RESIDENT) {
               if (leader) umma_commit(&b_empty[bs]);
               if (++bs == BS) { bs = 0; bph ^= 1u; }
             }
           }
-          if (leader) umma_commit(&a_empty[s]);
-          __syncwarp();
+          { PROF_T0(); if (leader) umma_commit(&a_empty[s]); __syncwarp(); PROF_ADD(pw[5]); }
           if (++s == AS) { s = 0; ph ^= 1u; }
         }
-        if (p.flush_each || pl == NP - 1) {
+        if (flush) {
           if (leader) umma_commit(&acc_full[ab]);
           __syncwarp();
           ++wc;
@@ -219,6 +266,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
         }
       }
     }
+#ifdef GIN_PROF
+    if (blockIdx.x == 0 && lane == 0)
+      printf("mma: total %lld wait_acc_empty %lld wait_a_full %lld wait_b_full %lld fences %lld issue %lld commit %lld\n", clock64() - t_begin, pw[0], pw[1],
+             pw[2], pw[3], pw[4], pw[5]);
+#endif
   } else if (warp == W_WEIGHT) {
     // =========================================================== weight tiles
     if (lane == 0) {
@@ -301,13 +353,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
       const long long gdl = (long long)G * p.group * p.P_dst + tile_base[t * Q + oq] + row_off + p.dst_plane_off[fl];
       const int gd = gdl < total_pix ? (int)gdl : -1; // B*P < 2^31 is checked by the launcher
       const uint32_t ab = wc & 1;
-      mbar_wait(&acc_full[ab], (wc >> 1) & 1u);
+      { PROF_T0(); mbar_wait(&acc_full[ab], (wc >> 1) & 1u); PROF_ADD(pw[0]); }
       tc_fence_after();
 #pragma unroll 1
       for (int slab = hslab * 32; slab < N_TILE; slab += 64) {
         uint32_t v[32];
+        { PROF_T0();
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * N_TILE + slab), v);
         tmem_ld_wait();
+        PROF_ADD(pw[1]); }
         float4* dst = reinterpret_cast<float4*>(my_stage + lane * STAGE_PITCH);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -330,6 +384,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
         __syncwarp();
       }
     }
+#ifdef GIN_PROF
+    if (blockIdx.x == 0 && lane == 0 && e == 0) printf("epilogue: total %lld wait_acc_full %lld tmem_ld %lld tiles %u\n", clock64() - t_begin, pw[0], pw[1], wc);
+#endif
   }
   tc_fence_before();
   __syncthreads();

@@ -201,10 +201,13 @@ GIN_DEVINL void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
   n0 = r * c; n1 = r * s;
 }
 
+__global__ void counter_inc_kernel(unsigned long long* c) { *c += 1ull; }
+
 // z = eps * exp(0.5*logvar) + mu; one Philox call per 4 elements, counter = (element/4, offset)
 __global__ void __launch_bounds__(256)
 reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ logvar, float* __restrict__ eps,
-                   float* __restrict__ z, long long n, uint64_t seed, uint64_t offset) {
+                   float* __restrict__ z, long long n, uint64_t seed, uint64_t offset, const unsigned long long* __restrict__ step) {
+  if (step) offset += *step;          // device-side step counter: a replayed CUDA graph still draws fresh noise every step
   const long long n4 = (n + 3) >> 2;
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
     uint32_t r[4];

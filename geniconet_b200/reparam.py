@@ -16,6 +16,16 @@ def manual_seed(seed):
     _state['seed'], _state['offset'] = int(seed) & (2 ** 64 - 1), 0
 
 
+_counters = {}
+
+
+def _graph_counter(device):
+    key = (device.type, device.index)
+    if key not in _counters:
+        _counters[key] = torch.zeros(1, dtype=torch.int64, device=device)
+    return _counters[key]
+
+
 def _next_key():
     if _state['seed'] is None:
         _state['seed'] = torch.initial_seed() & (2 ** 64 - 1)
@@ -33,8 +43,15 @@ class _ReparamFn(torch.autograd.Function):
         if mu.stride() != logvar.stride() or not (mu.is_contiguous() or mu.is_contiguous(memory_format=torch.channels_last)):
             mu, logvar = mu.contiguous(), logvar.contiguous()
         eps, z = torch.empty_like(mu), torch.empty_like(mu)
-        _lib.check(_lib.lib.gin_reparam_fwd(mu.data_ptr(), logvar.data_ptr(), eps.data_ptr(), z.data_ptr(), mu.numel(),
-                                            seed, offset, _stream()), 'gin_reparam_fwd')
+        if torch.cuda.is_current_stream_capturing():
+            # the (seed, offset) scalars would be frozen into the graph: add a device-side step counter that every replay advances
+            step = _graph_counter(mu.device)
+            _lib.check(_lib.lib.gin_reparam_fwd_step(mu.data_ptr(), logvar.data_ptr(), eps.data_ptr(), z.data_ptr(), mu.numel(),
+                                                     seed, offset, step.data_ptr(), _stream()), 'gin_reparam_fwd_step')
+        else:
+            _graph_counter(mu.device)       # exists before any capture (allocating it inside one would re-zero it on every replay)
+            _lib.check(_lib.lib.gin_reparam_fwd(mu.data_ptr(), logvar.data_ptr(), eps.data_ptr(), z.data_ptr(), mu.numel(),
+                                                seed, offset, _stream()), 'gin_reparam_fwd')
         ctx.save_for_backward(logvar, eps)
         ctx.mark_non_differentiable(eps)
         return z, eps

@@ -154,6 +154,10 @@ int gin_upsample_bf16(const void* plan_host, const void* plan_dev, const void* i
  * (seed, offset), z = eps*exp(0.5*logvar)+mu; eps is written out for the backward. */
 int gin_reparam_fwd(const float* mu, const float* logvar, float* eps, float* z, int64_t n,
                     uint64_t seed, uint64_t offset, void* stream);
+/* Same with the Philox offset taken as offset + *step, and *step incremented afterwards ON THE DEVICE: a captured CUDA graph
+ * that is replayed every training step still draws fresh noise (a host-side offset is frozen into the graph). */
+int gin_reparam_fwd_step(const float* mu, const float* logvar, float* eps, float* z, int64_t n, uint64_t seed, uint64_t offset,
+                         uint64_t* step /* device */, void* stream);
 int gin_reparam_bwd(const float* dz, const float* logvar, const float* eps, float* dmu, float* dlogvar,
                     int64_t n, void* stream);
 /* KLD_Loss.forward (losses.py:92-108), row a9: out[0] = mean_b(-0.5*mean_i(1+lv-mu^2-exp(lv))). */

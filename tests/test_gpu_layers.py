@@ -256,3 +256,26 @@ def test_hexconv_tc_matches_oracle(case):
     assert rel(mod.weight.grad, full['dw']) < 2e-2 and rel(mod.weight.grad, refq.weight.grad) < 2e-3, \
         ('wgrad', rel(mod.weight.grad, full['dw']), rel(mod.weight.grad, refq.weight.grad))
     assert rel(mod.bias.grad, full['db']) < 1e-4
+
+
+def test_reparam_draws_fresh_noise_under_graph_replay():
+    """A captured training step is replayed with frozen scalar arguments; the Philox offset therefore also takes a device-side
+    step counter (gin_reparam_fwd_step), so every replay draws new eps."""
+    from geniconet_b200 import reparam
+    mu = torch.zeros(4, 8, 20, 8, device='cuda')
+    lv = torch.zeros_like(mu)
+    reparam.manual_seed(5)
+    reparam.reparameterize(mu, lv)                      # eager warm-up (creates the counter outside the capture)
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            z = reparam.reparameterize(mu, lv)
+    outs = []
+    for _ in range(3):
+        g.replay()
+        torch.cuda.synchronize()
+        outs.append(z.clone())
+    assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[1], outs[2])
+    assert abs(outs[2].std().item() - 1.0) < 0.05
