@@ -89,7 +89,8 @@ int run_gather_gemm_simt(const int32_t* plan_dev, const GinSide& side, int group
 
 // tcgen05 path on the bf16 activation copy: patch mode for stride 1, gather mode otherwise
 int run_gemm_tc(const int32_t* plan_dev, const GinConvPlanHdr* h, const void* Xb, const char* packed, int B, bool dgrad,
-                const float* bias, float* Y, cudaStream_t st, int Cin, int Cout) {
+                const float* bias, float* Y, cudaStream_t st, int Cin, int Cout, float* stats = nullptr, int* stats_parts = nullptr) {
+  if (stats_parts) *stats_parts = 0;
   const GinSide& side = dgrad ? h->dg : h->fwd;
   const int K = dgrad ? Cout : Cin, N = dgrad ? Cin : Cout;
   const int groups = (B + h->group - 1) / h->group;
@@ -98,7 +99,9 @@ int run_gemm_tc(const int32_t* plan_dev, const GinConvPlanHdr* h, const void* Xb
   const GinPSide& ps = dgrad ? h->pdg : h->pfwd;
   int rc;
   if (h->stride == 1 && patch_mode_enabled() && gin::tcp_supported(ps, K, N)) {
-    if (tc_mode() == 2 && gin::cv2_supported(ps, K, N)) rc = gin::launch_patch_conv2(plan_dev, ps, h->group, side.P_dst, 2 << h->level_in, Xb, wb, bias, Y, B, K, N, dgrad ? 1 : 0, st);
+    if (tc_mode() == 2 && gin::cv2_supported(ps, K, N))
+      rc = gin::launch_patch_conv2(plan_dev, ps, h->group, side.P_dst, 2 << h->level_in, Xb, wb, bias, Y, B, K, N, dgrad ? 1 : 0, st, dgrad ? nullptr : stats,
+                                   dgrad ? nullptr : stats_parts);
     else rc = gin::launch_patch_gemm_tc(plan_dev, ps, h->group, side.P_dst, Xb, wb, bias, Y, B, K, N, dgrad ? 1 : 0, st);
     if (rc != GIN_OK) return fail(rc, "tcgen05 patch-GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -112,7 +115,7 @@ int run_gemm_tc(const int32_t* plan_dev, const GinConvPlanHdr* h, const void* Xb
   if (h->stride == 2 && tc_mode() == 2 && gin::cv2_supported(h->p2, K, N)) {
     // stride 2 in patch mode on the coarse lattice: four parity planes (gin_plan.h: GinP2Side)
     const int Pf = h->fwd.P_src, Pc = h->fwd.P_dst;
-    if (!dgrad) rc = gin::launch_patch_conv2_s2_fwd(plan_dev, h->p2, h->group, Pf, Pc, 2 << h->level_out, Xb, wb, bias, Y, B, K, N, st);
+    if (!dgrad) rc = gin::launch_patch_conv2_s2_fwd(plan_dev, h->p2, h->group, Pf, Pc, 2 << h->level_out, Xb, wb, bias, Y, B, K, N, st, stats, stats_parts);
     else rc = gin::launch_patch_conv2_s2_dgrad(plan_dev, h->p2, h->group, Pf, Pc, 2 << h->level_in, Xb, wb, Y, B, K, N, st);
     if (rc != GIN_OK) return fail(rc, "tcgen05 stride-2 patch launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -353,6 +356,16 @@ int gin_hexconv_fwd_bf16(const void* plan_host, const void* plan_dev, const void
   return run_gemm_tc(plan_words(plan_dev), h, xb, reinterpret_cast<const char*>(packed), B, false, bias, y, (cudaStream_t)stream, Cin, Cout);
 }
 
+int gin_hexconv_fwd_bf16_stats(const void* plan_host, const void* plan_dev, const void* xb, const void* packed, const float* bias, float* y, int B,
+                               int Cin, int Cout, float* stats_ws, int* nparts, void* stream) {
+  if (!xb || !packed || !y || !stats_ws || !nparts || B <= 0 || Cin <= 0 || Cout <= 0) return fail(GIN_ERR_ARG, "gin_hexconv_fwd_bf16_stats: bad argument");
+  const GinConvPlanHdr* h;
+  int rc = conv_hdr(plan_host, plan_dev, &h);
+  if (rc) return rc;
+  return run_gemm_tc(plan_words(plan_dev), h, xb, reinterpret_cast<const char*>(packed), B, false, bias, y, (cudaStream_t)stream, Cin, Cout, stats_ws,
+                     nparts);
+}
+
 int gin_hexconv_dgrad_bf16(const void* plan_host, const void* plan_dev, const void* dyb, const void* packed, float* dx, int B, int Cin, int Cout,
                            void* stream) {
   if (!dyb || !packed || !dx || B < 0 || Cin <= 0 || Cout <= 0) return fail(GIN_ERR_ARG, "gin_hexconv_dgrad_bf16: bad argument");
@@ -469,7 +482,18 @@ int gin_bn_stats(const float* y, int64_t ld, int64_t rows, int C, const float* g
   int rc = check_launch("bn_stats");
   if (rc) return rc;
   gin::bn::stats_final_kernel<<<C / 8, 256, 0, st>>>(reinterpret_cast<const float*>(ws), ctas, rows, C, gamma, beta, eps, momentum, running_mean,
-                                                     running_var, reinterpret_cast<long long*>(num_batches_tracked), stat);
+                                                     running_var, reinterpret_cast<long long*>(num_batches_tracked), stat, 0);
+  return check_launch("bn_stats_final");
+}
+
+size_t gin_hexconv_stats_ws_bytes(int Cout) { return Cout <= 0 ? 0 : (size_t)148 * 2 * Cout * 4; }
+
+int gin_bn_stats_from_parts(const float* parts, int nparts, int64_t ld, int64_t rows, int C, const float* gamma, const float* beta, float eps,
+                            float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked, float* stat, void* stream) {
+  if (!parts || nparts <= 0 || nparts > gin::bn::MAX_CTAS || !stat || rows <= 0 || !bn_shape_ok(C) || ld < C)
+    return fail(GIN_ERR_ARG, "gin_bn_stats_from_parts: bad argument");
+  gin::bn::stats_final_kernel<<<C / 8, 256, 0, (cudaStream_t)stream>>>(parts, nparts, rows, C, gamma, beta, eps, momentum, running_mean, running_var,
+                                                                       reinterpret_cast<long long*>(num_batches_tracked), stat, ld);
   return check_launch("bn_stats_final");
 }
 

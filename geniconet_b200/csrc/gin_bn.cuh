@@ -70,7 +70,8 @@ GIN_DEVINL void block_partials(const float s0[8], const float s1[8], int C, floa
 }
 
 // final[k][c] (double) = sum_b partial[b][k][c] for the 8 channels of this CTA; returned to threads 0..7 (k = 0) and 8..15 (k = 1)
-GIN_DEVINL double final_sum(const float* __restrict__ partial, int nblocks, int C) {
+GIN_DEVINL double final_sum(const float* __restrict__ partial, int nblocks, int C, long long ld = 0) {
+  if (ld == 0) ld = C;                                         // row stride of the partial-sum rows (a column slice of wider rows)
   __shared__ double red[16][17];
   const int j = threadIdx.x & 15, rg = threadIdx.x >> 4;       // j: (k, channel-in-8), rg: 16 row groups
   const int k = j >> 3, c = blockIdx.x * 8 + (j & 7);
@@ -81,7 +82,7 @@ GIN_DEVINL double final_sum(const float* __restrict__ partial, int nblocks, int 
 #pragma unroll
     for (int i = 0; i < (MAX_CTAS + 15) / 16; ++i) {
       const int b = rg + 16 * i;
-      v[i] = b < nblocks ? __ldg(partial + ((size_t)b * 2 + k) * C + c) : 0.f;
+      v[i] = b < nblocks ? __ldg(partial + ((size_t)b * 2 + k) * ld + c) : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < (MAX_CTAS + 15) / 16; ++i) acc += (double)v[i];
@@ -116,9 +117,9 @@ __global__ void __launch_bounds__(256) stats_kernel(Src y, long long rows, int C
 __global__ void __launch_bounds__(256)
 stats_final_kernel(const float* __restrict__ partial, int nblocks, long long rows, int C, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
-                   long long* __restrict__ num_batches_tracked, float* __restrict__ stat) {
+                   long long* __restrict__ num_batches_tracked, float* __restrict__ stat, long long ld) {
   __shared__ double sums[16];
-  const double t = final_sum(partial, nblocks, C);
+  const double t = final_sum(partial, nblocks, C, ld);
   if (threadIdx.x < 16) sums[threadIdx.x] = t;
   __syncthreads();
   const int c = blockIdx.x * 8 + threadIdx.x;

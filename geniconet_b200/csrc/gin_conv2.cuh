@@ -58,6 +58,7 @@ struct Params {
   const __nv_bfloat16* Wt;    // pre-swizzled bf16 tiles [7][K/64][N][64]
   const float* bias;
   float* Y;                   // [B*P_dst][N] fp32
+  float* stats;               // optional [gridDim.x / n_blocks][2][N]: per-CTA column sums of y and y^2 (BatchNorm statistics)
   int nplanes, flush_each;
   int ntaps[4];
   int8_t tap_id[4][8];        // weight index of each tap of a segment
@@ -67,6 +68,7 @@ struct Params {
   int dst_row_stride, dst_px_stride, dst_plane_off[4];
   int total_tiles, n_blocks;  // CTA c owns n-block c % n_blocks and tiles c / n_blocks + k * (gridDim.x / n_blocks)
   int a_stage_bytes, a_stages, b_stages, resident;
+  int* stats_parts;           // host: receives the number of per-CTA statistics rows written (0: none)
   int dbg;                    // GIN_DBG bit mask (experiments only): 1 no epilogue stores, 2 no patch loads, 4 no MMAs
 };
 
@@ -95,7 +97,7 @@ constexpr int BAR_BYTES = NBARS * 8 + 16;
 #define PROF_ADD(acc)
 #endif
 
-template <int N_TILE, bool RESIDENT>
+template <int N_TILE, bool RESIDENT, bool STATS>
 __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -347,6 +349,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
     const long long total_pix = (long long)p.B * p.P_dst;
     uint32_t wc = 0;
     const int nflush = p.flush_each ? NP : 1;
+    constexpr int NS = N_TILE / 64;                   // 32-column slabs this warp handles
+    float ssum[STATS ? NS : 1][4], ssq[STATS ? NS : 1][4];
+#pragma unroll
+    for (int si = 0; si < (STATS ? NS : 1); ++si)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { ssum[si][k] = 0.f; ssq[si][k] = 0.f; }
     for (int T = t_first; T < p.total_tiles; T += t_step)
     for (int fl = 0; fl < nflush; ++fl, ++wc) {
       const int G = T / p.ntiles, t = T - G * p.ntiles;
@@ -355,8 +363,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
       const uint32_t ab = wc & 1;
       { PROF_T0(); mbar_wait(&acc_full[ab], (wc >> 1) & 1u); PROF_ADD(pw[0]); }
       tc_fence_after();
-#pragma unroll 1
-      for (int slab = hslab * 32; slab < N_TILE; slab += 64) {
+#pragma unroll
+      for (int si = 0; si < NS; ++si) {
+        const int slab = hslab * 32 + si * 64;
         uint32_t v[32];
         { PROF_T0();
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * N_TILE + slab), v);
@@ -380,9 +389,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
           float4 o = *reinterpret_cast<const float4*>(my_stage + r2 * STAGE_PITCH + c4 * 4);
           o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
           if (gd2 >= 0 && !(p.dbg & 1)) *reinterpret_cast<float4*>(p.Y + (size_t)gd2 * p.N + n0 + slab + c4) = o;
+          if (STATS && gd2 >= 0) {
+            ssum[si][0] += o.x; ssum[si][1] += o.y; ssum[si][2] += o.z; ssum[si][3] += o.w;
+            ssq[si][0] = fmaf(o.x, o.x, ssq[si][0]); ssq[si][1] = fmaf(o.y, o.y, ssq[si][1]);
+            ssq[si][2] = fmaf(o.z, o.z, ssq[si][2]); ssq[si][3] = fmaf(o.w, o.w, ssq[si][3]);
+          }
         }
         __syncwarp();
       }
+    }
+    if (STATS) {
+      // column sums of this CTA's rows: lanes that share (lane & 7) hold the same columns; the four TMEM-quarter warps of a
+      // slab set meet in shared memory (the staging area is free now); one plain store per column, no global atomics
+      float* sred = reinterpret_cast<float*>(stage_smem);              // [2][N_TILE]
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      for (int i = (warp - W_EPI0) * 32 + lane; i < 2 * N_TILE; i += EPI_WARPS * 32) sred[i] = 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+#pragma unroll
+      for (int si = 0; si < NS; ++si)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float a = ssum[si][k], b = ssq[si][k];
+          a += __shfl_xor_sync(0xffffffffu, a, 8); a += __shfl_xor_sync(0xffffffffu, a, 16);
+          b += __shfl_xor_sync(0xffffffffu, b, 8); b += __shfl_xor_sync(0xffffffffu, b, 16);
+          if (lane < 8) {
+            const int col = hslab * 32 + si * 64 + c4 + k;
+            atomicAdd(&sred[col], a);
+            atomicAdd(&sred[N_TILE + col], b);
+          }
+        }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      float* out = p.stats + (size_t)(blockIdx.x / p.n_blocks) * 2 * p.N + n0;
+      for (int i = (warp - W_EPI0) * 32 + lane; i < 2 * N_TILE; i += EPI_WARPS * 32) out[(i / N_TILE) * p.N + (i % N_TILE)] = sred[i];
     }
 #ifdef GIN_PROF
     if (blockIdx.x == 0 && lane == 0 && e == 0) printf("epilogue: total %lld wait_acc_full %lld tmem_ld %lld tiles %u\n", clock64() - t_begin, pw[0], pw[1], wc);
@@ -425,8 +463,10 @@ int launch(Params p, cudaStream_t st) {
   if (!plan_smem(N_TILE, p.K, p.U, p.ntiles, p.Q, p, smem_total)) return -4;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(patch_conv_kernel<N_TILE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
-        cudaFuncSetAttribute(patch_conv_kernel<N_TILE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -3;
+    if (cudaFuncSetAttribute(patch_conv_kernel<N_TILE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
+        cudaFuncSetAttribute(patch_conv_kernel<N_TILE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
+        cudaFuncSetAttribute(patch_conv_kernel<N_TILE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
+        cudaFuncSetAttribute(patch_conv_kernel<N_TILE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -3;
     configured = true;
   }
   p.n_blocks = p.N / N_TILE;
@@ -434,8 +474,15 @@ int launch(Params p, cudaStream_t st) {
   int grid = (int)(items < 148 ? items : 148);
   grid -= grid % p.n_blocks;                         // every CTA keeps one n-block
   if (grid < p.n_blocks) grid = p.n_blocks;
-  if (p.resident) patch_conv_kernel<N_TILE, true><<<grid, NTHREADS, smem_total, st>>>(p);
-  else patch_conv_kernel<N_TILE, false><<<grid, NTHREADS, smem_total, st>>>(p);
+  const bool stats = p.stats != nullptr && !p.flush_each;
+  if (p.stats_parts) *p.stats_parts = stats ? grid / p.n_blocks : 0;
+  if (p.resident) {
+    if (stats) patch_conv_kernel<N_TILE, true, true><<<grid, NTHREADS, smem_total, st>>>(p);
+    else patch_conv_kernel<N_TILE, true, false><<<grid, NTHREADS, smem_total, st>>>(p);
+  } else {
+    if (stats) patch_conv_kernel<N_TILE, false, true><<<grid, NTHREADS, smem_total, st>>>(p);
+    else patch_conv_kernel<N_TILE, false, false><<<grid, NTHREADS, smem_total, st>>>(p);
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
@@ -483,8 +530,10 @@ inline int cv2_dispatch(cv2::Params& p, int max_ntile, cudaStream_t st) {
 
 // stride 1: forward (mirror 0) / in-chart dgrad (mirror 1: tap (di,dj) reads cell (-di,-dj)); W = 2n pixels per chart row
 inline int launch_patch_conv2(const int32_t* plan_dev, const GinPSide& ps, int group, int P, int W, const void* Xb, const void* Wb,
-                              const float* bias, float* Y, int B, int K, int N, int mirror, cudaStream_t st) {
+                              const float* bias, float* Y, int B, int K, int N, int mirror, cudaStream_t st, float* stats = nullptr,
+                              int* stats_parts = nullptr) {
   cv2::Params p{};
+  p.stats = stats; p.stats_parts = stats_parts;
   p.plan = plan_dev; p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P; p.P_dst = P;
   p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.Wt = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = bias; p.Y = Y;
   p.nplanes = 1; p.flush_each = 0; p.ntaps[0] = 7;
@@ -506,8 +555,10 @@ constexpr int kS2B[7] = {0, 0, 0, -1, 0, 0, -1};
 
 // stride 2 forward: X is the FINE map (P_f pixels per sample), Y the coarse one; Wc = 2n of the coarse level
 inline int launch_patch_conv2_s2_fwd(const int32_t* plan_dev, const GinP2Side& ps, int group, int P_f, int P_c, int Wc, const void* Xb,
-                                     const void* Wb, const float* bias, float* Y, int B, int K, int N, cudaStream_t st) {
+                                     const void* Wb, const float* bias, float* Y, int B, int K, int N, cudaStream_t st, float* stats = nullptr,
+                                     int* stats_parts = nullptr) {
   cv2::Params p{};
+  p.stats = stats; p.stats_parts = stats_parts;
   p.plan = plan_dev; p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P_f; p.P_dst = P_c;
   p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.Wt = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = bias; p.Y = Y;
   p.nplanes = 4; p.flush_each = 0;

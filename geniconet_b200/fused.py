@@ -94,10 +94,14 @@ def _pack_bf16(w0, w1, cin):
 
 
 def _conv_fwd(plan, xb, packed, bias, B, cin, cout, p_out):
+    """Returns (y fp32 [B*p_out][cout], per-CTA BatchNorm partial sums [nparts][2][cout] or None)."""
+    import ctypes
     y = _empty((B * p_out, cout), torch.float32, xb.device)
-    _lib.check(L.gin_hexconv_fwd_bf16(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), packed.data_ptr(), bias.data_ptr(), y.data_ptr(), B, cin, cout,
-                                      _stream()), 'gin_hexconv_fwd_bf16')
-    return y
+    parts = _empty(L.gin_hexconv_stats_ws_bytes(cout) // 4, torch.float32, xb.device)
+    n = ctypes.c_int(0)
+    _lib.check(L.gin_hexconv_fwd_bf16_stats(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), packed.data_ptr(), bias.data_ptr(), y.data_ptr(), B, cin, cout,
+                                            parts.data_ptr(), ctypes.addressof(n), _stream()), 'gin_hexconv_fwd_bf16_stats')
+    return y, ((parts, n.value) if n.value > 0 else None)
 
 
 def _conv_dgrad(plan, dyb, packed, B, cin, cout, p_in):
@@ -115,8 +119,14 @@ def _conv_wgrad(plan, xb, dyb, B, cin, cout):
     return dW
 
 
-def _bn_stats(y, col0, ld, rows, C, bn):
+def _bn_stats(y, col0, ld, rows, C, bn, parts=None):
     stat = _empty(4 * C, torch.float32, y.device)
+    if parts is not None:         # the conv epilogue already summed y and y^2 per CTA
+        pbuf, n = parts
+        _lib.check(L.gin_bn_stats_from_parts(pbuf.data_ptr() + 4 * col0, n, ld, rows, C, bn.weight.data_ptr(), bn.bias.data_ptr(), float(bn.eps),
+                                             float(bn.momentum), bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                                             bn.num_batches_tracked.data_ptr(), stat.data_ptr(), _stream()), 'gin_bn_stats_from_parts')
+        return stat
     ws = _empty(L.gin_bn_ws_bytes(C), torch.uint8, y.device)
     _lib.check(L.gin_bn_stats(y.data_ptr() + 4 * col0, ld, rows, C, bn.weight.data_ptr(), bn.bias.data_ptr(), float(bn.eps), float(bn.momentum),
                               bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), stat.data_ptr(), ws.data_ptr(),
@@ -204,13 +214,13 @@ class _Chain(torch.autograd.Function):
             rows = B * _P(lvl)
             bcat = torch.cat((blk.conv00.bias.detach(), blk.conv10.bias.detach()), 0)
             pk_cat = _pack_bf16(blk.conv00.weight.detach().contiguous(), blk.conv10.weight.detach().contiguous(), cin)
-            ycat = _conv_fwd(plan_a, a_b, pk_cat, bcat, B, cin, 2 * cout, _P(lvl))          # [rows][conv00 | conv10]
-            stat00 = _bn_stats(ycat, 0, 2 * cout, rows, cout, blk.icobn00)
-            stat10 = _bn_stats(ycat, cout, 2 * cout, rows, cout, blk.icobn10)
+            ycat, pcat = _conv_fwd(plan_a, a_b, pk_cat, bcat, B, cin, 2 * cout, _P(lvl))    # [rows][conv00 | conv10]
+            stat00 = _bn_stats(ycat, 0, 2 * cout, rows, cout, blk.icobn00, pcat)
+            stat10 = _bn_stats(ycat, cout, 2 * cout, rows, cout, blk.icobn10, pcat)
             h_b, _ = _bn_act(ycat, 0, 2 * cout, stat00, None, 0, 0, None, B, lvl, cout)
             pk01 = _pack_bf16(blk.conv01.weight.detach().contiguous(), None, cout)
-            y01 = _conv_fwd(plan_b, h_b, pk01, blk.conv01.bias.detach(), B, cout, cout, _P(lvl))
-            stat01 = _bn_stats(y01, 0, cout, rows, cout, blk.icobn01)
+            y01, p01 = _conv_fwd(plan_b, h_b, pk01, blk.conv01.bias.detach(), B, cout, cout, _P(lvl))
+            stat01 = _bn_stats(y01, 0, cout, rows, cout, blk.icobn01, p01)
             is_last = j == last
             keep_f = is_last or not mods[j + 1]._down         # an Up block upsamples from the fp32 map (one rounding instead of two)
             # the bf16 copy of the block output is the ReLU mask of the backward, so it is always produced

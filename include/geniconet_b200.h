@@ -114,6 +114,13 @@ int gin_cast_bf16_colsum(const void* plan_host, const void* plan_dev, int which,
                          int B, int C, void* stream);
 int gin_hexconv_fwd_bf16(const void* plan_host, const void* plan_dev, const void* xb, const void* packed, const float* bias,
                          float* y, int B, int Cin, int Cout, void* stream);
+/* Forward that also leaves the BatchNorm statistics of its output behind: stats_ws (gin_hexconv_stats_ws_bytes(Cout) bytes)
+ * receives *nparts rows of [2][Cout] per-CTA column sums of y and y^2 (taken in the epilogue, so the statistics cost no extra
+ * pass over y); gin_bn_stats_from_parts turns a column slice of them into stat[4][C].  *nparts = 0 when the kernel that ran
+ * cannot produce them (then call gin_bn_stats). */
+size_t gin_hexconv_stats_ws_bytes(int Cout);
+int gin_hexconv_fwd_bf16_stats(const void* plan_host, const void* plan_dev, const void* xb, const void* packed, const float* bias,
+                               float* y, int B, int Cin, int Cout, float* stats_ws, int* nparts, void* stream);
 int gin_hexconv_dgrad_bf16(const void* plan_host, const void* plan_dev, const void* dyb, const void* packed, float* dx,
                            int B, int Cin, int Cout, void* stream);
 /* dy (fp32) is only read for db and may be NULL when db is NULL */
@@ -136,6 +143,9 @@ size_t gin_bn_ws_bytes(int C);
 int gin_bn_stats(const float* y, int64_t ld, int64_t rows, int C, const float* gamma, const float* beta, float eps, float momentum,
                  float* running_mean, float* running_var, int64_t* num_batches_tracked /* may be NULL; += 1 */, float* stat, void* ws,
                  void* stream);
+/* The same from per-CTA partial sums `parts` = nparts rows of [2][ld] (here pointing at the first of the C columns wanted). */
+int gin_bn_stats_from_parts(const float* parts, int nparts, int64_t ld, int64_t rows, int C, const float* gamma, const float* beta, float eps,
+                            float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked, float* stat, void* stream);
 /* out = act(y1*scale1 + shift1 [+ y2*scale2 + shift2]) at level `level`: out_b (may be NULL) = bf16 [B*P + 2B][C] (pixels, then the
  * per-sample pole means) -- exactly what gin_cast_bf16 would produce from out; out_f (may be NULL) = fp32 [B*P][C]. */
 int gin_bn_act_fwd(const float* y1, int64_t ld1, const float* stat1, const float* y2 /* may be NULL */, int64_t ld2, const float* stat2,
