@@ -529,6 +529,29 @@ int gin_bn_act_bwd(const float* dout, int64_t ldg, const void* mask_b, const flo
   return check_launch("bn_bwd_apply");
 }
 
+size_t gin_bn_pair_ws_bytes(int C) { return C <= 0 ? 0 : (size_t)gin::bn::MAX_CTAS * 4 * C * 4; }
+
+int gin_bn_act_bwd_pair(const float* dout, int64_t ldg, const void* mask_b, const float* yA, int64_t ldA, const float* statA, float* bstatA,
+                        void* dyA_b, int64_t ldoA, const float* yB, int64_t ldB, const float* statB, float* bstatB, void* dyB_b, int64_t ldoB,
+                        void* ws, int B, int level, int C, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!dout || !yA || !yB || !statA || !statB || !bstatA || !bstatB || !dyA_b || !dyB_b || !ws || B <= 0 || level < 0 || level > 9 || !bn_shape_ok(C))
+    return fail(GIN_ERR_ARG, "gin_bn_act_bwd_pair: bad argument");
+  const int n = 1 << level, P = 10 << (2 * level);
+  const long long rows = (long long)B * P;
+  const gin::bn::Src sA{yA, (long long)ldA}, sB{yB, (long long)ldB};
+  const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(mask_b);
+  const int ctas = gin::bn::grid_for_rows(rows * (C >> 3));
+  gin::bn::bwd_reduce2_kernel<<<ctas, 256, 0, st>>>(dout, ldg, mask, sA, statA, sB, statB, rows, C, reinterpret_cast<float*>(ws));
+  int rc = check_launch("bn_bwd_reduce2");
+  if (rc) return rc;
+  gin::bn::bwd_final2_kernel<<<C / 8, 256, 0, st>>>(reinterpret_cast<const float*>(ws), ctas, rows, C, bstatA, bstatB);
+  if ((rc = check_launch("bn_bwd_final2"))) return rc;
+  gin::bn::bwd_apply2_kernel<<<ctas, 256, 0, st>>>(dout, ldg, mask, sA, statA, bstatA, sB, statB, bstatB, reinterpret_cast<__nv_bfloat16*>(dyA_b), ldoA,
+                                                   reinterpret_cast<__nv_bfloat16*>(dyB_b), ldoB, n, B, P, C);
+  return check_launch("bn_bwd_apply2");
+}
+
 static int up_hdr(const void* plan_host, const void* plan_dev, const GinUpPlanHdr** out);
 
 int gin_upsample_bf16(const void* plan_host, const void* plan_dev, const void* in, int in_is_f32, void* out_b, int B, int C, void* stream) {

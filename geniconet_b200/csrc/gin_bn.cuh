@@ -345,6 +345,122 @@ upsample_bf16_kernel(const int32_t* __restrict__ plan, const void* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ backward of a residual pair
+// out = relu(bnA(yA) + bnB(yB)) (models.py:38-39, 60-61): both BatchNorms see the SAME g = dout * (out > 0), so dout and the
+// mask are read once for both (10 -> 7 bytes per element and pass).  partial[blk][4][C] = sum g (A), sum g*yhatA, sum g (B: same
+// as A, kept for symmetry), sum g*yhatB.
+__global__ void __launch_bounds__(256)
+bwd_reduce2_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, Src yA, const float* __restrict__ statA,
+                   Src yB, const float* __restrict__ statB, long long rows, int C, float* __restrict__ partial) {
+  __shared__ float part[3][256][9];
+  const int C8 = C >> 3;
+  const long long n = rows * C8;
+  const int c = (int)(threadIdx.x % C8) * 8;
+  float meanA[8], invA[8], meanB[8], invB[8];
+  ld8(statA + c, meanA); ld8(statA + C + c, invA); ld8(statB + c, meanB); ld8(statB + C + c, invB);
+  float s0[8], s1[8], s2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s0[k] = s1[k] = s2[k] = 0.f;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+    const long long r = i / C8;
+    float g[8], yh[8], v[8];
+    grad_row(dout, ldg, mask, yA, r, c, C, meanA, invA, g, yh);
+    ld8(yB.p + r * yB.ld + c, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s0[k] += g[k];
+      s1[k] = fmaf(g[k], yh[k], s1[k]);
+      s2[k] = fmaf(g[k], (v[k] - meanB[k]) * invB[k], s2[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { part[0][threadIdx.x][k] = s0[k]; part[1][threadIdx.x][k] = s1[k]; part[2][threadIdx.x][k] = s2[k]; }
+  __syncthreads();
+  float* mine = partial + (size_t)blockIdx.x * 4 * C;
+  for (int i = threadIdx.x; i < 4 * C; i += 256) {
+    const int w = i / C, cc = i - w * C, g8 = cc >> 3, k = cc & 7;
+    const int src = w == 2 ? 0 : (w == 3 ? 2 : w);       // rows: sum g | sum g*yhatA | sum g | sum g*yhatB
+    float acc = 0.f;
+    for (int t = g8; t < 256; t += C8) acc += part[src][t][k];
+    mine[i] = acc;
+  }
+}
+
+// bstatA / bstatB [4][C] from partial[nblocks][4][C]; grid = C/8, block = 256 (8 row groups x 32 (sum, channel) lanes)
+__global__ void __launch_bounds__(256)
+bwd_final2_kernel(const float* __restrict__ partial, int nblocks, long long rows, int C, float* __restrict__ bstatA, float* __restrict__ bstatB) {
+  __shared__ double red[8][33];
+  const int j = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int k = j >> 3, c = blockIdx.x * 8 + (j & 7);
+  double acc = 0.0;
+  if (c < C) {
+    float v[(MAX_CTAS + 7) / 8];
+#pragma unroll
+    for (int i = 0; i < (MAX_CTAS + 7) / 8; ++i) {
+      const int b = rg + 8 * i;
+      v[i] = b < nblocks ? __ldg(partial + ((size_t)b * 4 + k) * C + c) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < (MAX_CTAS + 7) / 8; ++i) acc += (double)v[i];
+  }
+  red[rg][j] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32 && c < C) {
+    double t = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += red[r][threadIdx.x];
+    float* bs = k < 2 ? bstatA : bstatB;
+    const int kk = k & 1;
+    bs[kk * C + c] = (float)t;
+    bs[(2 + kk) * C + c] = (float)(t / (double)rows);
+  }
+}
+
+// dyA, dyB as bf16 gradient copies (row strides ldoA / ldoB, pole-mean rows included)
+__global__ void __launch_bounds__(256)
+bwd_apply2_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, Src yA, const float* __restrict__ statA,
+                  const float* __restrict__ bstatA, Src yB, const float* __restrict__ statB, const float* __restrict__ bstatB,
+                  __nv_bfloat16* __restrict__ dyA, long long ldoA, __nv_bfloat16* __restrict__ dyB, long long ldoB, int nlat, int B, int P, int C) {
+  const int C8 = C >> 3;
+  const long long rows = (long long)B * P, n_main = rows * C8, n_all = n_main + 2LL * B * C8;
+  const int c = (int)(threadIdx.x % C8) * 8;
+  float meanA[8], invA[8], scA[8], c1A[8], c2A[8], meanB[8], invB[8], scB[8], c1B[8], c2B[8];
+  ld8(statA + c, meanA); ld8(statA + C + c, invA); ld8(statA + 2 * C + c, scA); ld8(bstatA + 2 * C + c, c1A); ld8(bstatA + 3 * C + c, c2A);
+  ld8(statB + c, meanB); ld8(statB + C + c, invB); ld8(statB + 2 * C + c, scB); ld8(bstatB + 2 * C + c, c1B); ld8(bstatB + 3 * C + c, c2B);
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n_all; i += gridDim.x * 256LL) {
+    float oA[8], oB[8];
+    if (i < n_main) {
+      const long long r = i / C8;
+      float g[8], yh[8], v[8];
+      grad_row(dout, ldg, mask, yA, r, c, C, meanA, invA, g, yh);
+      ld8(yB.p + r * yB.ld + c, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        oA[k] = scA[k] * (g[k] - c1A[k] - yh[k] * c2A[k]);
+        oB[k] = scB[k] * (g[k] - c1B[k] - (v[k] - meanB[k]) * invB[k] * c2B[k]);
+      }
+    } else {
+      const long long j = (i - n_main) / C8;
+      const int sample = (int)(j >> 1), pole = (int)(j & 1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) oA[k] = oB[k] = 0.f;
+      for (int e = 0; e < 5; ++e) {
+        const long long r = (long long)sample * P + ring_pixel(nlat, pole, e);
+        float g[8], yh[8], v[8];
+        grad_row(dout, ldg, mask, yA, r, c, C, meanA, invA, g, yh);
+        ld8(yB.p + r * yB.ld + c, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          oA[k] = fmaf(0.2f * scA[k], g[k] - c1A[k] - yh[k] * c2A[k], oA[k]);
+          oB[k] = fmaf(0.2f * scB[k], g[k] - c1B[k] - (v[k] - meanB[k]) * invB[k] * c2B[k], oB[k]);
+        }
+      }
+    }
+    st8_bf16(dyA + (i / C8) * ldoA + c, oA);
+    st8_bf16(dyB + (i / C8) * ldoB + c, oB);
+  }
+}
+
 inline int grid_for_rows(long long n_threads) {
   long long b = (n_threads + 255) / 256;
   if (b < 1) b = 1;

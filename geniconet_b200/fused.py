@@ -250,8 +250,14 @@ class _Chain(torch.autograd.Function):
                 dev = d.device
                 dycat_b = torch.empty((B * _P(lvl) + 2 * B, 2 * cout), dtype=torch.bfloat16, device=dev)
                 dy01_b = torch.empty((B * _P(lvl) + 2 * B, cout), dtype=torch.bfloat16, device=dev)
-                bs01, _ = _bn_bwd(d, st['out_b'], st['y01'], 0, cout, st['stat01'], B, lvl, cout, dy01_b, 0, cout)
-                bs10, _ = _bn_bwd(d, st['out_b'], st['ycat'], cout, 2 * cout, st['stat10'], B, lvl, cout, dycat_b, cout, 2 * cout)
+                # bn01 and bn10 see the same g = d * (out > 0): one pass pair for both
+                bs01 = torch.empty(4 * cout, dtype=torch.float32, device=dev)
+                bs10 = torch.empty(4 * cout, dtype=torch.float32, device=dev)
+                ws = torch.empty(L.gin_bn_pair_ws_bytes(cout), dtype=torch.uint8, device=dev)
+                _lib.check(L.gin_bn_act_bwd_pair(d.data_ptr(), cout, st['out_b'].data_ptr(), st['y01'].data_ptr(), cout, st['stat01'].data_ptr(),
+                                                 bs01.data_ptr(), dy01_b.data_ptr(), cout, st['ycat'].data_ptr() + 4 * cout, 2 * cout,
+                                                 st['stat10'].data_ptr(), bs10.data_ptr(), dycat_b.data_ptr() + 2 * cout, 2 * cout, ws.data_ptr(),
+                                                 B, lvl, cout, _stream()), 'gin_bn_act_bwd_pair')
                 dW01 = _conv_wgrad(st['plan_b'], st['h_b'], dy01_b, B, cout, cout)
                 d_h = _conv_dgrad(st['plan_b'], dy01_b, st['pk01'], B, cout, cout, _P(lvl))
                 bs00, _ = _bn_bwd(d_h, st['h_b'], st['ycat'], 0, 2 * cout, st['stat00'], B, lvl, cout, dycat_b, 0, 2 * cout)

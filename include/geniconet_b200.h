@@ -155,6 +155,12 @@ int gin_bn_act_fwd(const float* y1, int64_t ld1, const float* stat1, const float
  * copy dy_b [B*P + 2B][.] with row stride ldo (pole-mean rows included) and / or as fp32 dy_f with row stride ldf. */
 int gin_bn_act_bwd(const float* dout, int64_t ldg, const void* mask_b, const float* y, int64_t ld, const float* stat, float* bstat,
                    void* dy_b, int64_t ldo, float* dy_f, int64_t ldf, void* ws, int B, int level, int C, void* stream);
+/* Backward of out = relu(bnA(yA) + bnB(yB)) (the residual output of models.py:38-39, 60-61) with respect to yA and yB in one pass pair:
+ * both BatchNorms see the same g = dout * (mask_b > 0), which is read once.  ws: gin_bn_pair_ws_bytes(C). */
+size_t gin_bn_pair_ws_bytes(int C);
+int gin_bn_act_bwd_pair(const float* dout, int64_t ldg, const void* mask_b, const float* yA, int64_t ldA, const float* statA, float* bstatA,
+                        void* dyA_b, int64_t ldoA, const float* yB, int64_t ldB, const float* statB, float* bstatB, void* dyB_b, int64_t ldoB,
+                        void* ws, int B, int level, int C, void* stream);
 /* IcoUpsampleS2S.forward whose result exists only as the next convolution's operand copy out_b = bf16 [B*Pf + 2B][C]
  * (upsample plan).  in: the fp32 coarse map [B*Pc][C] (in_is_f32 = 1) or its bf16 operand copy [B*Pc + 2B][C] (0). */
 int gin_upsample_bf16(const void* plan_host, const void* plan_dev, const void* in, int in_is_f32, void* out_b, int B, int C, void* stream);
