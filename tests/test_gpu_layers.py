@@ -279,3 +279,76 @@ def test_reparam_draws_fresh_noise_under_graph_replay():
         outs.append(z.clone())
     assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[1], outs[2])
     assert abs(outs[2].std().item() - 1.0) < 0.05
+
+
+@pytest.mark.parametrize('C,level,B,two', [(64, 3, 3, False), (128, 2, 5, True), (256, 2, 2, True)])
+def test_fused_bn_act_matches_torch(C, level, B, two):
+    """gin_bn_stats / gin_bn_act_fwd / gin_bn_act_bwd(_pair) against torch's own BatchNorm2d (training) + add + ReLU + autograd
+    (models.py:37-39, 59-61): statistics, running buffers, the bf16 operand copy incl. pole rows, dgamma / dbeta and dy."""
+    from geniconet_b200 import _lib, fused
+    L = _lib.lib
+    torch.manual_seed(0)
+    n = 2 ** level
+    P = 10 * 4 ** level
+    dev = 'cuda'
+    ld = 2 * C if two else C                                   # y1 is a column slice of a wider matrix in the `two` case
+    ybuf = torch.randn(B * P, ld, device=dev) * 2 + 0.5
+    y2 = torch.randn(B * P, C, device=dev) if two else None
+    bns = [torch.nn.BatchNorm2d(C).to(dev).train() for _ in range(2)]
+    for bn in bns:
+        bn.weight.data.uniform_(0.5, 1.5)
+        bn.bias.data.uniform_(-0.3, 0.3)
+    refbn = [torch.nn.BatchNorm2d(C).to(dev).train() for _ in range(2)]
+    for a, b in zip(refbn, bns):
+        a.load_state_dict(b.state_dict())
+    col0 = C if two else 0
+
+    def as_map(t):                                             # [B*P, C] -> [B, C, 5n, 2n]
+        return t.view(B, 5 * n, 2 * n, C).permute(0, 3, 1, 2)
+    # ---- torch reference
+    y1r = ybuf[:, col0:col0 + C].clone().requires_grad_(True)
+    y2r = y2.clone().requires_grad_(True) if two else None
+    z = refbn[0](as_map(y1r))
+    if two:
+        z = z + refbn[1](as_map(y2r))
+    out_r = torch.relu(z)
+    gout = torch.randn_like(out_r)
+    out_r.backward(gout)
+    # ---- fused kernels
+    stat1 = fused._bn_stats(ybuf, col0, ld, B * P, C, bns[0])
+    stat2 = fused._bn_stats(y2, 0, C, B * P, C, bns[1]) if two else None
+    out_b, out_f = fused._bn_act(ybuf, col0, ld, stat1, y2, 0, C, stat2, B, level, C, want_b=True, want_f=True)
+    torch.cuda.synchronize()
+    ref_flat = out_r.detach().permute(0, 2, 3, 1).reshape(B * P, C)
+    assert torch.allclose(out_f, ref_flat, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(out_b[:B * P].float(), ref_flat, rtol=1e-2, atol=1e-2)
+    ring = [[k * n * 2 * n for k in range(5)], [k * n * 2 * n + (n - 1) * 2 * n + 2 * n - 1 for k in range(5)]]
+    poles = torch.stack([ref_flat.view(B, P, C)[:, ring[p]].mean(1) for p in (0, 1)], 1).reshape(2 * B, C)     # [B][pole] rows
+    assert torch.allclose(out_b[B * P:].float(), poles, rtol=1e-2, atol=1e-2)
+    for a, b in zip(refbn[:2 if two else 1], bns):
+        assert torch.allclose(a.running_mean, b.running_mean, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(a.running_var, b.running_var, rtol=1e-4, atol=1e-5)
+        assert int(b.num_batches_tracked) == 1
+    d = gout.permute(0, 2, 3, 1).reshape(B * P, C).contiguous()
+    if two:
+        dyA = torch.empty(B * P + 2 * B, C, dtype=torch.bfloat16, device=dev)
+        dyB = torch.empty(B * P + 2 * B, C, dtype=torch.bfloat16, device=dev)
+        bsA, bsB = torch.empty(4 * C, device=dev), torch.empty(4 * C, device=dev)
+        ws = torch.empty(L.gin_bn_pair_ws_bytes(C), dtype=torch.uint8, device=dev)
+        _lib.check(L.gin_bn_act_bwd_pair(d.data_ptr(), C, out_b.data_ptr(), ybuf.data_ptr() + 4 * col0, ld, stat1.data_ptr(), bsA.data_ptr(),
+                                         dyA.data_ptr(), C, y2.data_ptr(), C, stat2.data_ptr(), bsB.data_ptr(), dyB.data_ptr(), C, ws.data_ptr(),
+                                         B, level, C, torch.cuda.current_stream().cuda_stream))
+        pairs = [(bsA, dyA, y1r, refbn[0]), (bsB, dyB, y2r, refbn[1])]
+    else:
+        dyA = torch.empty(B * P + 2 * B, C, dtype=torch.bfloat16, device=dev)
+        bsA, dyf = fused._bn_bwd(d, out_b, ybuf, col0, ld, stat1, B, level, C, dy_b=dyA, dy_b_col=0, ldo=C, want_f=True)
+        assert torch.allclose(dyf, y1r.grad, rtol=1e-3, atol=1e-5)
+        pairs = [(bsA, dyA, y1r, refbn[0])]
+    torch.cuda.synchronize()
+    for bs, dyb, yr, rb in pairs:
+        scale = yr.grad.abs().max().item()
+        assert torch.allclose(bs[:C], rb.bias.grad, rtol=1e-3, atol=1e-3)             # dbeta
+        assert torch.allclose(bs[C:2 * C], rb.weight.grad, rtol=1e-3, atol=1e-3)      # dgamma
+        assert (dyb[:B * P].float() - yr.grad).abs().max().item() <= 1e-2 * scale
+        gp = torch.stack([yr.grad.view(B, P, C)[:, ring[p]].mean(1) for p in (0, 1)], 1).reshape(2 * B, C)
+        assert (dyb[B * P:].float() - gp).abs().max().item() <= 1e-2 * scale
