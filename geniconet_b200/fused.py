@@ -111,12 +111,40 @@ def _conv_dgrad(plan, dyb, packed, B, cin, cout, p_in):
     return dx
 
 
-def _conv_wgrad(plan, xb, dyb, B, cin, cout):
-    dW = _empty((cout, cin, 7), torch.float32, xb.device)
-    ws = _empty(L.gin_hexconv_wgrad_ws_bytes(cin, cout), torch.uint8, xb.device)
-    _lib.check(L.gin_hexconv_wgrad_bf16(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), dyb.data_ptr(), None, dW.data_ptr(), None, ws.data_ptr(),
-                                        B, cin, cout, _stream()), 'gin_hexconv_wgrad_bf16')
+def _conv_wgrad(plan, xb, dyb, B, cin, cout, side=None):
+    """dW [cout][cin][7].  With `side` (a CUDA stream) the wgrad is issued there: nothing on the rest of the backward pass depends
+    on it, so the tensor-bound wgrad overlaps the memory-bound BatchNorm backward kernels of the main stream."""
+    if side is None:
+        dW = _empty((cout, cin, 7), torch.float32, xb.device)
+        ws = _empty(L.gin_hexconv_wgrad_ws_bytes(cin, cout), torch.uint8, xb.device)
+        _lib.check(L.gin_hexconv_wgrad_bf16(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), dyb.data_ptr(), None, dW.data_ptr(), None, ws.data_ptr(),
+                                            B, cin, cout, _stream()), 'gin_hexconv_wgrad_bf16')
+        return dW
+    main = torch.cuda.current_stream()
+    side.wait_stream(main)                               # dyb (and xb) are complete on the main stream
+    with torch.cuda.stream(side):
+        dW = _empty((cout, cin, 7), torch.float32, xb.device)
+        ws = _empty(L.gin_hexconv_wgrad_ws_bytes(cin, cout), torch.uint8, xb.device)
+        _lib.check(L.gin_hexconv_wgrad_bf16(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), dyb.data_ptr(), None, dW.data_ptr(), None, ws.data_ptr(),
+                                            B, cin, cout, side.cuda_stream), 'gin_hexconv_wgrad_bf16')
+    xb.record_stream(side)                               # their memory must not be recycled on the main stream while the side stream reads it
+    dyb.record_stream(side)
     return dW
+
+
+_side_streams = {}
+
+
+def _wgrad_stream(dev):
+    import os
+    # measured at I5 / B=36: no gain (4.30 vs 4.26 ms per step) -- the persistent conv kernels leave no room for co-resident CTAs --
+    # so the side stream is opt-in (GIN_WGRAD_STREAM=1)
+    if os.environ.get('GIN_WGRAD_STREAM', '0') != '1':
+        return None
+    key = (dev.type, dev.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=dev)
+    return _side_streams[key]
 
 
 def _bn_stats(y, col0, ld, rows, C, bn, parts=None):
@@ -244,6 +272,7 @@ class _Chain(torch.autograd.Function):
             d = d.contiguous()
         grads = []                # filled back to front, reversed at the end
         dx = None
+        side = _wgrad_stream(d.device)
         for st in reversed(saved):
             if st['kind'] in ('down', 'up'):
                 cin, cout, lvl = st['cin'], st['cout'], st['level']
@@ -258,10 +287,10 @@ class _Chain(torch.autograd.Function):
                                                  bs01.data_ptr(), dy01_b.data_ptr(), cout, st['ycat'].data_ptr() + 4 * cout, 2 * cout,
                                                  st['stat10'].data_ptr(), bs10.data_ptr(), dycat_b.data_ptr() + 2 * cout, 2 * cout, ws.data_ptr(),
                                                  B, lvl, cout, _stream()), 'gin_bn_act_bwd_pair')
-                dW01 = _conv_wgrad(st['plan_b'], st['h_b'], dy01_b, B, cout, cout)
+                dW01 = _conv_wgrad(st['plan_b'], st['h_b'], dy01_b, B, cout, cout, side)
                 d_h = _conv_dgrad(st['plan_b'], dy01_b, st['pk01'], B, cout, cout, _P(lvl))
                 bs00, _ = _bn_bwd(d_h, st['h_b'], st['ycat'], 0, 2 * cout, st['stat00'], B, lvl, cout, dycat_b, 0, 2 * cout)
-                dWcat = _conv_wgrad(st['plan_a'], st['a_b'], dycat_b, B, cin, 2 * cout)
+                dWcat = _conv_wgrad(st['plan_a'], st['a_b'], dycat_b, B, cin, 2 * cout, side)
                 p_in = _P(lvl + 1) if st['kind'] == 'down' else _P(lvl)
                 d_in = _conv_dgrad(st['plan_a'], dycat_b, st['pk_cat'], B, cin, 2 * cout, p_in)
                 if st['kind'] == 'up':
@@ -291,6 +320,8 @@ class _Chain(torch.autograd.Function):
             else:   # 'input': gradient of the fp32 map the chain started from
                 n = 2 ** st['level']
                 dx = d.view(B, 5 * n, 2 * n, st['C']).permute(0, 3, 1, 2)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)      # the weight gradients are consumed (optimizer, all-reduce) on the main stream
         grads.reverse()
         assert len(grads) == ctx.nparams
         return (dx, None) + tuple(grads)
