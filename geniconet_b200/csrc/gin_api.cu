@@ -72,6 +72,14 @@ int tc_mode() {
   return v;
 }
 bool patch_mode_enabled() { return tc_mode() >= 1; }
+// Cross-seam remainder of dgrad: the row-gather kernel over signature-sorted slot tiles (default), or GIN_SEAM=patch: the regular
+// form (GinPxSide, every tile runs all slots) through the patch kernel.  Measured equal within 5 % at I5 / B = 36 (both are bound
+// by the latency of ~20-40 tiny stages per CTA, not by work), so the one that moves less data stays the default.
+bool seam_v2_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GIN_SEAM"); v = (e && strcmp(e, "patch") == 0) ? 1 : 0; }
+  return v == 1;
+}
 
 // fp32 CUDA-core path
 int run_gather_gemm_simt(const int32_t* plan_dev, const GinSide& side, int group, GinSrcView X, const char* packed, int B, int K, int N,
@@ -105,7 +113,11 @@ int run_gemm_tc(const int32_t* plan_dev, const GinConvPlanHdr* h, const void* Xb
     else rc = gin::launch_patch_gemm_tc(plan_dev, ps, h->group, side.P_dst, Xb, wb, bias, Y, B, K, N, dgrad ? 1 : 0, st);
     if (rc != GIN_OK) return fail(rc, "tcgen05 patch-GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    if (dgrad && h->dgx.ntiles > 0) {       // cross-seam and pole entries, accumulated on top
+    if (dgrad && tc_mode() == 2 && seam_v2_enabled() && gin::cv2_seam_supported(h->px, K, N)) {   // cross-seam and pole entries, added on top
+      rc = gin::launch_patch_conv2_seam(plan_dev, h->px, h->group, side.P_src, side.P_dst, Xb, wb, Y, B, K, N, st);
+      if (rc != GIN_OK) return fail(rc, "tcgen05 seam pass (v2) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else if (dgrad && h->dgx.ntiles > 0) {
       rc = gin::launch_gather_gemm_tc(plan_dev, h->dgx, h->group, Xb, wb, nullptr, Y, B, K, N, groups * h->dgx.ntiles, st, 1);
       if (rc != GIN_OK) return fail(rc, "tcgen05 seam pass launch failed: %s", cudaGetErrorString(cudaGetLastError()));
       g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -119,7 +131,11 @@ int run_gemm_tc(const int32_t* plan_dev, const GinConvPlanHdr* h, const void* Xb
     else rc = gin::launch_patch_conv2_s2_dgrad(plan_dev, h->p2, h->group, Pf, Pc, 2 << h->level_in, Xb, wb, Y, B, K, N, st);
     if (rc != GIN_OK) return fail(rc, "tcgen05 stride-2 patch launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    if (dgrad && h->dgx.ntiles > 0) {
+    if (dgrad && seam_v2_enabled() && gin::cv2_seam_supported(h->px, K, N)) {
+      rc = gin::launch_patch_conv2_seam(plan_dev, h->px, h->group, Pc, Pf, Xb, wb, Y, B, K, N, st);
+      if (rc != GIN_OK) return fail(rc, "tcgen05 seam pass (v2) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else if (dgrad && h->dgx.ntiles > 0) {
       rc = gin::launch_gather_gemm_tc(plan_dev, h->dgx, h->group, Xb, wb, nullptr, Y, B, K, N, groups * h->dgx.ntiles, st, 1);
       if (rc != GIN_OK) return fail(rc, "tcgen05 seam pass launch failed: %s", cudaGetErrorString(cudaGetLastError()));
       g_launches.fetch_add(1, std::memory_order_relaxed);

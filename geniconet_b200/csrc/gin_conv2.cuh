@@ -44,6 +44,7 @@ constexpr int TAB_SLOTS = 8, TAB_ROWS = 256, TAB_BATCH = 4;
 constexpr int STAGE_PITCH = 144;             // epilogue staging: 32 fp32 + 16 bytes of padding per row (conflict-free both ways)
 constexpr int STAGE_BYTES = EPI_WARPS * 32 * STAGE_PITCH;
 constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int MAX_PLANES = 16;
 
 // A tile is processed as `nplanes` segments.  Each segment stages ONE image (its own source table) per 64-channel chunk and
 // applies its own short tap list to it.  Stride 1: one segment with all seven taps.  Stride-2 forward: four parity planes of
@@ -59,13 +60,16 @@ struct Params {
   const float* bias;
   float* Y;                   // [B*P_dst][N] fp32
   float* stats;               // optional [gridDim.x / n_blocks][2][N]: per-CTA column sums of y and y^2 (BatchNorm statistics)
-  int nplanes, flush_each;
-  int ntaps[4];
-  int8_t tap_id[4][8];        // weight index of each tap of a segment
-  int16_t tap_row[4][8];      // its start row inside the image (8-row groups are 10 rows apart)
+  int nplanes, flush_each;    // nplanes <= MAX_PLANES
+  int group_bytes;            // distance between the 8-row groups of a tile inside the image: 1280 (patch) or 1024 (gathered rows)
+  int accumulate;             // epilogue adds into Y (read-modify-write; every destination pixel belongs to one tile row only)
+  int dst_tab_off;            // >= 0: destination pixel of tile row r = plan[dst_tab_off + t*128 + r] (-1: none) instead of base + arithmetic
+  int ntaps[MAX_PLANES];
+  int8_t tap_id[MAX_PLANES][8];    // weight index of each tap of a segment
+  int16_t tap_row[MAX_PLANES][8];  // its start row inside the image
   int tab_off, tab_tstride, tab_pstride;      // source table of (tile t, segment pl): plan[tab_off + t*tab_tstride + pl*tab_pstride ...]
   int base_off, base_tstride, base_qstride;   // first destination pixel of octet column q of tile t
-  int dst_row_stride, dst_px_stride, dst_plane_off[4];
+  int dst_row_stride, dst_px_stride, dst_plane_off[MAX_PLANES];
   int total_tiles, n_blocks;  // CTA c owns n-block c % n_blocks and tiles c / n_blocks + k * (gridDim.x / n_blocks)
   int a_stage_bytes, a_stages, b_stages, resident;
   int* stats_parts;           // host: receives the number of per-CTA statistics rows written (0: none)
@@ -139,8 +143,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
     __syncwarp();
     tmem_alloc(tmem_slot, TM_COLS);
   }
-  for (int i = tid; i < p.ntiles * Q; i += NTHREADS)
-    tile_base[i] = __ldg(p.plan + p.base_off + (i / Q) * p.base_tstride + (i % Q) * p.base_qstride);
+  if (p.dst_tab_off < 0)
+    for (int i = tid; i < p.ntiles * Q; i += NTHREADS)
+      tile_base[i] = __ldg(p.plan + p.base_off + (i / Q) * p.base_tstride + (i % Q) * p.base_qstride);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -242,7 +247,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
               tc_fence_after();
               b_addr = smem_u32(b_smem + (size_t)bs * B_TILE);
             }
-            const uint64_t da = desc_kmajor(a_addr + (uint32_t)p.tap_row[pl][j] * 128u, 1280), db = desc_kmajor(b_addr, 1024);
+            const uint64_t da = desc_kmajor(a_addr + (uint32_t)p.tap_row[pl][j] * 128u, (uint32_t)p.group_bytes), db = desc_kmajor(b_addr, 1024);
             {
               PROF_T0();
 #pragma unroll
@@ -358,7 +363,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
     for (int T = t_first; T < p.total_tiles; T += t_step)
     for (int fl = 0; fl < nflush; ++fl, ++wc) {
       const int G = T / p.ntiles, t = T - G * p.ntiles;
-      const long long gdl = (long long)G * p.group * p.P_dst + tile_base[t * Q + oq] + row_off + p.dst_plane_off[fl];
+      long long gdl;
+      if (p.dst_tab_off >= 0) {
+        const int dr = __ldg(p.plan + p.dst_tab_off + t * BM + row);
+        gdl = dr >= 0 ? (long long)G * p.group * p.P_dst + dr : total_pix;
+      } else gdl = (long long)G * p.group * p.P_dst + tile_base[t * Q + oq] + row_off + p.dst_plane_off[fl];
       const int gd = gdl < total_pix ? (int)gdl : -1; // B*P < 2^31 is checked by the launcher
       const uint32_t ab = wc & 1;
       { PROF_T0(); mbar_wait(&acc_full[ab], (wc >> 1) & 1u); PROF_ADD(pw[0]); }
@@ -388,6 +397,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
           const int gd2 = __shfl_sync(0xffffffffu, gd, r2);
           float4 o = *reinterpret_cast<const float4*>(my_stage + r2 * STAGE_PITCH + c4 * 4);
           o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+          if (p.accumulate && gd2 >= 0) {
+            const float4 old = *reinterpret_cast<const float4*>(p.Y + (size_t)gd2 * p.N + n0 + slab + c4);
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          }
           if (gd2 >= 0 && !(p.dbg & 1)) *reinterpret_cast<float4*>(p.Y + (size_t)gd2 * p.N + n0 + slab + c4) = o;
           if (STATS && gd2 >= 0) {
             ssum[si][0] += o.x; ssum[si][1] += o.y; ssum[si][2] += o.z; ssum[si][3] += o.w;
@@ -536,7 +549,7 @@ inline int launch_patch_conv2(const int32_t* plan_dev, const GinPSide& ps, int g
   p.stats = stats; p.stats_parts = stats_parts;
   p.plan = plan_dev; p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P; p.P_dst = P;
   p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.Wt = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = bias; p.Y = Y;
-  p.nplanes = 1; p.flush_each = 0; p.ntaps[0] = 7;
+  p.nplanes = 1; p.flush_each = 0; p.ntaps[0] = 7; p.group_bytes = 1280; p.dst_tab_off = -1;
   for (int t = 0; t < 7; ++t) {
     const int di = mirror ? -cv2::kDi[t] : cv2::kDi[t], dj = mirror ? -cv2::kDj[t] : cv2::kDj[t];
     p.tap_id[0][t] = (int8_t)t;
@@ -561,7 +574,7 @@ inline int launch_patch_conv2_s2_fwd(const int32_t* plan_dev, const GinP2Side& p
   p.stats = stats; p.stats_parts = stats_parts;
   p.plan = plan_dev; p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P_f; p.P_dst = P_c;
   p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.Wt = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = bias; p.Y = Y;
-  p.nplanes = 4; p.flush_each = 0;
+  p.nplanes = 4; p.flush_each = 0; p.group_bytes = 1280; p.dst_tab_off = -1;
   for (int t = 0; t < 7; ++t) {
     const int pl = kS2Plane[t], j = p.ntaps[pl]++;
     p.tap_id[pl][j] = (int8_t)t;
@@ -579,7 +592,7 @@ inline int launch_patch_conv2_s2_dgrad(const int32_t* plan_dev, const GinP2Side&
   cv2::Params p{};
   p.plan = plan_dev; p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P_c; p.P_dst = P_f;
   p.X = reinterpret_cast<const __nv_bfloat16*>(dYb); p.Wt = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = nullptr; p.Y = dX;
-  p.nplanes = 4; p.flush_each = 1;
+  p.nplanes = 4; p.flush_each = 1; p.group_bytes = 1280; p.dst_tab_off = -1;
   for (int t = 0; t < 7; ++t) {
     const int pl = kS2Plane[t], j = p.ntaps[pl]++;
     p.tap_id[pl][j] = (int8_t)t;
@@ -590,6 +603,22 @@ inline int launch_patch_conv2_s2_dgrad(const int32_t* plan_dev, const GinP2Side&
   p.dst_row_stride = 2 * Wf; p.dst_px_stride = 2;
   for (int pl = 0; pl < 4; ++pl) p.dst_plane_off[pl] = (pl >> 1) * Wf + (pl & 1);
   return cv2_dispatch(p, 256, st);     // two accumulators of N_TILE columns, as everywhere
+}
+
+// The cross-seam / pole remainder of dgrad (GinPxSide), added into dX after the in-chart pass: every tile = `nslots` segments of
+// 128 gathered dy rows with one tap each, all accumulated into one tile, destination pixels from the plan, read-modify-write.
+inline bool cv2_seam_supported(const GinPxSide& px, int K, int N) {
+  return px.ntiles > 0 && px.nslots <= cv2::MAX_PLANES && cv2_supported(GIN_TILE_M, px.ntiles, 1, K, N);
+}
+inline int launch_patch_conv2_seam(const int32_t* plan_dev, const GinPxSide& px, int group, int P_src, int P_dst, const void* dYb, const void* Wb,
+                                   float* dX, int B, int K, int N, cudaStream_t st) {
+  cv2::Params p{};
+  p.plan = plan_dev; p.U = GIN_TILE_M; p.Q = 1; p.ntiles = px.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P_src; p.P_dst = P_dst;
+  p.X = reinterpret_cast<const __nv_bfloat16*>(dYb); p.Wt = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = nullptr; p.Y = dX;
+  p.nplanes = px.nslots; p.flush_each = 0; p.group_bytes = 1024; p.accumulate = 1; p.dst_tab_off = px.dst_off;
+  for (int s = 0; s < px.nslots; ++s) { p.ntaps[s] = 1; p.tap_id[s][0] = px.tap[s]; p.tap_row[s][0] = 0; }
+  p.tab_off = px.src_off; p.tab_tstride = px.nslots * GIN_TILE_M; p.tab_pstride = GIN_TILE_M;
+  return cv2_dispatch(p, 256, st);
 }
 
 }  // namespace gin

@@ -339,6 +339,40 @@ bool build_conv(int level, int stride, int corner_mode, std::vector<int32_t>& bl
       if (r >= 0) { const int sg = r / (int)only.size(), idx = r % (int)only.size(); r = sg * gi.P + pix[idx]; }
     X.P_dst = gi.P;
     emit_side(X, ring_out, h.dgx);
+    // ---- the same remainder in regular form (GinPxSide): global slot list = every (tap, bank) that occurs anywhere
+    {
+      int slot_of[32];
+      int nslots = 0;
+      uint32_t uni = 0;
+      for (const auto& row : only) {
+        int cnt[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (const Entry& e : row) uni |= 1u << (cnt[e.tap]++ * 7 + e.tap);
+      }
+      for (int b = 0; b < 32; ++b) slot_of[b] = (uni >> b & 1) ? nslots++ : -1;
+      if (nslots <= GIN_MAX_XSLOTS && !only.empty()) {
+        const int nb = (int)only.size(), rows_total = group * nb, ntiles = (rows_total + GIN_TILE_M - 1) / GIN_TILE_M;
+        std::vector<int32_t> xsrc((size_t)ntiles * nslots * GIN_TILE_M, GIN_SRC_ZERO), xdst((size_t)ntiles * GIN_TILE_M, -1);
+        for (int sg = 0; sg < group; ++sg)
+          for (int i = 0; i < nb; ++i) {
+            const int r = sg * nb + i, t = r / GIN_TILE_M, rr = r % GIN_TILE_M;
+            xdst[(size_t)t * GIN_TILE_M + rr] = sg * gi.P + pix[i];
+            int cnt[7] = {0, 0, 0, 0, 0, 0, 0};
+            for (const Entry& e : only[i]) {
+              const int slot = slot_of[cnt[e.tap]++ * 7 + e.tap];
+              const int code = (e.src >= 0) ? sg * go.P + e.src : -2 - (2 * sg + (-2 - e.src));
+              xsrc[((size_t)t * nslots + slot) * GIN_TILE_M + rr] = code;
+            }
+          }
+        GinPxSide& px = h.px;
+        px.ntiles = ntiles; px.nslots = nslots;
+        for (int b = 0; b < 32; ++b)
+          if (slot_of[b] >= 0) px.tap[slot_of[b]] = (int8_t)(b % 7);
+        px.src_off = (int)blob.size();
+        blob.insert(blob.end(), xsrc.begin(), xsrc.end());
+        px.dst_off = (int)blob.size();
+        blob.insert(blob.end(), xdst.begin(), xdst.end());
+      }
+    }
   }
   if (stride == 2 && go.s >= 2) {
     // ---- stride-2 patch tiles on the coarse lattice (see GinP2Side)

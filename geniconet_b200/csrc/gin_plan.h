@@ -60,6 +60,19 @@ struct GinP2Side {
   int32_t frows_off;          // int32 frows[ntiles][Q]: fine pixel (2*I0, 2*J0_q) of each octet column
 };
 
+// Cross-seam / pole remainder of dgrad in REGULAR form for the patch kernel: the boundary pixels of a sample group, 128 per
+// tile, and one global list of (tap, bank) slots.  src[tile][slot][128] is the dy row the tile's r-th pixel receives through
+// that slot (GIN_SRC_ZERO for most: a pixel has 1-5 entries).  Every tile runs all slots -- a few wasted MMAs buy a kernel
+// without per-tile control flow; zero rows cost no memory traffic (cp.async zero-fill).
+#define GIN_MAX_XSLOTS 16
+struct GinPxSide {
+  int32_t ntiles;             // per sample group (0 = not available)
+  int32_t nslots;             // <= GIN_MAX_XSLOTS
+  int32_t src_off;            // int32 src[ntiles][nslots][128]
+  int32_t dst_off;            // int32 dst[ntiles][128]: pixel inside the sample group or -1
+  int8_t tap[GIN_MAX_XSLOTS]; // weight index of each slot
+};
+
 struct GinConvPlanHdr {
   int32_t magic, kind, level_in, level_out, stride, corner_mode, group, total_words;
   GinSide fwd;                // y rows gathered from x   (also drives wgrad)
@@ -68,6 +81,7 @@ struct GinConvPlanHdr {
   GinPSide pdg;               // stride 1 only: in-chart part of dgrad in patch mode (halo cells are zero) ...
   GinSide dgx;                // ... plus the cross-seam / pole entries, ACCUMULATED on top by a gather-mode pass (both strides)
   GinP2Side p2;               // stride 2 only: forward / wgrad / in-chart dgrad in patch mode
+  GinPxSide px;               // the same remainder as dgx, regular form (patch kernel, read-modify-write after the in-chart pass)
 };
 
 struct GinUpPlanHdr {

@@ -350,3 +350,33 @@ def run_p2_dgrad(blob, h, p2, dy, Wd):
                     if gd < B * Pf:
                         dxf[gd] = acc[m]
     return dx
+
+
+def parse_px(blob):
+    d = dict(zip(['ntiles', 'nslots', 'src_off', 'dst_off'], [int(v) for v in blob[56:60]]))
+    d['tap'] = np.frombuffer(blob[60:64].tobytes(), dtype=np.int8)[:d['nslots']].astype(int)
+    return d
+
+
+def run_px_accumulate(blob, h, px, dy, Wd, dx):
+    """The regular-form seam pass (GinPxSide) as the patch kernel runs it: every tile applies ALL slots, then adds into dx."""
+    B = dy.shape[0]
+    P_src, P_dst, group = h['dgx']['P_src'], h['dgx']['P_dst'], h['group']
+    ring = blob[h['dgx']['ring_off']:h['dgx']['ring_off'] + 10]
+    dxf = dx.reshape(B * P_dst, -1)
+    seen = set()
+    for G in range((B + group - 1) // group):
+        for t in range(px['ntiles']):
+            acc = np.zeros((TILE, Wd.shape[2]), dtype=dy.dtype)
+            for s in range(px['nslots']):
+                off = px['src_off'] + (t * px['nslots'] + s) * TILE
+                acc += gather_rows(dy, blob[off:off + TILE], G * group, ring, P_src) @ Wd[px['tap'][s]]
+            dst = blob[px['dst_off'] + t * TILE: px['dst_off'] + (t + 1) * TILE]
+            for r, d in enumerate(dst):
+                if d >= 0:
+                    gd = G * group * P_dst + int(d)
+                    if gd < B * P_dst:
+                        assert gd not in seen               # plain read-modify-write is race free
+                        seen.add(gd)
+                        dxf[gd] += acc[r]
+    return dx

@@ -76,7 +76,11 @@ def test_patch_plan_reproduces_oracle(case):
         dWe = pe.run_p2_wgrad(blob, h, p2, xn, gyn)
     assert np.abs(ye - yn).max() < 1e-12
     assert not np.isnan(dxe).any()                                      # the in-chart pass writes every input pixel once
-    dxe = pe.run_side_accumulate(blob, h['dgx'], h['group'], gyn, Wd, dxe)   # + cross-seam / pole remainder
+    px = pe.parse_px(blob)
+    assert px['ntiles'] > 0 and px['nslots'] <= 16
+    dxe2 = pe.run_px_accumulate(blob, h, px, gyn, Wd, dxe.copy())            # + remainder, regular form (patch kernel)
+    assert np.abs(dxe2 - dxn).max() < 1e-12
+    dxe = pe.run_side_accumulate(blob, h['dgx'], h['group'], gyn, Wd, dxe)   # + cross-seam / pole remainder (gather kernel)
     assert np.abs(dxe - dxn).max() < 1e-12
     assert np.abs(dWe - dWn).max() < 1e-10
     # one boundary pixel per seam row: the seam pass may add without atomics
