@@ -354,21 +354,21 @@ def test_fused_bn_act_matches_torch(C, level, B, two):
         assert (dyb[B * P:].float() - gp).abs().max().item() <= 1e-2 * scale
 
 
-def test_dgrad_seam_variants_agree():
-    """The cross-seam remainder of dgrad has two device forms (GIN_SEAM, read once per process): this test drives the C ABI
-    directly through both launchers by comparing against the fp32 oracle in two subprocess-free ways is not possible, so it
-    checks the default form here and the regular form through the plan emulator on the CPU (tests/test_plans.py)."""
-    from geniconet_b200.ico_conv import IcoConvS2S
-    torch.manual_seed(4)
-    ref = icocnn_ref.IcoConvS2S(64, 64, 1, True, 3, 'average')
-    mod = IcoConvS2S(64, 64, 1, True, 3, 'average', impl='tc').cuda()
-    mod.load_state_dict(ref.state_dict())
-    x = torch.randn(2, 64, 40, 16)
-    xr = x.clone().requires_grad_(True)
-    yr = ref(xr)
-    gy = torch.randn_like(yr)
-    yr.backward(gy)
-    xc = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
-    mod(xc).backward(gy.cuda())
-    rel = ((xc.grad.cpu() - xr.grad).abs().max() / xr.grad.abs().max()).item()
-    assert rel < 2e-2, rel
+@pytest.mark.parametrize('env', [{'GIN_SEAM': 'patch'}, {'GIN_TC_MODE': 'patch1'}, {'GIN_TC_MODE': 'gather'}])
+def test_alternative_kernel_paths_match_oracle(env):
+    """The A/B kernel selections (read once per process from the environment): regular-form seam pass through the patch kernel,
+    first-generation patch kernels, first-generation gather kernels -- each in a fresh process, conv fwd / dgrad / wgrad of a
+    stride-1 and a stride-2 layer against the oracle fed bf16-rounded operands (tools/diag_conv.py)."""
+    import os
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for spec in (['64', '128', '1', '3', '3'], ['64', '64', '2', '3', '2']):
+        out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'diag_conv.py')] + spec, env=dict(os.environ, **env),
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        rels = dict(re.findall(r'^(fwd|dgrad|wgrad) max err \S+ rel (\S+)', out.stdout, flags=re.M))
+        assert set(rels) == {'fwd', 'dgrad', 'wgrad'}, out.stdout
+        for k, v in rels.items():
+            assert float(v) < 2e-3, (env, spec, k, v)
