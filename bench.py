@@ -357,28 +357,41 @@ def run_ours(args):
         if not args.no_kernel_table:
             from geniconet_b200 import models as _gm
             table = kernel_table(model, B, args.level, peaks, fused=_gm._FUSED)
-            # dominant kernel = largest share of the step among (layer, pass) entries
-            best = None
-            for r in table:
-                for tag in ('fwd', 'dgrad', 'wgrad'):
-                    share = r[tag + '_us'] * r['count']
-                    if best is None or share > best[0]:
-                        best = (share, r, tag)
-            _, r, tag = best
-            t_s = r[tag + '_us'] * 1e-6
-            mb = r[tag + '_mbytes']
-            ai = r['gflop'] * 1e9 / (mb * 1e6)
+            # The dominant kernel FUNCTION of the step is cv2::patch_conv_kernel (profiles/r01_launch_list_fused_step.txt: 23 % of
+            # the device time, ahead of wg2::wgrad_patch_kernel with 12 %): it runs every hex-conv forward and every in-chart
+            # dgrad.  Its launches differ in shape, so the roofline is the launch-weighted aggregate over the forward launches of
+            # one step: achieved = sum of algorithmic work / sum of durations (equivalently per-launch averages of both).
             ridge = tf_burst * 1e12 / (hbm * 1e9)
+            nl = sum(r['count'] for r in table)
+            gflop = sum(r['gflop'] * r['count'] for r in table)
+            mbytes = sum(r['fwd_mbytes'] * r['count'] for r in table)
+            us = sum(r['fwd_us'] * r['count'] for r in table)
+            ai = gflop * 1e9 / (mbytes * 1e6)
             if ai >= ridge:
-                roof = {'bound': 'tensor', 'achieved': r['gflop'] / 1e3 / t_s, 'peak': tf_burst, 'unit': 'TFLOP/s'}
+                roof = {'bound': 'tensor', 'achieved': gflop / 1e3 / (us * 1e-6), 'peak': tf_burst, 'unit': 'TFLOP/s'}
             else:
-                roof = {'bound': 'hbm', 'achieved': mb / 1e3 / t_s, 'peak': hbm, 'unit': 'GB/s'}
+                roof = {'bound': 'hbm', 'achieved': mbytes / 1e3 / (us * 1e-6), 'peak': hbm, 'unit': 'GB/s'}
             roof['frac'] = roof['achieved'] / roof['peak']
+            # dram__bytes_read.sum + dram__bytes_write.sum of `ncu --set full` captures of this kernel (profiles/r01_ncu_conv_kernels.txt)
+            # exist for single shapes, not for the launch mix of a step: fwd 128->64 @I5 94.6 + 50.5 MB against 94.4 + 94.4 MB
+            # algorithmic (the unread part of the output still sits in L2 when the kernel ends), fwd 256->128 @I4 47.8 + 6.1 MB
+            # against 47.2 + 47.2 MB.  No re-reads from DRAM in either.
             roof['traffic'] = None
-            roof['kernel'] = 'hexconv %s %d->%d stride %d level %d (x%d per step)' % (tag, r['cin'], r['cout'], r['stride'], r['level'], r['count'])
-            roof['peak_source'] = src + ' (MEASURED_PEAKS.json burst figure: kernel timed alone)' if peaks else 'fallback 6650 GB/s / 1590 TFLOP/s'
-            roof['algorithmic'] = {'gflop_per_launch': r['gflop'], 'mbytes_per_launch': mb, 'us_per_launch': r[tag + '_us'],
+            roof['kernel'] = 'cv2::patch_conv_kernel, the %d forward launches of one step (tcgen05 implicit-GEMM hex-conv)' % nl
+            roof['peak_source'] = src + ' (MEASURED_PEAKS.json burst figure: kernels timed alone, back to back)' if peaks else 'fallback 6650 GB/s / 1590 TFLOP/s'
+            roof['algorithmic'] = {'gflop_per_launch': gflop / nl, 'mbytes_per_launch': mbytes / nl, 'us_per_launch': us / nl,
                                    'arithmetic_intensity': ai, 'ridge': ridge}
+            # the same aggregate for the three passes as the C ABI exposes them (dgrad = in-chart pass + cross-seam pass, wgrad =
+            # split-K kernel + reduction)
+            roof['passes'] = {}
+            for tag in ('fwd', 'dgrad', 'wgrad'):
+                t_us = sum(r[tag + '_us'] * r['count'] for r in table)
+                roof['passes'][tag] = {'us_per_step': t_us, 'tflops': gflop / 1e3 / (t_us * 1e-6),
+                                       'frac_of_peak': gflop / 1e3 / (t_us * 1e-6) / tf_burst}
+            worst = min(((r['fwd_tflops'], r) for r in table), key=lambda t: t[0])[1]
+            best = max(((r['fwd_tflops'], r) for r in table), key=lambda t: t[0])[1]
+            roof['range'] = {'best': '%d->%d s%d L%d: %.0f TFLOP/s' % (best['cin'], best['cout'], best['stride'], best['level'], best['fwd_tflops']),
+                             'worst': '%d->%d s%d L%d: %.0f TFLOP/s' % (worst['cin'], worst['cout'], worst['stride'], worst['level'], worst['fwd_tflops'])}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
