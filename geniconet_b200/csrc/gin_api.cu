@@ -15,6 +15,7 @@
 #include "gin_gemm_tc.cuh"
 #include "gin_gemm_tcp.cuh"
 #include "gin_conv2.cuh"
+#include "gin_conv2_pair.cuh"
 #include "gin_wgrad2.cuh"
 #include "gin_wgrad_tcp.cuh"
 #include "gin_loss.cuh"
@@ -31,6 +32,10 @@ void gin_set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+namespace gin {
+int cv2_launch_pair(cv2::Params& p, int nt, cudaStream_t st) { return nt == 128 ? cv2::launch_pair<128>(p, st) : cv2::launch_pair<64>(p, st); }
+}  // namespace gin
 
 namespace {
 

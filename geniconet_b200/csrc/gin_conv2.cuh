@@ -527,6 +527,25 @@ inline int cv2_pick_ntile(long long tiles, int N) {
   return best;
 }
 
+// Tile-pair mode (gin_conv2_pair.cuh): for streamed weights, when pairing the tiles costs no extra round of CTAs.
+int cv2_launch_pair(cv2::Params& p, int nt, cudaStream_t st);
+inline bool cv2_pair_ok(const cv2::Params& p, int nt) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("GIN_PAIR"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
+  if (!enabled || p.flush_each || p.accumulate || p.dst_tab_off >= 0 || p.nplanes > 4) return false;
+  const int ntp = nt < 128 ? nt : 128;
+  if (7 * (p.K / 64) * ntp * 128 <= 114688) return false;                   // the weights fit: the resident single-tile kernel is better
+  auto rounds = [&](long long items, int n_blocks) {
+    int ctas = (int)(items < 148 ? items : 148);
+    ctas -= ctas % n_blocks;
+    if (ctas < n_blocks) ctas = n_blocks;
+    return (items + ctas - 1) / ctas;
+  };
+  const long long r1 = rounds((long long)p.total_tiles * (p.N / nt), p.N / nt) * nt;                       // ~ MMA time, single tiles
+  const long long r2 = rounds((long long)((p.total_tiles + 1) / 2) * (p.N / ntp), p.N / ntp) * 2 * ntp;   // ~ MMA time, tile pairs
+  return r2 <= r1;
+}
+
 inline int cv2_dispatch(cv2::Params& p, int max_ntile, cudaStream_t st) {
   if ((long long)p.B * (p.P_src > p.P_dst ? p.P_src : p.P_dst) + 2LL * p.B >= 0x7fffffffLL) return -4;
   const int groups = (p.B + p.group - 1) / p.group;
@@ -534,6 +553,7 @@ inline int cv2_dispatch(cv2::Params& p, int max_ntile, cudaStream_t st) {
   { const char* e = getenv("GIN_DBG"); p.dbg = e ? atoi(e) : 0; }
   int nt = cv2_pick_ntile(p.total_tiles, p.N);
   while (nt > max_ntile) nt /= 2;
+  if (cv2_pair_ok(p, nt)) return cv2_launch_pair(p, nt < 128 ? nt : 128, st);
   switch (nt) {
     case 256: return cv2::launch<256>(p, st);
     case 128: return cv2::launch<128>(p, st);
