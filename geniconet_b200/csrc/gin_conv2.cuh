@@ -553,7 +553,10 @@ inline int cv2_dispatch(cv2::Params& p, int max_ntile, cudaStream_t st) {
   { const char* e = getenv("GIN_DBG"); p.dbg = e ? atoi(e) : 0; }
   int nt = cv2_pick_ntile(p.total_tiles, p.N);
   while (nt > max_ntile) nt /= 2;
-  if (cv2_pair_ok(p, nt)) return cv2_launch_pair(p, nt < 128 ? nt : 128, st);
+  if (cv2_pair_ok(p, nt)) {
+    const int rc = cv2_launch_pair(p, nt < 128 ? nt : 128, st);
+    if (rc != -4) return rc;          // -4: the pair kernel's shared-memory plan does not fit this patch size: single tiles
+  }
   switch (nt) {
     case 256: return cv2::launch<256>(p, st);
     case 128: return cv2::launch<128>(p, st);

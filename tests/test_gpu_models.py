@@ -221,3 +221,33 @@ def test_fused_chain_matches_modulewise(name):
             assert int(b2[k]) == int(b0[k]) == 1, k
     # a conv bias in front of a BatchNorm: exactly zero on the fused path
     assert float(g2['encoder.3.conv00.bias'].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('name,level,B', [('ico2ico', 5, 36), ('ico2ico_vae', 5, 36), ('ico2ico', 6, 16)])
+def test_bench_configurations_run_and_agree(name, level, B):
+    """The BASELINE.json configurations at their FULL sizes (tile counts, kernel selections and shared-memory plans depend on the
+    batch): one fused and one module-wise training step from the same weights must give the same loss and finite gradients."""
+    from geniconet_b200 import models as gm, losses, data, reparam
+    params = gm.default_params(name, level)
+    x, tgt = data.synthetic_batch(level, 0, 2)
+    x = x.repeat((B + 1) // 2, 1, 1, 1)[:B].cuda()
+    tgt = tgt.repeat((B + 1) // 2, 1, 1)[:B].cuda()
+    f = (params['ico']['factor_pos'], params['ico']['factor_nor'], params['ico']['factor_lap'])
+    vals = {}
+    try:
+        for fused in (True, False):
+            gm.set_fused(fused)
+            torch.manual_seed(5)
+            mod = getattr(gm, name)(params).cuda().train()
+            crit = losses.P2PKLD_Loss(level, *f, 1.0) if name == 'ico2ico_vae' else losses.P2P_Loss(level, *f)
+            reparam.manual_seed(7)
+            loss = crit(mod(x), tgt)
+            loss.backward()
+            torch.cuda.synchronize()
+            assert all(torch.isfinite(p.grad).all() for p in mod.parameters())
+            vals[fused] = loss.item()
+            del mod, loss
+            torch.cuda.empty_cache()
+    finally:
+        gm.set_fused(True)
+    assert abs(vals[True] - vals[False]) <= 5e-3 * abs(vals[False]), vals
