@@ -249,7 +249,11 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device -- geniconet_b200 has no CPU path')
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
-    os.environ.setdefault('NCCL_DEBUG', 'WARN')          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+    # NCCL writes its version banner to the C-level stdout; rank 0 must print ONE JSON line there.  Everything else that goes to
+    # file descriptor 1 is sent to stderr, the JSON line is written to the saved descriptor at the end.
+    json_fd = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(2, 1)
     local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
     if world > 1:
@@ -442,7 +446,7 @@ def run_ours(args):
             os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
             with open(os.path.join(ROOT, 'gpurun_out', 'kernel_table.json'), 'w') as fh:
                 json.dump(table, fh, indent=1)
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + '\n').encode())
     if world > 1:
         # Leave without tearing the communicator down: destroying an NCCL communicator whose collectives live in a captured
         # CUDA graph hung at exit (N = 2, r01).  Every rank has finished its work once the barrier returns.
