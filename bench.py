@@ -404,6 +404,14 @@ def run_ours(args):
             # algorithmic (the unread part of the output still sits in L2 when the kernel ends), fwd 256->128 @I4 47.8 + 6.1 MB
             # against 47.2 + 47.2 MB.  No re-reads from DRAM in either.
             roof['traffic'] = None
+            try:          # the ncu measurement of exactly this launch set (tools/measure_traffic.py), committed under profiles/
+                tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
+                if tr.get('launches') == nl and args.model == 'ico2ico' and args.level == 5 and B == 36:
+                    roof['traffic'] = tr['dram_bytes_per_launch'] / 1e6
+                    roof['traffic_unit'] = 'MB per launch (dram__bytes_read.sum + dram__bytes_write.sum, L2 flushed before every launch; compare ' \
+                                           'algorithmic.mbytes_per_launch -- part of the fp32 output is still in L2 when a kernel ends)'
+            except Exception:
+                pass
             roof['kernel'] = 'cv2::patch_conv_kernel, the %d forward launches of one step (tcgen05 implicit-GEMM hex-conv)' % nl
             roof['peak_source'] = src + ' (MEASURED_PEAKS.json burst figure: kernels timed alone, back to back)' if peaks else 'fallback 6650 GB/s / 1590 TFLOP/s'
             roof['algorithmic'] = {'gflop_per_launch': gflop / nl, 'mbytes_per_launch': mbytes / nl, 'us_per_launch': us / nl,
