@@ -16,13 +16,15 @@
 #pragma once
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "gin_common.cuh"
 #include "gin_resample.cuh"
 
 namespace gin {
 namespace bn {
 
-constexpr int MAX_CTAS = 148 * 2;
+constexpr int MAX_CTAS = 148 * 4;          // upper bound (sizes the partial-sum buffers); the grid actually used: bn_ctas()
 
 struct Src {               // a [rows][C] fp32 view inside a wider row-major matrix
   const float* p;
@@ -461,10 +463,16 @@ bwd_apply2_kernel(const float* __restrict__ dout, long long ldg, const __nv_bflo
   }
 }
 
+// CTAs of the streaming BatchNorm kernels: GIN_BN_CTAS (experiments), default 4 per SM
+inline int bn_ctas() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GIN_BN_CTAS"); v = e ? atoi(e) : MAX_CTAS; if (v < 1 || v > MAX_CTAS) v = MAX_CTAS; }
+  return v;
+}
 inline int grid_for_rows(long long n_threads) {
   long long b = (n_threads + 255) / 256;
   if (b < 1) b = 1;
-  return (int)(b < MAX_CTAS ? b : MAX_CTAS);
+  return (int)(b < bn_ctas() ? b : bn_ctas());
 }
 
 }  // namespace bn

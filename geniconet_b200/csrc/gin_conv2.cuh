@@ -531,7 +531,7 @@ inline int cv2_pick_ntile(long long tiles, int N) {
 int cv2_launch_pair(cv2::Params& p, int nt, cudaStream_t st);
 inline bool cv2_pair_ok(const cv2::Params& p, int nt) {
   static int enabled = -1;
-  if (enabled < 0) { const char* e = getenv("GIN_PAIR"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
+  if (enabled < 0) { const char* e = getenv("GIN_PAIR"); enabled = e ? atoi(e) : 1; }      // 0 off, 1 when it costs no extra round, 2 always
   if (!enabled || p.flush_each || p.accumulate || p.dst_tab_off >= 0 || p.nplanes > 4) return false;
   const int ntp = nt < 128 ? nt : 128;
   if (7 * (p.K / 64) * ntp * 128 <= 114688) return false;                   // the weights fit: the resident single-tile kernel is better
@@ -543,7 +543,7 @@ inline bool cv2_pair_ok(const cv2::Params& p, int nt) {
   };
   const long long r1 = rounds((long long)p.total_tiles * (p.N / nt), p.N / nt) * nt;                       // ~ MMA time, single tiles
   const long long r2 = rounds((long long)((p.total_tiles + 1) / 2) * (p.N / ntp), p.N / ntp) * 2 * ntp;   // ~ MMA time, tile pairs
-  return r2 <= r1;
+  return enabled == 2 || r2 <= r1;
 }
 
 inline int cv2_dispatch(cv2::Params& p, int max_ntile, cudaStream_t st) {
