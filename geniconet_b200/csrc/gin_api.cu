@@ -82,7 +82,7 @@ bool patch_mode_enabled() { return tc_mode() >= 1; }
 // by the latency of ~20-40 tiny stages per CTA, not by work), so the one that moves less data stays the default.
 bool seam_v2_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("GIN_SEAM"); v = (e && strcmp(e, "patch") == 0) ? 1 : 0; }
+  if (v < 0) { const char* e = getenv("GIN_SEAM"); v = (e && strcmp(e, "gather") == 0) ? 0 : 1; }
   return v == 1;
 }
 

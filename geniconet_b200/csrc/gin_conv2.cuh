@@ -364,11 +364,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
     for (int fl = 0; fl < nflush; ++fl, ++wc) {
       const int G = T / p.ntiles, t = T - G * p.ntiles;
       long long gdl;
+      bool atomic_row = false;
       if (p.dst_tab_off >= 0) {
-        const int dr = __ldg(p.plan + p.dst_tab_off + t * BM + row);
+        int dr = __ldg(p.plan + p.dst_tab_off + t * BM + row);
+        if (dr <= -2) { atomic_row = true; dr = -2 - dr; }       // a pixel with several rows: all of them add atomically
         gdl = dr >= 0 ? (long long)G * p.group * p.P_dst + dr : total_pix;
       } else gdl = (long long)G * p.group * p.P_dst + tile_base[t * Q + oq] + row_off + p.dst_plane_off[fl];
-      const int gd = gdl < total_pix ? (int)gdl : -1; // B*P < 2^31 is checked by the launcher
+      int gd = gdl < total_pix ? (int)gdl : -1;       // B*P < 2^31 is checked by the launcher
+      if (atomic_row && gd >= 0) gd = -2 - gd;
       const uint32_t ab = wc & 1;
       { PROF_T0(); mbar_wait(&acc_full[ab], (wc >> 1) & 1u); PROF_ADD(pw[0]); }
       tc_fence_after();
@@ -394,9 +397,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r2 = 4 * i + rsub;
-          const int gd2 = __shfl_sync(0xffffffffu, gd, r2);
+          int gd2 = __shfl_sync(0xffffffffu, gd, r2);
           float4 o = *reinterpret_cast<const float4*>(my_stage + r2 * STAGE_PITCH + c4 * 4);
           o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+          if (gd2 <= -2) {                                // atomic row (accumulate mode only)
+            float* yp = p.Y + (size_t)(-2 - gd2) * p.N + n0 + slab + c4;
+            atomicAdd(yp, o.x); atomicAdd(yp + 1, o.y); atomicAdd(yp + 2, o.z); atomicAdd(yp + 3, o.w);
+            gd2 = -1;
+          }
           if (p.accumulate && gd2 >= 0) {
             const float4 old = *reinterpret_cast<const float4*>(p.Y + (size_t)gd2 * p.N + n0 + slab + c4);
             o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;

@@ -339,34 +339,45 @@ bool build_conv(int level, int stride, int corner_mode, std::vector<int32_t>& bl
       if (r >= 0) { const int sg = r / (int)only.size(), idx = r % (int)only.size(); r = sg * gi.P + pix[idx]; }
     X.P_dst = gi.P;
     emit_side(X, ring_out, h.dgx);
-    // ---- the same remainder in regular form (GinPxSide): global slot list = every (tap, bank) that occurs anywhere
+    // ---- the same remainder in regular form (GinPxSide).  Slots = the TAPS that occur (bank 0).  The few pixels that use a tap
+    // twice (the stitched corners) get one extra ROW per further entry; all rows of such a pixel are marked atomic
+    // (dst = -2 - pixel), every other pixel owns exactly one row and is updated with a plain read-modify-write.
     {
-      int slot_of[32];
-      int nslots = 0;
-      uint32_t uni = 0;
-      for (const auto& row : only) {
-        int cnt[7] = {0, 0, 0, 0, 0, 0, 0};
-        for (const Entry& e : row) uni |= 1u << (cnt[e.tap]++ * 7 + e.tap);
-      }
-      for (int b = 0; b < 32; ++b) slot_of[b] = (uni >> b & 1) ? nslots++ : -1;
-      if (nslots <= GIN_MAX_XSLOTS && !only.empty()) {
-        const int nb = (int)only.size(), rows_total = group * nb, ntiles = (rows_total + GIN_TILE_M - 1) / GIN_TILE_M;
+      int slot_of_tap[7], nslots = 0;
+      uint32_t taps_used = 0;
+      for (const auto& row : only)
+        for (const Entry& e : row) taps_used |= 1u << e.tap;
+      for (int t = 0; t < 7; ++t) slot_of_tap[t] = (taps_used >> t & 1) ? nslots++ : -1;
+      if (!only.empty()) {
+        struct XRow { int pix; bool atomic; std::vector<Entry> ent; };
+        std::vector<XRow> xr;
+        for (size_t i = 0; i < only.size(); ++i) {
+          int cnt[7] = {0, 0, 0, 0, 0, 0, 0}, maxbank = 0;
+          for (const Entry& e : only[i]) maxbank = std::max(maxbank, cnt[e.tap]++);
+          for (int bank = 0; bank <= maxbank; ++bank) {
+            XRow r{pix[i], maxbank > 0, {}};
+            int c2[7] = {0, 0, 0, 0, 0, 0, 0};
+            for (const Entry& e : only[i])
+              if (c2[e.tap]++ == bank) r.ent.push_back(e);
+            xr.push_back(std::move(r));
+          }
+        }
+        const int nb = (int)xr.size(), rows_total = group * nb, ntiles = (rows_total + GIN_TILE_M - 1) / GIN_TILE_M;
         std::vector<int32_t> xsrc((size_t)ntiles * nslots * GIN_TILE_M, GIN_SRC_ZERO), xdst((size_t)ntiles * GIN_TILE_M, -1);
         for (int sg = 0; sg < group; ++sg)
           for (int i = 0; i < nb; ++i) {
             const int r = sg * nb + i, t = r / GIN_TILE_M, rr = r % GIN_TILE_M;
-            xdst[(size_t)t * GIN_TILE_M + rr] = sg * gi.P + pix[i];
-            int cnt[7] = {0, 0, 0, 0, 0, 0, 0};
-            for (const Entry& e : only[i]) {
-              const int slot = slot_of[cnt[e.tap]++ * 7 + e.tap];
+            const int gp = sg * gi.P + xr[i].pix;
+            xdst[(size_t)t * GIN_TILE_M + rr] = xr[i].atomic ? -2 - gp : gp;
+            for (const Entry& e : xr[i].ent) {
               const int code = (e.src >= 0) ? sg * go.P + e.src : -2 - (2 * sg + (-2 - e.src));
-              xsrc[((size_t)t * nslots + slot) * GIN_TILE_M + rr] = code;
+              xsrc[((size_t)t * nslots + slot_of_tap[e.tap]) * GIN_TILE_M + rr] = code;
             }
           }
         GinPxSide& px = h.px;
         px.ntiles = ntiles; px.nslots = nslots;
-        for (int b = 0; b < 32; ++b)
-          if (slot_of[b] >= 0) px.tap[slot_of[b]] = (int8_t)(b % 7);
+        for (int t = 0; t < 7; ++t)
+          if (slot_of_tap[t] >= 0) px.tap[slot_of_tap[t]] = (int8_t)t;
         px.src_off = (int)blob.size();
         blob.insert(blob.end(), xsrc.begin(), xsrc.end());
         px.dst_off = (int)blob.size();

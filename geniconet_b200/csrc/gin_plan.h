@@ -60,16 +60,17 @@ struct GinP2Side {
   int32_t frows_off;          // int32 frows[ntiles][Q]: fine pixel (2*I0, 2*J0_q) of each octet column
 };
 
-// Cross-seam / pole remainder of dgrad in REGULAR form for the patch kernel: the boundary pixels of a sample group, 128 per
-// tile, and one global list of (tap, bank) slots.  src[tile][slot][128] is the dy row the tile's r-th pixel receives through
-// that slot (GIN_SRC_ZERO for most: a pixel has 1-5 entries).  Every tile runs all slots -- a few wasted MMAs buy a kernel
-// without per-tile control flow; zero rows cost no memory traffic (cp.async zero-fill).
+// Cross-seam / pole remainder of dgrad in REGULAR form for the patch kernel: the boundary pixels of a sample group, 128 rows per
+// tile, and one global list of slots = the taps that occur.  src[tile][slot][128] is the dy row the tile's r-th pixel receives
+// through that tap (GIN_SRC_ZERO for most: a pixel has 1-5 entries).  Every tile runs all slots -- a few wasted MMAs buy a kernel
+// without per-tile control flow; zero rows cost no memory traffic (cp.async zero-fill).  A pixel that uses one tap twice (the
+// stitched corners) has one more row per further entry, and ALL its rows carry dst = -2 - pixel: they are added atomically.
 #define GIN_MAX_XSLOTS 16
 struct GinPxSide {
   int32_t ntiles;             // per sample group (0 = not available)
   int32_t nslots;             // <= GIN_MAX_XSLOTS
   int32_t src_off;            // int32 src[ntiles][nslots][128]
-  int32_t dst_off;            // int32 dst[ntiles][128]: pixel inside the sample group or -1
+  int32_t dst_off;            // int32 dst[ntiles][128]: pixel inside the sample group, -1 (no row), or -2 - pixel (atomic add)
   int8_t tap[GIN_MAX_XSLOTS]; // weight index of each slot
 };
 

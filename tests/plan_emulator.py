@@ -364,7 +364,7 @@ def run_px_accumulate(blob, h, px, dy, Wd, dx):
     P_src, P_dst, group = h['dgx']['P_src'], h['dgx']['P_dst'], h['group']
     ring = blob[h['dgx']['ring_off']:h['dgx']['ring_off'] + 10]
     dxf = dx.reshape(B * P_dst, -1)
-    seen = set()
+    seen, atomic = set(), set()
     for G in range((B + group - 1) // group):
         for t in range(px['ntiles']):
             acc = np.zeros((TILE, Wd.shape[2]), dtype=dy.dtype)
@@ -373,10 +373,17 @@ def run_px_accumulate(blob, h, px, dy, Wd, dx):
                 acc += gather_rows(dy, blob[off:off + TILE], G * group, ring, P_src) @ Wd[px['tap'][s]]
             dst = blob[px['dst_off'] + t * TILE: px['dst_off'] + (t + 1) * TILE]
             for r, d in enumerate(dst):
-                if d >= 0:
-                    gd = G * group * P_dst + int(d)
-                    if gd < B * P_dst:
+                d = int(d)
+                if d == -1:
+                    continue
+                is_atomic = d <= -2
+                gd = G * group * P_dst + (-2 - d if is_atomic else d)
+                if gd < B * P_dst:
+                    if is_atomic:
+                        atomic.add(gd)
+                    else:
                         assert gd not in seen               # plain read-modify-write is race free
                         seen.add(gd)
-                        dxf[gd] += acc[r]
+                    dxf[gd] += acc[r]
+    assert not (seen & atomic)                              # a pixel is either plain (one row) or atomic (all its rows)
     return dx
