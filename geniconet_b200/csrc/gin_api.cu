@@ -22,6 +22,7 @@
 #include "gin_narrow.cuh"
 #include "gin_bn.cuh"
 #include "gin_resample.cuh"
+#include "gin_dist.cuh"
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
@@ -487,6 +488,27 @@ int gin_kld_bwd(const float* mu, const float* logvar, const float* dout, float s
   gin::kld_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(mu, logvar, dout, scale * (float)(-0.5 / (double)n), dmu,
                                                                          dlogvar, n);
   return check_launch("kld_bwd");
+}
+
+// ------------------------------------------------------------------ evaluation metric: point-to-mesh distance
+size_t gin_point_mesh_ws_bytes(int B, int N) { return (B <= 0 || N <= 0) ? 0 : (size_t)B * N * sizeof(unsigned long long); }
+
+int gin_point_mesh_distance(const float* points, const float* verts, const int32_t* faces, float* dist, int32_t* face_idx, void* ws, int B,
+                            int N, int V, int F, void* stream) {
+  if (B < 0 || N < 0 || V <= 0 || F <= 0) return fail(GIN_ERR_ARG, "gin_point_mesh_distance: bad sizes B=%d N=%d V=%d F=%d", B, N, V, F);
+  if (B == 0 || N == 0) return GIN_OK;
+  if (!points || !verts || !faces || !dist || !ws) return fail(GIN_ERR_ARG, "gin_point_mesh_distance: null pointer");
+  if (B > 65535) return fail(GIN_ERR_ARG, "gin_point_mesh_distance: B=%d exceeds 65535", B);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)B * N;
+  if (cudaMemsetAsync(ws, 0xFF, n * sizeof(unsigned long long), st) != cudaSuccess) return fail(GIN_ERR_CUDA, "gin_point_mesh_distance: memset failed");
+  dim3 grid((N + gin::dist::kThreads - 1) / gin::dist::kThreads, (F + gin::dist::kChunk - 1) / gin::dist::kChunk, B);
+  if (grid.y > 65535) return fail(GIN_ERR_ARG, "gin_point_mesh_distance: F=%d exceeds %d", F, 65535 * gin::dist::kChunk);
+  gin::dist::point_mesh_kernel<<<grid, gin::dist::kThreads, 0, st>>>(points, verts, faces, (unsigned long long*)ws, N, V, F);
+  int rc = check_launch("point_mesh");
+  if (rc != GIN_OK) return rc;
+  gin::dist::unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const unsigned long long*)ws, dist, face_idx, (long long)n);
+  return check_launch("point_mesh_unpack");
 }
 
 // ------------------------------------------------------------------ fused BatchNorm + activation + operand cast

@@ -202,6 +202,15 @@ int gin_p2p_loss_bwd(const void* plan_host, const void* plan_dev, const float* x
                      const float* target, float f_pos, float f_nor, float f_lap,
                      const float* dout /* device scalar */, float* dx, void* ws, int B, void* stream);
 
+/* ------------------------------------------------------------------ device: evaluation metric --- */
+/* ico_utils.py:26-44 computeDistance(mode='point2mesh') -> kaolin 0.9.1 point_to_mesh_distance: per point the SQUARED distance
+ * to the closest triangle, and that triangle's index (lowest index among equal distances).
+ * points [B][N][3], verts [B][V][3] fp32, faces [F][3] int32 (shared by the batch), dist [B][N] fp32, face_idx [B][N] int32 or NULL.
+ * ws: gin_point_mesh_ws_bytes(B, N). */
+size_t gin_point_mesh_ws_bytes(int B, int N);
+int gin_point_mesh_distance(const float* points, const float* verts, const int32_t* faces, float* dist, int32_t* face_idx,
+                            void* ws, int B, int N, int V, int F, void* stream);
+
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
 int64_t gin_launch_count(void);
 
