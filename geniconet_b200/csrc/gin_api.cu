@@ -23,6 +23,7 @@
 #include "gin_bn.cuh"
 #include "gin_resample.cuh"
 #include "gin_dist.cuh"
+#include "gin_head.cuh"
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
@@ -240,6 +241,7 @@ size_t gin_hexconv_wgrad_ws_bytes(int Cin, int Cout) {
   if (Cin <= 0 || Cout <= 0) return 0;
   size_t n = (size_t)28 * Cin * Cout;
   if (gin::tc_supported(Cin, Cout)) n += gin::wg2::partial_bytes(Cin, Cout);
+  if (Cin == 3) n += gin::narrow::wgrad_partial_bytes(Cin, Cout);       // per-CTA sums of the xyz-layer kernel
   return n;
 }
 
@@ -284,9 +286,9 @@ static int wgrad_common(const GinConvPlanHdr* h, const void* plan_dev, const flo
       g_launches.fetch_add(1, std::memory_order_relaxed);
     } else if (impl == GIN_IMPL_AUTO && gin::narrow_supported(Cin, Cout, side)) {
       GinSrcView X{x, (long long)sb, (long long)sp, (long long)sc, side.P_src};
-      rc = gin::launch_narrow_wgrad(plan_words(plan_dev), side, h->group, X, dy, dWp, db, B, Cin, Cout, st);   // db comes with it
+      rc = gin::launch_narrow_wgrad(plan_words(plan_dev), side, h->group, X, dy, dWp, db, dWp + (size_t)7 * Cin * Cout, B, Cin, Cout, st);   // db comes with it
       if (rc != GIN_OK) return fail(rc, "narrow wgrad launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-      g_launches.fetch_add(1, std::memory_order_relaxed);
+      g_launches.fetch_add(2, std::memory_order_relaxed);
       db = nullptr;
     } else {
       GinSrcView X{x, (long long)sb, (long long)sp, (long long)sc, side.P_src};
@@ -488,6 +490,41 @@ int gin_kld_bwd(const float* mu, const float* logvar, const float* dout, float s
   gin::kld_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(mu, logvar, dout, scale * (float)(-0.5 / (double)n), dmu,
                                                                          dlogvar, n);
   return check_launch("kld_bwd");
+}
+
+// ------------------------------------------------------------------ decoder head: 1x1 conv + tanh
+size_t gin_head_ws_bytes(void) { return (size_t)gin::head::MAX_CTAS * gin::head::PART * sizeof(float); }
+
+static int head_args_ok(const char* what, int B, int64_t P, int Cin, int Cout) {
+  if (B < 0 || P <= 0) return fail(GIN_ERR_ARG, "%s: bad sizes B=%d P=%lld", what, B, (long long)P);
+  if (Cin != gin::head::CIN || Cout != gin::head::COUT) return fail(GIN_ERR_UNSUPPORTED, "%s: only %d -> %d channels (got %d -> %d)", what, gin::head::CIN, gin::head::COUT, Cin, Cout);
+  return GIN_OK;
+}
+
+int gin_head_fwd(const float* x, const float* w, const float* bias, float* y, int B, int64_t P, int Cin, int Cout, void* stream) {
+  int rc = head_args_ok("gin_head_fwd", B, P, Cin, Cout);
+  if (rc != GIN_OK || B == 0) return rc;
+  if (!x || !w || !bias || !y) return fail(GIN_ERR_ARG, "gin_head_fwd: null pointer");
+  if (((uintptr_t)x | (uintptr_t)w) & 15) return fail(GIN_ERR_ARG, "gin_head_fwd: x and w must be 16-byte aligned");
+  const long long rows = (long long)B * P;
+  gin::head::fwd_kernel<<<gin::head::grid_for_rows(rows), gin::head::kThreads, 0, (cudaStream_t)stream>>>(x, w, bias, y, rows, P);
+  return check_launch("head_fwd");
+}
+
+int gin_head_bwd(const float* x, const float* w, const float* y, const float* dy, float* dx, float* dw, float* db, void* ws, int B, int64_t P,
+                 int Cin, int Cout, void* stream) {
+  int rc = head_args_ok("gin_head_bwd", B, P, Cin, Cout);
+  if (rc != GIN_OK) return rc;
+  if (!x || !w || !y || !dy || !dx || !dw || !db || !ws) return fail(GIN_ERR_ARG, "gin_head_bwd: null pointer");
+  if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)dx) & 15) return fail(GIN_ERR_ARG, "gin_head_bwd: x, w and dx must be 16-byte aligned");
+  const long long rows = (long long)B * P;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = gin::head::grid_for_rows(rows);
+  gin::head::bwd_kernel<<<grid, gin::head::kThreads, 0, st>>>(x, w, y, dy, dx, (float*)ws, rows, P);
+  rc = check_launch("head_bwd");
+  if (rc != GIN_OK) return rc;
+  gin::head::bwd_final_kernel<<<1, 256, 0, st>>>((const float*)ws, grid, dw, db);
+  return check_launch("head_bwd_final");
 }
 
 // ------------------------------------------------------------------ evaluation metric: point-to-mesh distance

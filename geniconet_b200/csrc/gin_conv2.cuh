@@ -364,14 +364,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
     for (int fl = 0; fl < nflush; ++fl, ++wc) {
       const int G = T / p.ntiles, t = T - G * p.ntiles;
       long long gdl;
-      bool atomic_row = false;
+      bool extra_row = false;
       if (p.dst_tab_off >= 0) {
-        int dr = __ldg(p.plan + p.dst_tab_off + t * BM + row);
-        if (dr <= -2) { atomic_row = true; dr = -2 - dr; }       // a pixel with several rows: all of them add atomically
+        const int dr = __ldg(p.plan + p.dst_tab_off + t * BM + row);
+        extra_row = dr == -3;                         // a further row of the pixel above (same 32-row group): folded in below
         gdl = dr >= 0 ? (long long)G * p.group * p.P_dst + dr : total_pix;
       } else gdl = (long long)G * p.group * p.P_dst + tile_base[t * Q + oq] + row_off + p.dst_plane_off[fl];
-      int gd = gdl < total_pix ? (int)gdl : -1;       // B*P < 2^31 is checked by the launcher
-      if (atomic_row && gd >= 0) gd = -2 - gd;
+      const int gd = extra_row ? -3 : (gdl < total_pix ? (int)gdl : -1);       // B*P < 2^31 is checked by the launcher
       const uint32_t ab = wc & 1;
       { PROF_T0(); mbar_wait(&acc_full[ab], (wc >> 1) & 1u); PROF_ADD(pw[0]); }
       tc_fence_after();
@@ -397,13 +396,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r2 = 4 * i + rsub;
-          int gd2 = __shfl_sync(0xffffffffu, gd, r2);
+          const int gd2 = __shfl_sync(0xffffffffu, gd, r2);
           float4 o = *reinterpret_cast<const float4*>(my_stage + r2 * STAGE_PITCH + c4 * 4);
           o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-          if (gd2 <= -2) {                                // atomic row (accumulate mode only)
-            float* yp = p.Y + (size_t)(-2 - gd2) * p.N + n0 + slab + c4;
-            atomicAdd(yp, o.x); atomicAdd(yp + 1, o.y); atomicAdd(yp + 2, o.z); atomicAdd(yp + 3, o.w);
-            gd2 = -1;
+          if (p.dst_tab_off >= 0) {                       // seam form: up to two extra rows below belong to this pixel
+            const int x1 = __shfl_sync(0xffffffffu, gd, (r2 + 1) & 31), x2 = __shfl_sync(0xffffffffu, gd, (r2 + 2) & 31);
+            if (r2 + 1 < 32 && x1 == -3) {
+              const float4 u = *reinterpret_cast<const float4*>(my_stage + (r2 + 1) * STAGE_PITCH + c4 * 4);
+              o.x += u.x; o.y += u.y; o.z += u.z; o.w += u.w;
+              if (r2 + 2 < 32 && x2 == -3) {
+                const float4 w2 = *reinterpret_cast<const float4*>(my_stage + (r2 + 2) * STAGE_PITCH + c4 * 4);
+                o.x += w2.x; o.y += w2.y; o.z += w2.z; o.w += w2.w;
+              }
+            }
           }
           if (p.accumulate && gd2 >= 0) {
             const float4 old = *reinterpret_cast<const float4*>(p.Y + (size_t)gd2 * p.N + n0 + slab + c4);
@@ -422,9 +427,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
     if (STATS) {
       // column sums of this CTA's rows: lanes that share (lane & 7) hold the same columns; the four TMEM-quarter warps of a
       // slab set meet in shared memory (the staging area is free now); one plain store per column, no global atomics
-      float* sred = reinterpret_cast<float*>(stage_smem);              // [2][N_TILE]
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-      for (int i = (warp - W_EPI0) * 32 + lane; i < 2 * N_TILE; i += EPI_WARPS * 32) sred[i] = 0.f;
+      float* sred = reinterpret_cast<float*>(stage_smem);              // [4 quarters][2][N_TILE]
+      // one slot per (TMEM quarter, column): every slot is written exactly once, the four quarters are then added in a fixed
+      // order -- no atomics, so the statistics (and everything downstream of them) are reproducible run to run
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
 #pragma unroll
       for (int si = 0; si < NS; ++si)
@@ -435,13 +440,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
           b += __shfl_xor_sync(0xffffffffu, b, 8); b += __shfl_xor_sync(0xffffffffu, b, 16);
           if (lane < 8) {
             const int col = hslab * 32 + si * 64 + c4 + k;
-            atomicAdd(&sred[col], a);
-            atomicAdd(&sred[N_TILE + col], b);
+            sred[(q * 2) * N_TILE + col] = a;
+            sred[(q * 2 + 1) * N_TILE + col] = b;
           }
         }
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       float* out = p.stats + (size_t)(blockIdx.x / p.n_blocks) * 2 * p.N + n0;
-      for (int i = (warp - W_EPI0) * 32 + lane; i < 2 * N_TILE; i += EPI_WARPS * 32) out[(i / N_TILE) * p.N + (i % N_TILE)] = sred[i];
+      for (int i = (warp - W_EPI0) * 32 + lane; i < 2 * N_TILE; i += EPI_WARPS * 32)
+        out[(i / N_TILE) * p.N + (i % N_TILE)] = (sred[i] + sred[2 * N_TILE + i]) + (sred[4 * N_TILE + i] + sred[6 * N_TILE + i]);
     }
 #ifdef GIN_PROF
     if (blockIdx.x == 0 && lane == 0 && e == 0) printf("epilogue: total %lld wait_acc_full %lld tmem_ld %lld tiles %u\n", clock64() - t_begin, pw[0], pw[1], wc);

@@ -340,40 +340,50 @@ bool build_conv(int level, int stride, int corner_mode, std::vector<int32_t>& bl
     X.P_dst = gi.P;
     emit_side(X, ring_out, h.dgx);
     // ---- the same remainder in regular form (GinPxSide).  Slots = the TAPS that occur (bank 0).  The few pixels that use a tap
-    // twice (the stitched corners) get one extra ROW per further entry; all rows of such a pixel are marked atomic
-    // (dst = -2 - pixel), every other pixel owns exactly one row and is updated with a plain read-modify-write.
+    // twice (the stitched corners) get one extra ROW per further entry, placed directly below the pixel's first row and inside
+    // the same 32-row group (dst = -3): the epilogue warp that owns the group adds them to the row above before its single
+    // read-modify-write, so the pass needs no atomics and its result does not depend on any execution order.
     {
       int slot_of_tap[7], nslots = 0;
       uint32_t taps_used = 0;
       for (const auto& row : only)
         for (const Entry& e : row) taps_used |= 1u << e.tap;
       for (int t = 0; t < 7; ++t) slot_of_tap[t] = (taps_used >> t & 1) ? nslots++ : -1;
-      if (!only.empty()) {
-        struct XRow { int pix; bool atomic; std::vector<Entry> ent; };
-        std::vector<XRow> xr;
-        for (size_t i = 0; i < only.size(); ++i) {
-          int cnt[7] = {0, 0, 0, 0, 0, 0, 0}, maxbank = 0;
-          for (const Entry& e : only[i]) maxbank = std::max(maxbank, cnt[e.tap]++);
-          for (int bank = 0; bank <= maxbank; ++bank) {
-            XRow r{pix[i], maxbank > 0, {}};
-            int c2[7] = {0, 0, 0, 0, 0, 0, 0};
-            for (const Entry& e : only[i])
-              if (c2[e.tap]++ == bank) r.ent.push_back(e);
-            xr.push_back(std::move(r));
+      struct XRow { int pix; int span; std::vector<Entry> ent; };      // span: rows of this pixel (on its first row), 0 on extra rows
+      std::vector<XRow> xr;
+      bool ok = !only.empty();
+      for (size_t i = 0; i < only.size() && ok; ++i) {
+        int cnt[7] = {0, 0, 0, 0, 0, 0, 0}, maxbank = 0;
+        for (const Entry& e : only[i]) maxbank = std::max(maxbank, cnt[e.tap]++);
+        if (maxbank > 2) ok = false;                                   // the epilogue folds at most two extra rows
+        for (int bank = 0; bank <= maxbank; ++bank) {
+          XRow r{pix[i], bank == 0 ? maxbank + 1 : 0, {}};
+          int c2[7] = {0, 0, 0, 0, 0, 0, 0};
+          for (const Entry& e : only[i])
+            if (c2[e.tap]++ == bank) r.ent.push_back(e);
+          xr.push_back(std::move(r));
+        }
+      }
+      if (ok) {
+        std::vector<std::pair<int, int>> seq;                          // (sample in group, index into xr) or (-1, -1): padding row
+        for (int sg = 0; sg < group; ++sg)
+          for (size_t i = 0; i < xr.size(); ++i) {
+            if (xr[i].span > 0)
+              while ((int)(seq.size() % 32) + xr[i].span > 32) seq.emplace_back(-1, -1);
+            seq.emplace_back(sg, (int)i);
+          }
+        const int rows_total = (int)seq.size(), ntiles = (rows_total + GIN_TILE_M - 1) / GIN_TILE_M;
+        std::vector<int32_t> xsrc((size_t)ntiles * nslots * GIN_TILE_M, GIN_SRC_ZERO), xdst((size_t)ntiles * GIN_TILE_M, -1);
+        for (int r = 0; r < rows_total; ++r) {
+          if (seq[r].first < 0) continue;
+          const int sg = seq[r].first, t = r / GIN_TILE_M, rr = r % GIN_TILE_M;
+          const XRow& row = xr[seq[r].second];
+          xdst[(size_t)t * GIN_TILE_M + rr] = row.span > 0 ? sg * gi.P + row.pix : -3;
+          for (const Entry& e : row.ent) {
+            const int code = (e.src >= 0) ? sg * go.P + e.src : -2 - (2 * sg + (-2 - e.src));
+            xsrc[((size_t)t * nslots + slot_of_tap[e.tap]) * GIN_TILE_M + rr] = code;
           }
         }
-        const int nb = (int)xr.size(), rows_total = group * nb, ntiles = (rows_total + GIN_TILE_M - 1) / GIN_TILE_M;
-        std::vector<int32_t> xsrc((size_t)ntiles * nslots * GIN_TILE_M, GIN_SRC_ZERO), xdst((size_t)ntiles * GIN_TILE_M, -1);
-        for (int sg = 0; sg < group; ++sg)
-          for (int i = 0; i < nb; ++i) {
-            const int r = sg * nb + i, t = r / GIN_TILE_M, rr = r % GIN_TILE_M;
-            const int gp = sg * gi.P + xr[i].pix;
-            xdst[(size_t)t * GIN_TILE_M + rr] = xr[i].atomic ? -2 - gp : gp;
-            for (const Entry& e : xr[i].ent) {
-              const int code = (e.src >= 0) ? sg * go.P + e.src : -2 - (2 * sg + (-2 - e.src));
-              xsrc[((size_t)t * nslots + slot_of_tap[e.tap]) * GIN_TILE_M + rr] = code;
-            }
-          }
         GinPxSide& px = h.px;
         px.ntiles = ntiles; px.nslots = nslots;
         for (int t = 0; t < 7; ++t)

@@ -125,11 +125,11 @@ fwd_kernel(const int32_t* __restrict__ plan, GinSide side, GinSrcView X, const f
 }
 
 // ------------------------------------------------------------------------------------------------ wgrad (+ bias grad)
-// dWp is [7][CIN][COUT] (zeroed by the caller), db [COUT] (zeroed by the caller) or null.
+// partial [gridDim.x][7*CIN + 1][COUT]: this CTA's sums of dW ([7][CIN][COUT]) and of the bias gradient; wgrad_final_kernel adds the rows.
 template <int CIN, int CPL>
 __global__ void __launch_bounds__(THREADS, CPL <= 2 ? 3 : 2)
-wgrad_kernel(const int32_t* __restrict__ plan, GinSide side, GinSrcView X, const float* __restrict__ dY, float* __restrict__ dWp,
-             float* __restrict__ db, int group, int B, int total_tiles) {
+wgrad_kernel(const int32_t* __restrict__ plan, GinSide side, GinSrcView X, const float* __restrict__ dY, float* __restrict__ partial,
+             int group, int B, int total_tiles) {
   extern __shared__ __align__(16) float smem_f[];
   constexpr int COUT = 32 * CPL;
   constexpr int NACC = 7 * CIN + 1;                    // + bias
@@ -220,23 +220,42 @@ wgrad_kernel(const int32_t* __restrict__ plan, GinSide side, GinSrcView X, const
       }
     }
   }
-  // block reduction through shared memory, then one atomic per (accumulator, channel) and CTA
+  // block reduction through shared memory, warp after warp in a fixed order, then this CTA's sums go to its own row of
+  // `partial` (wgrad_final_kernel adds the rows, again in a fixed order): no atomics, reproducible run to run
   __syncthreads();
   for (int i = threadIdx.x; i < NACC * COUT; i += THREADS) red[i] = 0.f;
   __syncthreads();
+#pragma unroll 1
+  for (int w = 0; w < WARPS; ++w) {
+    if (warp == w) {
 #pragma unroll
-  for (int t = 0; t < 7; ++t)
+      for (int t = 0; t < 7; ++t)
 #pragma unroll
-    for (int c = 0; c < CIN; ++c)
+        for (int c = 0; c < CIN; ++c)
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) atomicAdd(red + (t * CIN + c) * COUT + lane * CPL + k, acc[t][c][k]);
+          for (int k = 0; k < CPL; ++k) red[(t * CIN + c) * COUT + lane * CPL + k] += acc[t][c][k];
 #pragma unroll
-  for (int k = 0; k < CPL; ++k) atomicAdd(red + 7 * CIN * COUT + lane * CPL + k, bsum[k]);
-  __syncthreads();
-  for (int i = threadIdx.x; i < 7 * CIN * COUT; i += THREADS) atomicAdd(dWp + i, red[i]);
-  if (db)
-    for (int i = threadIdx.x; i < COUT; i += THREADS) atomicAdd(db + i, red[7 * CIN * COUT + i]);
+      for (int k = 0; k < CPL; ++k) red[7 * CIN * COUT + lane * CPL + k] += bsum[k];
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < NACC * COUT; i += THREADS) partial[(size_t)blockIdx.x * NACC * COUT + i] = red[i];
 }
+
+// dWp[i] / db[i]: sum over the CTAs' rows, one thread per output, two accumulators, fixed order
+__global__ void wgrad_final_kernel(const float* __restrict__ partial, int nparts, int n_w, int n_b, float* __restrict__ dWp, float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, n = n_w + n_b;
+  if (i >= n) return;
+  float s0 = 0.f, s1 = 0.f;
+  int k = 0;
+#pragma unroll 8
+  for (; k + 1 < nparts; k += 2) { s0 += partial[(size_t)k * n + i]; s1 += partial[(size_t)(k + 1) * n + i]; }
+  if (k < nparts) s0 += partial[(size_t)k * n + i];
+  if (i < n_w) dWp[i] = s0 + s1; else if (db) db[i - n_w] = s0 + s1;
+}
+
+constexpr int WGRAD_MAX_CTAS = 148 * 3;
+inline size_t wgrad_partial_bytes(int cin, int cout) { return (size_t)WGRAD_MAX_CTAS * (7 * cin + 1) * cout * 4; }
 
 inline size_t fwd_smem(int cin, int cout, int max_slots) { return (size_t)(7 * cin * cout + max_slots * cin * TM) * 4 + TM * 8; }
 inline size_t wgrad_smem(int cin, int cout, int max_slots) { return (size_t)((7 * cin + 1) * cout + max_slots * cin * TM) * 4 + TM * 8; }
@@ -270,20 +289,24 @@ inline int launch_narrow_fwd(const int32_t* plan_dev, const GinSide& side, int g
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
+// partial: narrow::wgrad_partial_bytes(Cin, Cout) of workspace.  dWp [7][Cin][Cout] and db (or null) are plainly overwritten.
 inline int launch_narrow_wgrad(const int32_t* plan_dev, const GinSide& side, int group, GinSrcView X, const float* dY, float* dWp, float* db,
-                               int B, int Cin, int Cout, cudaStream_t st) {
+                               float* partial, int B, int Cin, int Cout, cudaStream_t st) {
   const int groups = (B + group - 1) / group, total = groups * side.ntiles;
   const size_t smem = narrow::wgrad_smem(Cin, Cout, side.max_slots);
-  const int grid = total < 148 * 3 ? total : 148 * 3;
+  const int grid = total < narrow::WGRAD_MAX_CTAS ? total : narrow::WGRAD_MAX_CTAS;
   if (Cout == 64) {
     auto k = narrow::wgrad_kernel<3, 2>;
     if (narrow_config(k, smem)) return -3;
-    k<<<grid, narrow::THREADS, smem, st>>>(plan_dev, side, X, dY, dWp, db, group, B, total);
+    k<<<grid, narrow::THREADS, smem, st>>>(plan_dev, side, X, dY, partial, group, B, total);
   } else {
     auto k = narrow::wgrad_kernel<3, 4>;
     if (narrow_config(k, smem)) return -3;
-    k<<<grid, narrow::THREADS, smem, st>>>(plan_dev, side, X, dY, dWp, db, group, B, total);
+    k<<<grid, narrow::THREADS, smem, st>>>(plan_dev, side, X, dY, partial, group, B, total);
   }
+  if (cudaGetLastError() != cudaSuccess) return -3;
+  const int n_w = 7 * Cin * Cout;
+  narrow::wgrad_final_kernel<<<(n_w + Cout + 255) / 256, 256, 0, st>>>(partial, grid, n_w, Cout, dWp, db);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 

@@ -64,13 +64,14 @@ struct GinP2Side {
 // tile, and one global list of slots = the taps that occur.  src[tile][slot][128] is the dy row the tile's r-th pixel receives
 // through that tap (GIN_SRC_ZERO for most: a pixel has 1-5 entries).  Every tile runs all slots -- a few wasted MMAs buy a kernel
 // without per-tile control flow; zero rows cost no memory traffic (cp.async zero-fill).  A pixel that uses one tap twice (the
-// stitched corners) has one more row per further entry, and ALL its rows carry dst = -2 - pixel: they are added atomically.
+// stitched corners) has one more row per further entry directly below its first row, inside the same 32-row group, with
+// dst = -3: the epilogue adds such rows to the row above before the store (no atomics).
 #define GIN_MAX_XSLOTS 16
 struct GinPxSide {
   int32_t ntiles;             // per sample group (0 = not available)
   int32_t nslots;             // <= GIN_MAX_XSLOTS
   int32_t src_off;            // int32 src[ntiles][nslots][128]
-  int32_t dst_off;            // int32 dst[ntiles][128]: pixel inside the sample group, -1 (no row), or -2 - pixel (atomic add)
+  int32_t dst_off;            // int32 dst[ntiles][128]: pixel inside the sample group, -1 (no row), or -3 (extra row: add to the nearest pixel row above)
   int8_t tap[GIN_MAX_XSLOTS]; // weight index of each slot
 };
 

@@ -331,3 +331,48 @@ def run_chain(x, mods):
     """Forward of the module list `mods` (see chain_supported) on the fused path; x fp32 CUDA, returns the fp32 output map."""
     mods = list(mods)
     return _Chain.apply(x, mods, *chain_params(mods))
+
+
+# ------------------------------------------------------------------ decoder head: Conv2d(64, 3, 1) -> Tanh (models.py:151-154)
+def head_supported(head, x):
+    """head = nn.Sequential(Conv2d 1x1 64->3 with bias, Tanh) without hooks, x a dense fp32 CUDA map."""
+    mods = list(head)
+    if len(mods) != 2 or not isinstance(mods[0], torch.nn.Conv2d) or not isinstance(mods[1], torch.nn.Tanh):
+        return False
+    c = mods[0]
+    if (c.kernel_size != (1, 1) or c.stride != (1, 1) or c.padding != (0, 0) or c.groups != 1 or c.bias is None
+            or c.in_channels != 64 or c.out_channels != 3 or c.weight.dtype != torch.float32):
+        return False
+    if any(m._forward_hooks or m._forward_pre_hooks or m._backward_hooks for m in [head] + mods):
+        return False
+    return x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 64
+
+
+class _Head(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        from .ico_conv import as_channels_last
+        B, C, H, W = x.shape
+        xs = as_channels_last(x)                              # [B*P][64] in memory; no copy after a fused chain
+        w = weight.reshape(3, C).contiguous()
+        y = torch.empty((B, 3, H, W), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib.gin_head_fwd(xs.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), B, H * W, C, 3, _stream()), 'gin_head_fwd')
+        ctx.save_for_backward(xs, w, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xs, w, y = ctx.saved_tensors
+        B, C, H, W = xs.shape
+        dy = dy.contiguous()
+        dx = torch.empty_strided(xs.shape, xs.stride(), dtype=torch.float32, device=xs.device)
+        dw = torch.empty((3, C, 1, 1), dtype=torch.float32, device=xs.device)
+        db = torch.empty(3, dtype=torch.float32, device=xs.device)
+        ws = _empty(_lib.lib.gin_head_ws_bytes(), torch.uint8, xs.device)
+        _lib.check(_lib.lib.gin_head_bwd(xs.data_ptr(), w.data_ptr(), y.data_ptr(), dy.data_ptr(), dx.data_ptr(), dw.data_ptr(), db.data_ptr(),
+                                         ws.data_ptr(), B, H * W, C, 3, _stream()), 'gin_head_bwd')
+        return dx, dw, db
+
+
+def run_head(head, x):
+    return _Head.apply(x, head[0].weight, head[0].bias)

@@ -24,11 +24,14 @@ from .reparam import reparameterize as _reparameterize
 # Fused execution of the encoder / decoder bodies (geniconet_b200/fused.py) in training mode; GIN_FUSED=0 or
 # set_fused(False) runs every module on its own, exactly as the unmodified reference models.py does.
 _FUSED = os.environ.get('GIN_FUSED', '1') != '0'
+_HEAD = os.environ.get('GIN_HEAD', '1') != '0'           # the decoder head through gin_head_* (A/B: GIN_HEAD=0 keeps Conv2d + Tanh)
 
 
-def set_fused(flag):
-    global _FUSED
+def set_fused(flag, head=None):
+    global _FUSED, _HEAD
     _FUSED = bool(flag)
+    if head is not None:
+        _HEAD = bool(head)
 
 
 def _run(mods, x):
@@ -87,6 +90,13 @@ class _ResidualBlock(torch.nn.Module):
         main = self.icobn01(self.conv01(relu(self.icobn00(self.conv00(a)))))
         skip = self.icobn10(self.conv10(b))
         return relu(main + skip)
+
+
+def _head(head, x):
+    """The decoder head `Conv2d(64,3,1) -> Tanh` (models.py:151-154): one kernel each way instead of the stock modules."""
+    if _FUSED and _HEAD and isinstance(head, torch.nn.Sequential) and _fused.head_supported(head, x):
+        return _fused.run_head(head, x)
+    return head(x)
 
 
 class BasicIcoS2SDownBlock(_ResidualBlock):
@@ -192,8 +202,8 @@ class ico2ico(torch.nn.Module):
 
     def forward(self, x):
         if isinstance(self.enc, torch.nn.Identity) and not self.enc._forward_hooks:
-            return self.enc2icoConv(_run(list(self.encoder) + list(self.decoder), x))       # one fused chain through both halves
-        return self.enc2icoConv(_run(self.decoder, self.enc(_run(self.encoder, x))))
+            return _head(self.enc2icoConv, _run(list(self.encoder) + list(self.decoder), x))       # one fused chain through both halves
+        return _head(self.enc2icoConv, _run(self.decoder, self.enc(_run(self.encoder, x))))
 
 
 class ico2enc(torch.nn.Module):
@@ -212,7 +222,7 @@ class enc2ico(torch.nn.Module):
         self.decoder, self.enc2icoConv = createenc2ico(params['ico']['corner_mode'], params['ico2ico']['model'], self.subdivisions)
 
     def forward(self, x):
-        return self.enc2icoConv(self.decoder(x))
+        return _head(self.enc2icoConv, self.decoder(x))
 
 
 def _latent_head(params, level):
@@ -246,7 +256,7 @@ class ico2ico_vae(VAE):
         return self.mu_hook(self.mu(h)), self.logvar_hook(self.logvar(h))
 
     def decode(self, z):
-        return self.final_layer(_run(self.decoder, self.reparameterize_hook(z)))
+        return _head(self.final_layer, _run(self.decoder, self.reparameterize_hook(z)))
 
 
 class ico2enc_vae(VAE):
@@ -279,7 +289,7 @@ class enc2ico_vae(VAE):
         return torch.add(trn_mean, trn_logvar * torch.randn(trn_logvar.shape))
 
     def decode(self, z):
-        return self.final_layer(self.decoder(z))
+        return _head(self.final_layer, self.decoder(z))
 
     def forward(self, x):
         return self.decode(x), torch.tensor([]), torch.tensor([])

@@ -202,6 +202,15 @@ int gin_p2p_loss_bwd(const void* plan_host, const void* plan_dev, const float* x
                      const float* target, float f_pos, float f_nor, float f_lap,
                      const float* dout /* device scalar */, float* dx, void* ws, int B, void* stream);
 
+/* ------------------------------------------------------------------ device: decoder head --- */
+/* `Conv2d(64,3,1) -> Tanh` (models.py:151-154) over a pixel-major activation: x [B*P][Cin] fp32, w [Cout][Cin], bias [Cout],
+ * y / dy [B][Cout][P] (plain NCHW), dx [B*P][Cin], dw [Cout][Cin], db [Cout].  Only Cin = 64, Cout = 3 (GIN_ERR_UNSUPPORTED
+ * otherwise: callers keep the stock modules).  ws: gin_head_ws_bytes(). */
+size_t gin_head_ws_bytes(void);
+int gin_head_fwd(const float* x, const float* w, const float* bias, float* y, int B, int64_t P, int Cin, int Cout, void* stream);
+int gin_head_bwd(const float* x, const float* w, const float* y, const float* dy, float* dx, float* dw, float* db, void* ws,
+                 int B, int64_t P, int Cin, int Cout, void* stream);
+
 /* ------------------------------------------------------------------ device: evaluation metric --- */
 /* ico_utils.py:26-44 computeDistance(mode='point2mesh') -> kaolin 0.9.1 point_to_mesh_distance: per point the SQUARED distance
  * to the closest triangle, and that triangle's index (lowest index among equal distances).

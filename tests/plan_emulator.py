@@ -364,7 +364,7 @@ def run_px_accumulate(blob, h, px, dy, Wd, dx):
     P_src, P_dst, group = h['dgx']['P_src'], h['dgx']['P_dst'], h['group']
     ring = blob[h['dgx']['ring_off']:h['dgx']['ring_off'] + 10]
     dxf = dx.reshape(B * P_dst, -1)
-    seen, atomic = set(), set()
+    seen = set()
     for G in range((B + group - 1) // group):
         for t in range(px['ntiles']):
             acc = np.zeros((TILE, Wd.shape[2]), dtype=dy.dtype)
@@ -374,16 +374,20 @@ def run_px_accumulate(blob, h, px, dy, Wd, dx):
             dst = blob[px['dst_off'] + t * TILE: px['dst_off'] + (t + 1) * TILE]
             for r, d in enumerate(dst):
                 d = int(d)
-                if d == -1:
+                if d < 0:
+                    assert d in (-1, -3)
                     continue
-                is_atomic = d <= -2
-                gd = G * group * P_dst + (-2 - d if is_atomic else d)
+                tot = acc[r].copy()
+                for k in (1, 2):                            # extra rows (dst -3) directly below, inside the same 32-row group
+                    if (r + k) // 32 == r // 32 and r + k < TILE and all(int(dst[r + j]) == -3 for j in range(1, k + 1)):
+                        tot = tot + acc[r + k]
+                gd = G * group * P_dst + d
                 if gd < B * P_dst:
-                    if is_atomic:
-                        atomic.add(gd)
-                    else:
-                        assert gd not in seen               # plain read-modify-write is race free
-                        seen.add(gd)
-                    dxf[gd] += acc[r]
-    assert not (seen & atomic)                              # a pixel is either plain (one row) or atomic (all its rows)
+                    assert gd not in seen                   # one read-modify-write per pixel: race free without atomics
+                    seen.add(gd)
+                    dxf[gd] += tot
+            for r, d in enumerate(dst):                     # every extra row has its pixel row at most two above, same group
+                if int(d) == -3:
+                    k = 1 if int(dst[r - 1]) >= 0 else 2
+                    assert r - k >= 0 and (r - k) // 32 == r // 32 and int(dst[r - k]) >= 0 and all(int(dst[r - j]) == -3 for j in range(0, k))
     return dx

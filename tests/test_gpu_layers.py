@@ -372,3 +372,32 @@ def test_alternative_kernel_paths_match_oracle(env):
         assert set(rels) == {'fwd', 'dgrad', 'wgrad'}, out.stdout
         for k, v in rels.items():
             assert float(v) < 2e-3, (env, spec, k, v)
+
+
+@pytest.mark.parametrize('level,B', [(1, 3), (2, 1), (5, 4)])
+def test_decoder_head_matches_float64(level, B):
+    """Conv2d(64,3,1) -> Tanh (models.py:151-154) through gin_head_fwd / gin_head_bwd against the same maths in float64; level 1
+    has P = 40, so the 32-pixel blocks straddle samples and the last one is ragged."""
+    from geniconet_b200 import fused
+    n = 2 ** level
+    g = torch.Generator().manual_seed(level)
+    head = torch.nn.Sequential(torch.nn.Conv2d(64, 3, kernel_size=(1, 1)), torch.nn.Tanh()).cuda()
+    x = torch.randn(B, 64, 5 * n, 2 * n, generator=g).cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    gy = torch.randn(B, 3, 5 * n, 2 * n, generator=g).cuda()
+    assert fused.head_supported(head, x)
+    y = fused.run_head(head, x)
+    assert y.shape == (B, 3, 5 * n, 2 * n) and y.is_contiguous()
+    y.backward(gy)
+    w64, b64, x64 = head[0].weight.detach().double().reshape(3, 64), head[0].bias.detach().double(), x.detach().double().requires_grad_(True)
+    w64.requires_grad_(True); b64.requires_grad_(True)
+    y64 = torch.tanh(torch.einsum('oc,bchw->bohw', w64, x64) + b64[None, :, None, None])
+    y64.backward(gy.double())
+    assert (y.double() - y64).abs().max().item() <= 2e-6
+    assert (x.grad.double() - x64.grad).abs().max().item() <= 1e-5 * x64.grad.abs().max().item()
+    assert (head[0].weight.grad.double().reshape(3, 64) - w64.grad).abs().max().item() <= 1e-4 * w64.grad.abs().max().item()
+    assert (head[0].bias.grad.double() - b64.grad).abs().max().item() <= 1e-4 * max(1.0, b64.grad.abs().max().item())
+    # a hooked or differently shaped head keeps the stock modules
+    hooked = torch.nn.Sequential(torch.nn.Conv2d(64, 3, kernel_size=(1, 1)), torch.nn.Tanh()).cuda()
+    hooked[1].register_forward_hook(lambda m, i, o: None)
+    assert not fused.head_supported(hooked, x)
+    assert not fused.head_supported(torch.nn.Sequential(torch.nn.Conv2d(32, 3, kernel_size=(1, 1)), torch.nn.Tanh()).cuda(), x)

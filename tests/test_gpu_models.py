@@ -168,36 +168,51 @@ def test_cuda_path_reproduces_reference_golden():
     assert abs(x3.grad.norm().item() - g3['grad_norm']) <= 1e-4 * g3['grad_norm']
 
 
+def _seeded_step(name, level, x, tgt, factors, fused, impl, head=None):
+    """One forward + loss + backward from the deterministic parameter fill; returns (loss, grads, buffers)."""
+    from geniconet_b200 import models as gm, losses, reparam
+    from geniconet_b200.ico_conv import set_impl
+    params = gm.default_params(name, level)
+    gm.set_fused(fused, head)
+    torch.manual_seed(3)
+    mod = set_impl(om.fill_params_deterministic(getattr(gm, name)(params)).cuda().train(), impl)
+    crit = losses.P2PKLD_Loss(level, *factors, 1.0) if name == 'ico2ico_vae' else losses.P2P_Loss(level, *factors)
+    reparam.manual_seed(11)
+    loss = crit(mod(x), tgt)
+    loss.backward()
+    torch.cuda.synchronize()
+    return loss.item(), _grads(mod), {k: b.detach().cpu().clone() for k, b in mod.named_buffers()}
+
+
 @pytest.mark.parametrize('name', ['ico2ico', 'ico2ico_vae'])
 def test_fused_chain_matches_modulewise(name):
     """geniconet_b200/fused.py (one Function per encoder/decoder body: sibling convs as one GEMM, fused BatchNorm + ReLU + add +
-    bf16 cast) against the module-by-module path over the SAME tcgen05 kernels and against the fp32 CUDA-core path: identical
-    weights, inputs and reparam noise.  Both bf16 paths are judged by their distance to the fp32 gradients: the VAE loss
-    (normals + Laplacian + KLD) amplifies operand rounding to cosine ~0.90-0.93 on the deepest layers for EITHER bf16 path
-    (tools/diag_fused.py), so the fused path must stay within 0.05 of the module-wise one, parameter by parameter."""
-    from geniconet_b200 import models as gm, losses, data, reparam
-    from geniconet_b200.ico_conv import set_impl
+    bf16 cast, the 1x1 head through gin_head_*) against the module-by-module path over the SAME tcgen05 kernels and against the
+    fp32 CUDA-core path: identical weights, inputs and reparam noise.  Both bf16 paths are judged by their distance to the fp32
+    gradients, parameter by parameter, under the position (+ KLD) loss.  The VAE's normal / Laplacian terms are left out of the
+    gradient comparison: on the near-degenerate mesh a random-init network emits, their gradient is chaotic (ANY rounding
+    difference, even a TF32 head, re-draws ~40 % of it -- profiles/r01_vae_grad_conditioning.txt), so there only the loss and
+    the finiteness of the gradients are compared; the loss kernels themselves are checked against the oracle in
+    tests/test_gpu_layers.py."""
+    from geniconet_b200 import models as gm, data
     level, B = 5, 3
     params = gm.default_params(name, level)
     x, tgt = data.synthetic_batch(level, 0, B)
     x, tgt = x.cuda(), tgt.cuda()
-    f = (params['ico']['factor_pos'], params['ico']['factor_nor'], params['ico']['factor_lap'])
-    res = {}
+    f_ref = (params['ico']['factor_pos'], params['ico']['factor_nor'], params['ico']['factor_lap'])
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False                  # the module-wise paths keep the stock 1x1 head: make it real fp32
     try:
-        for tag, fused, impl in (('fp32', False, 'simt'), ('tc', False, 'auto'), ('fused', True, 'auto')):
-            gm.set_fused(fused)
-            torch.manual_seed(3)
-            mod = set_impl(om.fill_params_deterministic(getattr(gm, name)(params)).cuda().train(), impl)
-            crit = losses.P2PKLD_Loss(level, *f, 1.0) if name == 'ico2ico_vae' else losses.P2P_Loss(level, *f)
-            reparam.manual_seed(11)
-            loss = crit(mod(x), tgt)
-            loss.backward()
-            torch.cuda.synchronize()
-            res[tag] = (loss.item(), _grads(mod), {k: b.detach().cpu().clone() for k, b in mod.named_buffers()})
+        res = {tag: _seeded_step(name, level, x, tgt, (1.0, 0.0, 0.0), fused, impl)
+               for tag, fused, impl in (('fp32', False, 'simt'), ('tc', False, 'auto'), ('fused', True, 'auto'))}
+        full = {tag: _seeded_step(name, level, x, tgt, f_ref, fused, impl) for tag, fused, impl in (('tc', False, 'auto'), ('fused', True, 'auto'))}
     finally:
-        gm.set_fused(True)
+        gm.set_fused(True, True)
+        torch.backends.cudnn.allow_tf32 = tf32
     (l0, g0, b0), (l1, g1, b1), (l2, g2, b2) = res['fp32'], res['tc'], res['fused']
     assert abs(l2 - l0) <= 2e-3 * abs(l0) and abs(l2 - l1) <= 2e-3 * abs(l1), (l0, l1, l2)
+    assert abs(full['fused'][0] - full['tc'][0]) <= 2e-3 * abs(full['tc'][0])
+    assert all(torch.isfinite(g).all() for g in full['fused'][1].values())
 
     def cos(a, b):
         a, b = a.flatten().double(), b.flatten().double()
@@ -209,11 +224,9 @@ def test_fused_chain_matches_modulewise(name):
         c_tc, c_fused = cos(g1[k], ref), cos(g2[k], ref)
         cs_tc.append(c_tc)
         cs_fused.append(c_fused)
-        # per parameter the two bf16 paths are different noise realisations of the same gradient (measured spread +-0.05 at
-        # this batch of 3); on average the fused path must be as close to the fp32 gradient as the module-wise one
-        assert c_fused >= c_tc - 0.1, (k, c_tc, c_fused)
-        assert 0.85 <= (g2[k].norm() / ref.norm()).item() <= 1.15, k
-    assert sum(cs_fused) / len(cs_fused) >= sum(cs_tc) / len(cs_tc) - 0.04, (sum(cs_fused) / len(cs_fused), sum(cs_tc) / len(cs_tc))
+        assert c_fused >= 0.985 and c_fused >= c_tc - 0.01, (k, c_tc, c_fused)       # measured: >= 0.9938, |fused - tc| <= 6e-4
+        assert 0.93 <= (g2[k].norm() / ref.norm()).item() <= 1.07, k
+    assert sum(cs_fused) / len(cs_fused) >= sum(cs_tc) / len(cs_tc) - 0.002, (sum(cs_fused) / len(cs_fused), sum(cs_tc) / len(cs_tc))
     for k in b0:
         if k.endswith('running_mean') or k.endswith('running_var'):
             assert torch.allclose(b2[k], b0[k], rtol=2e-2, atol=2e-3), k
@@ -221,6 +234,31 @@ def test_fused_chain_matches_modulewise(name):
             assert int(b2[k]) == int(b0[k]) == 1, k
     # a conv bias in front of a BatchNorm: exactly zero on the fused path
     assert float(g2['encoder.3.conv00.bias'].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('name', ['ico2ico', 'ico2ico_vae'])
+def test_fused_step_is_reproducible(name):
+    """The same seeded training step twice, the allocator's free blocks overwritten in between: loss and every gradient must be
+    bit-identical.  No kernel on the path combines partial results with atomics (conv-epilogue BatchNorm sums, seam rows,
+    split-K and per-CTA reductions all add in a fixed order); a last-bit difference would not stay small -- every bf16 operand
+    cast downstream re-rounds, so it grows to the bf16 noise floor within three blocks (profiles/r01_vae_grad_conditioning.txt)."""
+    from geniconet_b200 import models as gm, data
+    level, B = 5, 5                                          # odd batch: a ragged last sample group
+    params = gm.default_params(name, level)
+    x, tgt = data.synthetic_batch(level, 0, B)
+    x, tgt = x.cuda(), tgt.cuda()
+    f = (params['ico']['factor_pos'], params['ico']['factor_nor'], params['ico']['factor_lap'])
+    try:
+        _seeded_step(name, level, x, tgt, f, True, 'auto')                               # warm-up: plans, caches
+        l0, g0, _ = _seeded_step(name, level, x, tgt, f, True, 'auto')
+        junk = torch.full((1 << 30,), 0xFF, dtype=torch.uint8, device='cuda')
+        del junk
+        l1, g1, _ = _seeded_step(name, level, x, tgt, f, True, 'auto')
+    finally:
+        gm.set_fused(True, True)
+    assert l0 == l1
+    differing = [k for k in g0 if not torch.equal(g0[k], g1[k])]
+    assert not differing, differing
 
 
 @pytest.mark.parametrize('name,level,B', [('ico2ico', 5, 36), ('ico2ico_vae', 5, 36), ('ico2ico', 6, 16)])

@@ -12,9 +12,14 @@ params = gm.default_params(name, level)
 x, tgt = data.synthetic_batch(level, 0, B)
 x, tgt = x.cuda(), tgt.cuda()
 f = (params['ico']['factor_pos'], params['ico']['factor_nor'], params['ico']['factor_lap'])
+if os.environ.get('DIAG_FACTORS'):                          # e.g. 1,0,0: position term only (well conditioned at random init)
+    f = tuple(float(v) for v in os.environ['DIAG_FACTORS'].split(','))
+if os.environ.get('DIAG_TF32', '1') == '0':                 # make the stock 1x1 head (cuDNN) compute in fp32 as well
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
 res = {}
-for tag, fused, impl in (('fp32', False, 'simt'), ('tc', False, 'auto'), ('fused', True, 'auto')):
-    gm.set_fused(fused)
+for tag, fused, impl, head in (('fp32', False, 'simt', True), ('tc', False, 'auto', True), ('fused', True, 'auto', True), ('fused_stockhead', True, 'auto', False)):
+    gm.set_fused(fused, head)
     torch.manual_seed(3)
     mod = set_impl(om.fill_params_deterministic(getattr(gm, name)(params)).cuda().train(), impl)
     crit = losses.P2PKLD_Loss(level, *f, 1.0) if name == 'ico2ico_vae' else losses.P2P_Loss(level, *f)
@@ -30,6 +35,6 @@ for k in res['fp32'][1]:
     r = res['fp32'][1][k]
     if r.norm() < 1e-6:
         continue
-    print('%-28s |g| %.3e   tc %.5f  fused %.5f  fused-vs-tc %.5f   norm ratio fused/fp32 %.4f' % (
-        k, r.norm().item(), cos(res['tc'][1][k], r), cos(res['fused'][1][k], r), cos(res['fused'][1][k], res['tc'][1][k]),
-        (res['fused'][1][k].norm() / r.norm()).item()))
+    print('%-28s |g| %.3e   tc %.5f  fused %.5f  fused(stock head) %.5f  fused-vs-tc %.5f   norm ratio fused/fp32 %.4f' % (
+        k, r.norm().item(), cos(res['tc'][1][k], r), cos(res['fused'][1][k], r), cos(res['fused_stockhead'][1][k], r),
+        cos(res['fused'][1][k], res['tc'][1][k]), (res['fused'][1][k].norm() / r.norm()).item()))
