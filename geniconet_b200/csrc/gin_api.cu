@@ -185,7 +185,7 @@ int gin_hexconv_pack_weights_bf16(const float* w0, int Cout0, const float* w1, i
     return fail(GIN_ERR_ARG, "gin_hexconv_pack_weights_bf16: bad argument (channel counts must be multiples of 64)");
   char* pk = reinterpret_cast<char*>(packed);
   const long long n = 7LL * Cin * Cout;
-  gin::pack_weights_bf16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+  gin::launch_pdl(gin::pack_weights_bf16_kernel, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, 
       w0, Cout0, w1, reinterpret_cast<unsigned short*>(pk + packed_off_bf(Cin, Cout)), reinterpret_cast<unsigned short*>(pk + packed_off_bd(Cin, Cout)),
       Cin, Cout);
   return check_launch("pack_weights_bf16");
@@ -507,7 +507,7 @@ int gin_head_fwd(const float* x, const float* w, const float* bias, float* y, in
   if (!x || !w || !bias || !y) return fail(GIN_ERR_ARG, "gin_head_fwd: null pointer");
   if (((uintptr_t)x | (uintptr_t)w) & 15) return fail(GIN_ERR_ARG, "gin_head_fwd: x and w must be 16-byte aligned");
   const long long rows = (long long)B * P;
-  gin::head::fwd_kernel<<<gin::head::grid_for_rows(rows), gin::head::kThreads, 0, (cudaStream_t)stream>>>(x, w, bias, y, rows, P);
+  gin::launch_pdl(gin::head::fwd_kernel, dim3(gin::head::grid_for_rows(rows)), dim3(gin::head::kThreads), 0, (cudaStream_t)stream, x, w, bias, y, rows, P);
   return check_launch("head_fwd");
 }
 
@@ -520,10 +520,10 @@ int gin_head_bwd(const float* x, const float* w, const float* y, const float* dy
   const long long rows = (long long)B * P;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = gin::head::grid_for_rows(rows);
-  gin::head::bwd_kernel<<<grid, gin::head::kThreads, 0, st>>>(x, w, y, dy, dx, (float*)ws, rows, P);
+  gin::launch_pdl(gin::head::bwd_kernel, dim3(grid), dim3(gin::head::kThreads), 0, st, x, w, y, dy, dx, (float*)ws, rows, P);
   rc = check_launch("head_bwd");
   if (rc != GIN_OK) return rc;
-  gin::head::bwd_final_kernel<<<1, 256, 0, st>>>((const float*)ws, grid, dw, db);
+  gin::launch_pdl(gin::head::bwd_final_kernel, dim3(1), dim3(256), 0, st, (const float*)ws, grid, dw, db);
   return check_launch("head_bwd_final");
 }
 
@@ -558,10 +558,10 @@ int gin_bn_stats(const float* y, int64_t ld, int64_t rows, int C, const float* g
   cudaStream_t st = (cudaStream_t)stream;
   if (!y || !stat || !ws || rows <= 0 || !bn_shape_ok(C) || ld < C || (ld & 3)) return fail(GIN_ERR_ARG, "gin_bn_stats: bad argument (C/8 must divide 256)");
   const int ctas = gin::bn::grid_for_rows(rows * (C >> 3));
-  gin::bn::stats_kernel<<<ctas, 256, 0, st>>>(gin::bn::Src{y, (long long)ld}, rows, C, reinterpret_cast<float*>(ws));
+  gin::launch_pdl(gin::bn::stats_kernel, dim3(ctas), dim3(256), 0, st, gin::bn::Src{y, (long long)ld}, rows, C, reinterpret_cast<float*>(ws));
   int rc = check_launch("bn_stats");
   if (rc) return rc;
-  gin::bn::stats_final_kernel<<<C / 8, 256, 0, st>>>(reinterpret_cast<const float*>(ws), ctas, rows, C, gamma, beta, eps, momentum, running_mean,
+  gin::launch_pdl(gin::bn::stats_final_kernel, dim3(C / 8), dim3(256), 0, st, reinterpret_cast<const float*>(ws), ctas, rows, C, gamma, beta, eps, momentum, running_mean,
                                                      running_var, reinterpret_cast<long long*>(num_batches_tracked), stat, 0);
   return check_launch("bn_stats_final");
 }
@@ -572,7 +572,7 @@ int gin_bn_stats_from_parts(const float* parts, int nparts, int64_t ld, int64_t 
                             float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked, float* stat, void* stream) {
   if (!parts || nparts <= 0 || nparts > gin::bn::MAX_CTAS || !stat || rows <= 0 || !bn_shape_ok(C) || ld < C)
     return fail(GIN_ERR_ARG, "gin_bn_stats_from_parts: bad argument");
-  gin::bn::stats_final_kernel<<<C / 8, 256, 0, (cudaStream_t)stream>>>(parts, nparts, rows, C, gamma, beta, eps, momentum, running_mean, running_var,
+  gin::launch_pdl(gin::bn::stats_final_kernel, dim3(C / 8), dim3(256), 0, (cudaStream_t)stream, parts, nparts, rows, C, gamma, beta, eps, momentum, running_mean, running_var,
                                                                        reinterpret_cast<long long*>(num_batches_tracked), stat, ld);
   return check_launch("bn_stats_final");
 }
@@ -585,8 +585,8 @@ int gin_bn_act_fwd(const float* y1, int64_t ld1, const float* stat1, const float
   const int n = 1 << level, P = 10 << (2 * level);
   const int ctas = gin::bn::grid_for_rows(((long long)B * P + 2LL * B) * (C >> 3));
   const gin::bn::Src s1{y1, (long long)ld1}, s2{y2, (long long)ld2};
-  if (y2) gin::bn::act_fwd_kernel<true><<<ctas, 256, 0, st>>>(s1, stat1, s2, stat2, relu, reinterpret_cast<__nv_bfloat16*>(out_b), out_f, n, B, P, C);
-  else gin::bn::act_fwd_kernel<false><<<ctas, 256, 0, st>>>(s1, stat1, s2, stat2, relu, reinterpret_cast<__nv_bfloat16*>(out_b), out_f, n, B, P, C);
+  if (y2) gin::launch_pdl(gin::bn::act_fwd_kernel<true>, dim3(ctas), dim3(256), 0, st, s1, stat1, s2, stat2, relu, reinterpret_cast<__nv_bfloat16*>(out_b), out_f, n, B, P, C);
+  else gin::launch_pdl(gin::bn::act_fwd_kernel<false>, dim3(ctas), dim3(256), 0, st, s1, stat1, s2, stat2, relu, reinterpret_cast<__nv_bfloat16*>(out_b), out_f, n, B, P, C);
   return check_launch("bn_act_fwd");
 }
 
@@ -600,12 +600,12 @@ int gin_bn_act_bwd(const float* dout, int64_t ldg, const void* mask_b, const flo
   const gin::bn::Src sy{y, (long long)ld};
   const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(mask_b);
   const int ctas = gin::bn::grid_for_rows(rows * (C >> 3));
-  gin::bn::bwd_reduce_kernel<<<ctas, 256, 0, st>>>(dout, ldg, mask, sy, stat, rows, C, reinterpret_cast<float*>(ws));
+  gin::launch_pdl(gin::bn::bwd_reduce_kernel, dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sy, stat, rows, C, reinterpret_cast<float*>(ws));
   int rc = check_launch("bn_bwd_reduce");
   if (rc) return rc;
-  gin::bn::bwd_final_kernel<<<C / 8, 256, 0, st>>>(reinterpret_cast<const float*>(ws), ctas, rows, C, bstat);
+  gin::launch_pdl(gin::bn::bwd_final_kernel, dim3(C / 8), dim3(256), 0, st, reinterpret_cast<const float*>(ws), ctas, rows, C, bstat);
   if ((rc = check_launch("bn_bwd_final"))) return rc;
-  gin::bn::bwd_apply_kernel<<<ctas, 256, 0, st>>>(dout, ldg, mask, sy, stat, bstat, reinterpret_cast<__nv_bfloat16*>(dy_b), ldo, dy_f, ldf, n, B, P, C);
+  gin::launch_pdl(gin::bn::bwd_apply_kernel, dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sy, stat, bstat, reinterpret_cast<__nv_bfloat16*>(dy_b), ldo, dy_f, ldf, n, B, P, C);
   return check_launch("bn_bwd_apply");
 }
 
@@ -622,12 +622,12 @@ int gin_bn_act_bwd_pair(const float* dout, int64_t ldg, const void* mask_b, cons
   const gin::bn::Src sA{yA, (long long)ldA}, sB{yB, (long long)ldB};
   const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(mask_b);
   const int ctas = gin::bn::grid_for_rows(rows * (C >> 3));
-  gin::bn::bwd_reduce2_kernel<<<ctas, 256, 0, st>>>(dout, ldg, mask, sA, statA, sB, statB, rows, C, reinterpret_cast<float*>(ws));
+  gin::launch_pdl(gin::bn::bwd_reduce2_kernel, dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sA, statA, sB, statB, rows, C, reinterpret_cast<float*>(ws));
   int rc = check_launch("bn_bwd_reduce2");
   if (rc) return rc;
-  gin::bn::bwd_final2_kernel<<<C / 8, 256, 0, st>>>(reinterpret_cast<const float*>(ws), ctas, rows, C, bstatA, bstatB);
+  gin::launch_pdl(gin::bn::bwd_final2_kernel, dim3(C / 8), dim3(256), 0, st, reinterpret_cast<const float*>(ws), ctas, rows, C, bstatA, bstatB);
   if ((rc = check_launch("bn_bwd_final2"))) return rc;
-  gin::bn::bwd_apply2_kernel<<<ctas, 256, 0, st>>>(dout, ldg, mask, sA, statA, bstatA, sB, statB, bstatB, reinterpret_cast<__nv_bfloat16*>(dyA_b), ldoA,
+  gin::launch_pdl(gin::bn::bwd_apply2_kernel, dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sA, statA, bstatA, sB, statB, bstatB, reinterpret_cast<__nv_bfloat16*>(dyA_b), ldoA,
                                                    reinterpret_cast<__nv_bfloat16*>(dyB_b), ldoB, n, B, P, C);
   return check_launch("bn_bwd_apply2");
 }
@@ -642,8 +642,8 @@ int gin_upsample_bf16(const void* plan_host, const void* plan_dev, const void* i
   if (rc) return rc;
   const int ctas = gin::bn::grid_for_rows(((long long)B * h->Pf + 2LL * B) * (C >> 3));
   const int grid = ctas * 4 > 148 * 8 ? 148 * 8 : ctas * 4;
-  if (in_is_f32) gin::bn::upsample_bf16_kernel<true><<<grid, 256, 0, st>>>(plan_words(plan_dev), in, reinterpret_cast<__nv_bfloat16*>(out_b), 2 << h->level, B, C);
-  else gin::bn::upsample_bf16_kernel<false><<<grid, 256, 0, st>>>(plan_words(plan_dev), in, reinterpret_cast<__nv_bfloat16*>(out_b), 2 << h->level, B, C);
+  if (in_is_f32) gin::launch_pdl(gin::bn::upsample_bf16_kernel<true>, dim3(grid), dim3(256), 0, st, plan_words(plan_dev), in, reinterpret_cast<__nv_bfloat16*>(out_b), 2 << h->level, B, C);
+  else gin::launch_pdl(gin::bn::upsample_bf16_kernel<false>, dim3(grid), dim3(256), 0, st, plan_words(plan_dev), in, reinterpret_cast<__nv_bfloat16*>(out_b), 2 << h->level, B, C);
   return check_launch("upsample_bf16");
 }
 

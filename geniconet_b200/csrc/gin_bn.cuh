@@ -100,6 +100,7 @@ GIN_DEVINL double final_sum(const float* __restrict__ partial, int nblocks, int 
 
 // ------------------------------------------------------------------------------------------------ forward statistics
 __global__ void __launch_bounds__(256) stats_kernel(Src y, long long rows, int C, float* __restrict__ partial) {
+  GIN_PDL_SYNC();
   const int C8 = C >> 3;
   const long long n = rows * C8;
   float s0[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, s1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(256)
 stats_final_kernel(const float* __restrict__ partial, int nblocks, long long rows, int C, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                    long long* __restrict__ num_batches_tracked, float* __restrict__ stat, long long ld) {
+  GIN_PDL_SYNC();
   __shared__ double sums[16];
   const double t = final_sum(partial, nblocks, C, ld);
   if (threadIdx.x < 16) sums[threadIdx.x] = t;
@@ -167,6 +169,7 @@ template <bool TWO>
 __global__ void __launch_bounds__(256)
 act_fwd_kernel(Src y1, const float* __restrict__ stat1, Src y2, const float* __restrict__ stat2, int relu, __nv_bfloat16* __restrict__ out_b,
                float* __restrict__ out_f, int nlat, int B, int P, int C) {
+  GIN_PDL_SYNC();
   const int C8 = C >> 3;
   const long long rows = (long long)B * P, n_main = rows * C8, n_all = n_main + 2LL * B * C8;
   const int c = (int)(threadIdx.x % C8) * 8;            // fixed for this thread: C8 | 256 | grid stride
@@ -215,6 +218,7 @@ GIN_DEVINL void grad_row(const float* __restrict__ dout, long long ldg, const __
 __global__ void __launch_bounds__(256)
 bwd_reduce_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, Src y, const float* __restrict__ stat,
                   long long rows, int C, float* __restrict__ partial) {
+  GIN_PDL_SYNC();
   const int C8 = C >> 3;
   const long long n = rows * C8;
   const int c = (int)(threadIdx.x % C8) * 8;
@@ -233,6 +237,7 @@ bwd_reduce_kernel(const float* __restrict__ dout, long long ldg, const __nv_bflo
 // bstat[0..3][C] = dbeta = sum g, dgamma = sum g*yhat, c1 = mean(g), c2 = mean(g*yhat).  grid = C/8.
 __global__ void __launch_bounds__(256)
 bwd_final_kernel(const float* __restrict__ partial, int nblocks, long long rows, int C, float* __restrict__ bstat) {
+  GIN_PDL_SYNC();
   const double t = final_sum(partial, nblocks, C);
   if (threadIdx.x < 16) {
     const int k = threadIdx.x >> 3, c = blockIdx.x * 8 + (threadIdx.x & 7);
@@ -245,6 +250,7 @@ __global__ void __launch_bounds__(256)
 bwd_apply_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, Src y, const float* __restrict__ stat,
                  const float* __restrict__ bstat, __nv_bfloat16* __restrict__ dy_b, long long ldo, float* __restrict__ dy_f, long long ldf,
                  int nlat, int B, int P, int C) {
+  GIN_PDL_SYNC();
   const int C8 = C >> 3;
   const long long rows = (long long)B * P, n_main = rows * C8, n_all = n_main + (dy_b ? 2LL * B * C8 : 0);
   const int c = (int)(threadIdx.x % C8) * 8;
@@ -320,6 +326,7 @@ GIN_DEVINL void up_pixel(const int32_t* __restrict__ src, const void* __restrict
 template <bool F32>
 __global__ void __launch_bounds__(256)
 upsample_bf16_kernel(const int32_t* __restrict__ plan, const void* __restrict__ xin, __nv_bfloat16* __restrict__ out, int nfine, int B, int C) {
+  GIN_PDL_SYNC();
   const GinUpPlanHdr* h = reinterpret_cast<const GinUpPlanHdr*>(plan);
   const int Pc = h->Pc, Pf = h->Pf, C8 = C >> 3;
   const int32_t* src = plan + h->fwd_off;
@@ -354,6 +361,7 @@ upsample_bf16_kernel(const int32_t* __restrict__ plan, const void* __restrict__ 
 __global__ void __launch_bounds__(256)
 bwd_reduce2_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, Src yA, const float* __restrict__ statA,
                    Src yB, const float* __restrict__ statB, long long rows, int C, float* __restrict__ partial) {
+  GIN_PDL_SYNC();
   __shared__ float part[3][256][9];
   const int C8 = C >> 3;
   const long long n = rows * C8;
@@ -391,6 +399,7 @@ bwd_reduce2_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfl
 // bstatA / bstatB [4][C] from partial[nblocks][4][C]; grid = C/8, block = 256 (8 row groups x 32 (sum, channel) lanes)
 __global__ void __launch_bounds__(256)
 bwd_final2_kernel(const float* __restrict__ partial, int nblocks, long long rows, int C, float* __restrict__ bstatA, float* __restrict__ bstatB) {
+  GIN_PDL_SYNC();
   __shared__ double red[8][33];
   const int j = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int k = j >> 3, c = blockIdx.x * 8 + (j & 7);
@@ -423,6 +432,7 @@ __global__ void __launch_bounds__(256)
 bwd_apply2_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, Src yA, const float* __restrict__ statA,
                   const float* __restrict__ bstatA, Src yB, const float* __restrict__ statB, const float* __restrict__ bstatB,
                   __nv_bfloat16* __restrict__ dyA, long long ldoA, __nv_bfloat16* __restrict__ dyB, long long ldoB, int nlat, int B, int P, int C) {
+  GIN_PDL_SYNC();
   const int C8 = C >> 3;
   const long long rows = (long long)B * P, n_main = rows * C8, n_all = n_main + 2LL * B * C8;
   const int c = (int)(threadIdx.x % C8) * 8;

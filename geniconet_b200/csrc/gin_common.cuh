@@ -2,16 +2,45 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "gin_plan.h"
 
 #define GIN_DEVINL __device__ __forceinline__
+
+// Programmatic dependent launch (GIN_PDL=1): a kernel launched through launch_pdl may start while its predecessor in the stream is
+// still draining; its CTAs set up (barriers, TMEM, constant tables) and then block in GIN_PDL_SYNC() until the predecessor grid has
+// completed and its memory is visible.  EVERY kernel launched through launch_pdl must execute GIN_PDL_SYNC() in all threads before
+// its first access to memory another kernel produces or consumes (completion of a grid then implies completion of everything
+// before it in the stream).  Without the launch attribute the instructions are no-ops.
+#define GIN_PDL_SYNC() asm volatile("griddepcontrol.wait;\n\tgriddepcontrol.launch_dependents;" ::: "memory")
 
 struct GinSrcView {      // a gathered fp32 tensor with arbitrary element strides
   const float* p;
   long long sb, sp, sc;  // element (b, pixel, channel) -> p[b*sb + pixel*sp + channel*sc]
   int P;                 // pixels per sample
 };
+
+namespace gin {
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GIN_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (pdl_enabled()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+}  // namespace gin
 
 __host__ GIN_DEVINL const int32_t* plan_words(const void* plan) { return reinterpret_cast<const int32_t*>(plan); }
 

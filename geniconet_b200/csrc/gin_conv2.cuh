@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  GIN_PDL_SYNC();                                    // everything above touched only shared memory, TMEM and the constant plan
 #ifdef GIN_PROF
   long long pw[6] = {0, 0, 0, 0, 0, 0};
   const long long t_begin = clock64();
@@ -504,11 +505,11 @@ int launch(Params p, cudaStream_t st) {
   const bool stats = p.stats != nullptr && !p.flush_each;
   if (p.stats_parts) *p.stats_parts = stats ? grid / p.n_blocks : 0;
   if (p.resident) {
-    if (stats) patch_conv_kernel<N_TILE, true, true><<<grid, NTHREADS, smem_total, st>>>(p);
-    else patch_conv_kernel<N_TILE, true, false><<<grid, NTHREADS, smem_total, st>>>(p);
+    if (stats) launch_pdl(patch_conv_kernel<N_TILE, true, true>, dim3(grid), dim3(NTHREADS), smem_total, st, p);
+    else launch_pdl(patch_conv_kernel<N_TILE, true, false>, dim3(grid), dim3(NTHREADS), smem_total, st, p);
   } else {
-    if (stats) patch_conv_kernel<N_TILE, false, true><<<grid, NTHREADS, smem_total, st>>>(p);
-    else patch_conv_kernel<N_TILE, false, false><<<grid, NTHREADS, smem_total, st>>>(p);
+    if (stats) launch_pdl(patch_conv_kernel<N_TILE, false, true>, dim3(grid), dim3(NTHREADS), smem_total, st, p);
+    else launch_pdl(patch_conv_kernel<N_TILE, false, false>, dim3(grid), dim3(NTHREADS), smem_total, st, p);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

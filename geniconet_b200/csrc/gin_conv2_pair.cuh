@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_pair_kernel(const Para
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  GIN_PDL_SYNC();
 
   if (warp < PROD_WARPS) {
     // =========================================================== producers: per (pair, segment): tables of both tiles, then per chunk one
@@ -327,8 +328,8 @@ int launch_pair(Params p, cudaStream_t st) {
   if (grid < p.n_blocks) grid = p.n_blocks;
   const bool stats = p.stats != nullptr;
   if (p.stats_parts) *p.stats_parts = stats ? grid / p.n_blocks : 0;
-  if (stats) patch_conv_pair_kernel<N_TILE, true><<<grid, NTHREADS, smem_total, st>>>(p);
-  else patch_conv_pair_kernel<N_TILE, false><<<grid, NTHREADS, smem_total, st>>>(p);
+  if (stats) launch_pdl(patch_conv_pair_kernel<N_TILE, true>, dim3(grid), dim3(NTHREADS), smem_total, st, p);
+  else launch_pdl(patch_conv_pair_kernel<N_TILE, false>, dim3(grid), dim3(NTHREADS), smem_total, st, p);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 

@@ -309,6 +309,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
 // chains need: two sibling convolutions become one GEMM without materialising the concatenation.
 __global__ void pack_weights_bf16_kernel(const float* __restrict__ w0, int Cout0, const float* __restrict__ w1, unsigned short* __restrict__ bf,
                                          unsigned short* __restrict__ bd, int Cin, int Cout) {
+  GIN_PDL_SYNC();
   const long long n = (long long)Cin * Cout * 7;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int t = (int)(i % 7);

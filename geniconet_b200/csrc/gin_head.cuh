@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "gin_common.cuh"
+
 namespace gin {
 namespace head {
 
@@ -23,6 +25,7 @@ __device__ __forceinline__ long long lane_pixel(long long blk, int lane) { retur
 
 __global__ void __launch_bounds__(kThreads) fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                                        float* __restrict__ y, long long rows, long long P) {
+  GIN_PDL_SYNC();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l16 = lane & 15, h = lane >> 4;
   float4 wr[COUT];
 #pragma unroll
@@ -55,6 +58,7 @@ __global__ void __launch_bounds__(kThreads) fwd_kernel(const float* __restrict__
 __global__ void __launch_bounds__(kThreads) bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ y,
                                                        const float* __restrict__ dy, float* __restrict__ dx, float* __restrict__ partial,
                                                        long long rows, long long P) {
+  GIN_PDL_SYNC();
   __shared__ float red[kWarps][PART];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l16 = lane & 15, h = lane >> 4;
   float4 wr[COUT];
@@ -118,6 +122,7 @@ __global__ void __launch_bounds__(kThreads) bwd_kernel(const float* __restrict__
 
 // one thread per output; two accumulators, fixed order -> deterministic
 __global__ void bwd_final_kernel(const float* __restrict__ partial, int nparts, float* __restrict__ dw, float* __restrict__ db) {
+  GIN_PDL_SYNC();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= COUT * CIN + COUT) return;
   float s0 = 0.f, s1 = 0.f;

@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_patch_kernel(const Params p
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  GIN_PDL_SYNC();
 
   if (warp < PROD_WARPS) {
     // =========================================================== producers: patch rows + dY rows, then the epilogue
@@ -258,6 +259,7 @@ struct TapMap { int8_t acc[8], half[8]; };
 // the 20-40 MB of partials it streams from L2, not by latency.)
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int Cin, int Cout, int n_blk, int slices, int n_cblk, TapMap tm) {
+  GIN_PDL_SYNC();
   const long long n = 7LL * Cin * Cout;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int co = (int)(i % Cout);
@@ -298,14 +300,14 @@ int launch(Params p, float* dW, cudaStream_t st) {
   if (slices < 1) slices = 1;
   p.slices = slices;
   p.tiles_per_cta = (p.total_tiles + slices - 1) / slices;
-  kern<<<units * slices, NTHREADS, p.stages * stage_bytes + fixed, st>>>(p);
+  launch_pdl(kern, dim3(units * slices), dim3(NTHREADS), p.stages * stage_bytes + fixed, st, p);
   if (cudaGetLastError() != cudaSuccess) return -3;
   const long long n = 7LL * p.Cin * p.Cout;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   TapMap tm;
   for (int t = 0; t < 8; ++t) { tm.acc[t] = p.tap_acc[t]; tm.half[t] = p.tap_half[t]; }
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(p.partial, dW, p.Cin, p.Cout, N_BLK, slices, p.n_cblk, tm);
+  launch_pdl(wgrad_reduce_kernel, dim3(blocks), dim3(256), 0, st, (const float*)p.partial, dW, p.Cin, p.Cout, N_BLK, slices, p.n_cblk, tm);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
