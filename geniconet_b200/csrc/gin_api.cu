@@ -523,7 +523,7 @@ int gin_head_bwd(const float* x, const float* w, const float* y, const float* dy
   gin::launch_pdl(gin::head::bwd_kernel, dim3(grid), dim3(gin::head::kThreads), 0, st, x, w, y, dy, dx, (float*)ws, rows, P);
   rc = check_launch("head_bwd");
   if (rc != GIN_OK) return rc;
-  gin::launch_pdl(gin::head::bwd_final_kernel, dim3(1), dim3(256), 0, st, (const float*)ws, grid, dw, db);
+  gin::launch_pdl(gin::head::bwd_final_kernel, dim3((gin::head::COUT * gin::head::CIN + gin::head::COUT + 7) / 8), dim3(256), 0, st, (const float*)ws, grid, dw, db);
   return check_launch("head_bwd_final");
 }
 

@@ -120,17 +120,17 @@ __global__ void __launch_bounds__(kThreads) bwd_kernel(const float* __restrict__
   }
 }
 
-// one thread per output; two accumulators, fixed order -> deterministic
-__global__ void bwd_final_kernel(const float* __restrict__ partial, int nparts, float* __restrict__ dw, float* __restrict__ db) {
+// one WARP per output: lane l adds partials l, l+32, ... in order, then a fixed shuffle tree -> deterministic, and 32x the
+// memory parallelism of a serial loop (the serial version took 25 us for 592 partials)
+__global__ void __launch_bounds__(256) bwd_final_kernel(const float* __restrict__ partial, int nparts, float* __restrict__ dw, float* __restrict__ db) {
   GIN_PDL_SYNC();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= COUT * CIN + COUT) return;
-  float s0 = 0.f, s1 = 0.f;
-  int k = 0;
-#pragma unroll 8
-  for (; k + 1 < nparts; k += 2) { s0 += partial[(size_t)k * PART + i]; s1 += partial[(size_t)(k + 1) * PART + i]; }
-  if (k < nparts) s0 += partial[(size_t)k * PART + i];
-  if (i < COUT * CIN) dw[i] = s0 + s1; else db[i - COUT * CIN] = s0 + s1;
+  float s = 0.f;
+  for (int k = lane; k < nparts; k += 32) s += partial[(size_t)k * PART + i];
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  if (lane == 0) { if (i < COUT * CIN) dw[i] = s; else db[i - COUT * CIN] = s; }
 }
 
 inline int grid_for_rows(long long rows) {

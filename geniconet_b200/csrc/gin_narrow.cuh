@@ -242,16 +242,16 @@ wgrad_kernel(const int32_t* __restrict__ plan, GinSide side, GinSrcView X, const
   for (int i = threadIdx.x; i < NACC * COUT; i += THREADS) partial[(size_t)blockIdx.x * NACC * COUT + i] = red[i];
 }
 
-// dWp[i] / db[i]: sum over the CTAs' rows, one thread per output, two accumulators, fixed order
-__global__ void wgrad_final_kernel(const float* __restrict__ partial, int nparts, int n_w, int n_b, float* __restrict__ dWp, float* __restrict__ db) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x, n = n_w + n_b;
+// dWp[i] / db[i]: sum over the CTAs' rows.  One WARP per output: lane l adds rows l, l+32, ... in order, then a fixed shuffle tree.
+__global__ void __launch_bounds__(256) wgrad_final_kernel(const float* __restrict__ partial, int nparts, int n_w, int n_b, float* __restrict__ dWp,
+                                                          float* __restrict__ db) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, n = n_w + n_b;
   if (i >= n) return;
-  float s0 = 0.f, s1 = 0.f;
-  int k = 0;
-#pragma unroll 8
-  for (; k + 1 < nparts; k += 2) { s0 += partial[(size_t)k * n + i]; s1 += partial[(size_t)(k + 1) * n + i]; }
-  if (k < nparts) s0 += partial[(size_t)k * n + i];
-  if (i < n_w) dWp[i] = s0 + s1; else if (db) db[i - n_w] = s0 + s1;
+  float s = 0.f;
+  for (int k = lane; k < nparts; k += 32) s += partial[(size_t)k * n + i];
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  if (lane == 0) { if (i < n_w) dWp[i] = s; else if (db) db[i - n_w] = s; }
 }
 
 constexpr int WGRAD_MAX_CTAS = 148 * 3;
@@ -306,7 +306,7 @@ inline int launch_narrow_wgrad(const int32_t* plan_dev, const GinSide& side, int
   }
   if (cudaGetLastError() != cudaSuccess) return -3;
   const int n_w = 7 * Cin * Cout;
-  narrow::wgrad_final_kernel<<<(n_w + Cout + 255) / 256, 256, 0, st>>>(partial, grid, n_w, Cout, dWp, db);
+  narrow::wgrad_final_kernel<<<(n_w + Cout + 7) / 8, 256, 0, st>>>(partial, grid, n_w, Cout, dWp, db);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
