@@ -384,8 +384,8 @@ def run_ours(args):
         if not args.no_kernel_table:
             from geniconet_b200 import models as _gm
             table = kernel_table(model, B, args.level, peaks, fused=_gm._FUSED)
-            # The dominant kernel FUNCTION of the step is cv2::patch_conv_kernel (profiles/r01_launch_list_fused_step.txt: 23 % of
-            # the device time, ahead of wg2::wgrad_patch_kernel with 12 %): it runs every hex-conv forward and every in-chart
+            # The dominant kernel FUNCTION of the step is cv2::patch_conv_kernel (profiles/r01_launch_list_final_step.txt: 30 % of
+            # the device time with its pair variant, ahead of wg2::wgrad_patch_kernel with 14 %): it runs every hex-conv forward and every in-chart
             # dgrad.  Its launches differ in shape, so the roofline is the launch-weighted aggregate over the forward launches of
             # one step: achieved = sum of algorithmic work / sum of durations (equivalently per-launch averages of both).
             ridge = tf_burst * 1e12 / (hbm * 1e9)
