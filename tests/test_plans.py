@@ -41,6 +41,7 @@ def test_hexconv_plan_reproduces_oracle(case):
 PATCH_CASES = [  # level, stride, corner_mode, B, Cin, Cout
     (2, 1, 'average', 5, 3, 4), (3, 1, 'average', 2, 3, 2), (3, 1, 'zeros', 1, 2, 3), (4, 1, 'average', 1, 2, 2),
     (3, 2, 'average', 5, 3, 2), (4, 2, 'average', 2, 2, 3), (4, 2, 'zeros', 1, 2, 2), (5, 2, 'average', 1, 1, 2),
+    (5, 1, 'average', 3, 1, 2), (6, 2, 'average', 1, 1, 1),     # the bench levels: I5 stride 1 with a ragged sample group, I6 -> I5
 ]
 
 
