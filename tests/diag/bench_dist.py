@@ -1,12 +1,13 @@
 """Times gin_point_mesh_distance at the reference's evaluation size (level 5: 10242 points x 20480 faces per mesh) with CUDA
 events and prints one JSON line: meshes/s, point-triangle tests/s and the oracle's (numpy float64, one core) rate beside it."""
 import json
+import os
 import sys
 import time
 
 import torch
 
-sys.path.insert(0, __file__.rsplit('/', 2)[0])
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from geniconet_b200 import data as gd, ico_utils as iu          # noqa: E402
 from geniconet_b200.ico_geometry import get_ico_faces            # noqa: E402
 from oracle.kaolin_ref import point_to_mesh_distance as p2m_ref  # noqa: E402

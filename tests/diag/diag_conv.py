@@ -1,5 +1,5 @@
 import sys, os, torch, numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, 'tests')]
 from oracle import icocnn_ref
 from geniconet_b200.ico_conv import IcoConvS2S

@@ -1,6 +1,6 @@
 """Per-parameter gradient cosines of the tcgen05 module-wise path and of the fused chain against the fp32 CUDA-core path."""
 import sys, os, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, 'tests')]
 import oracle_models as om
 from geniconet_b200 import models as gm, losses, data, reparam

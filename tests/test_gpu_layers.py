@@ -358,14 +358,14 @@ def test_fused_bn_act_matches_torch(C, level, B, two):
 def test_alternative_kernel_paths_match_oracle(env):
     """The A/B kernel selections (read once per process from the environment): signature-sorted gather seam pass (the default is the regular-form pass through the patch kernel),
     first-generation patch kernels, first-generation gather kernels -- each in a fresh process, conv fwd / dgrad / wgrad of a
-    stride-1 and a stride-2 layer against the oracle fed bf16-rounded operands (tools/diag_conv.py)."""
+    stride-1 and a stride-2 layer against the oracle fed bf16-rounded operands (tests/diag/diag_conv.py)."""
     import os
     import re
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for spec in (['64', '128', '1', '3', '3'], ['64', '64', '2', '3', '2']):
-        out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'diag_conv.py')] + spec, env=dict(os.environ, **env),
+        out = subprocess.run([sys.executable, os.path.join(root, 'tests', 'diag', 'diag_conv.py')] + spec, env=dict(os.environ, **env),
                              capture_output=True, text=True, timeout=300)
         assert out.returncode == 0, out.stderr[-2000:]
         rels = dict(re.findall(r'^(fwd|dgrad|wgrad) max err \S+ rel (\S+)', out.stdout, flags=re.M))

@@ -25,7 +25,7 @@ def _compare_grads(gc, gr, cos_min, what):
     return worst
 
 
-# Measured on B200 (tools/diag_parity.py, profiles/r01_parity_by_layer.txt): the fp32 CUDA-core path tracks the fp32
+# Measured on B200 (tests/diag/diag_parity.py, profiles/r01_parity_by_layer.txt): the fp32 CUDA-core path tracks the fp32
 # oracle to 4e-6 on activations and cosine 1.000000 on every gradient; the tcgen05 path rounds every conv operand to
 # bf16, which accumulates to 2e-2 on the output and, through 25 layers of backward at batch 2, to cosine 0.984 on the
 # first layer's weight gradient (0.996 at batch 8).  Tolerances below are those measurements with ~2x head-room.
