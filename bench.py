@@ -84,8 +84,10 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_step_time(model_name, level, batch, steps, warmup):
-    """The reference's CPU path: models.<name> graph over the oracle icocnn port + losses (fp32, all host threads)."""
+def cpu_reference_step_time(model_name, level, batch, steps, warmup, anomaly=False):
+    """The reference's CPU path: models.<name> graph over the oracle icocnn port + losses (fp32, all host threads).
+    anomaly=True wraps the loop in torch.autograd.detect_anomaly() as the reference's train() does (run.py:237)."""
+    import contextlib
     import torch
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     import oracle_models as om
@@ -97,20 +99,24 @@ def cpu_reference_step_time(model_name, level, batch, steps, warmup):
     x, tgt = data.synthetic_batch(level, 0, batch)
     f = (params['ico']['factor_pos'], params['ico']['factor_nor'], params['ico']['factor_lap'])
     times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        opt.zero_grad()
-        out = model(x)
-        if model_name == 'ico2ico_vae':
-            rec, mu, lv = out
-            loss = om.ref_p2p_loss(level, rec, tgt, *f)[0] + om.ref_kld(mu, lv)
-        else:
-            loss = om.ref_p2p_loss(level, out, tgt, *f)[0]
-        loss.backward()
-        opt.step()
-        float(loss)
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        with (torch.autograd.detect_anomaly() if anomaly else contextlib.nullcontext()):
+            for i in range(warmup + steps):
+                t0 = time.perf_counter()
+                opt.zero_grad()
+                out = model(x)
+                if model_name == 'ico2ico_vae':
+                    rec, mu, lv = out
+                    loss = om.ref_p2p_loss(level, rec, tgt, *f)[0] + om.ref_kld(mu, lv)
+                else:
+                    loss = om.ref_p2p_loss(level, out, tgt, *f)[0]
+                loss.backward()
+                opt.step()
+                float(loss)
+                if i >= warmup:
+                    times.append(time.perf_counter() - t0)
     return statistics.median(times), torch.get_num_threads()
 
 
@@ -123,6 +129,7 @@ def run_reference(args):
     steps = max(1, min(args.steps, 5))
     warmup = max(1, min(args.warmup, 2))
     t, threads = cpu_reference_step_time(args.model, args.level, batch, steps, warmup)
+    t_anom, _ = cpu_reference_step_time(args.model, args.level, batch, min(steps, 3), 1, anomaly=True)   # as run.py:237 trains
     val = batch / t
     B = args.batch or (36 if args.level == 5 else 16)
     line = {'impl': 'reference', 'metric': 'train_meshes_per_sec', 'value': val, 'unit': 'meshes/s', 'n_gpus': args.gpus,
@@ -131,7 +138,8 @@ def run_reference(args):
             'config': {'workload': '%s I%d train step (fwd+loss+bwd+Adam), batch %d/GPU' % (args.model, args.level, B)},
             'cpu_baseline': {'value': val, 'unit': 'meshes/s', 'cores': threads, 'kind': 'port',
                              'sample': 'batch %d per step, median of %d steps after %d warm-up; oracle port of icocnn under the '
-                                       'reference graph, PyTorch CPU (oneDNN), fp32' % (batch, steps, warmup)},
+                                       'reference graph, PyTorch CPU (oneDNN), fp32' % (batch, steps, warmup),
+                             'with_detect_anomaly': batch / t_anom},
             'e2e': {'value': val, 'unit': 'meshes/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
 
