@@ -12,11 +12,10 @@ from geniconet_b200 import _lib
 LEVELS = [0, 1, 2, 3, 4, 5]
 
 
-@pytest.mark.parametrize('s', LEVELS + [6])
+@pytest.mark.parametrize('s', LEVELS + [6, 7])
 def test_index_map_bit_exact_product_vs_oracle(s):
     got = _lib.index_map(s)
-    if s <= 5:
-        assert np.array_equal(got, geo.pad_index_map(s))
+    assert np.array_equal(got, geo.pad_index_map(s))          # every level the layer sweep uses (I3-I7) and below
     n, P = 2 ** s, 10 * 4 ** s
     assert got.shape == (5, n + 2, 2 * n + 2) and got.dtype == np.int32
     # interior cells are the identity
