@@ -42,7 +42,8 @@ def params_for(name):
     return p
 
 
-def main():
+def build():
+    """The fixture as a dict (needs /root/reference)."""
     torch.set_num_threads(8)
     models = import_reference('models')
     saved = install_oracle_modules()
@@ -98,6 +99,11 @@ def main():
         xi = torch.randn(2, c, 5 * n, 2 * n, generator=g)
         layers['up_%d_l%d_%s' % (c, level, cm)] = {'output_sample': sample(up(xi)), 'input_seed': 505}
     out['layers'] = layers
+    return out
+
+
+def main():
+    out = build()
     with open(os.path.join(HERE, 'reference_over_oracle.json'), 'w') as f:
         json.dump(out, f, indent=1)
     print('wrote', os.path.join(HERE, 'reference_over_oracle.json'))
