@@ -25,11 +25,23 @@ def _topology(s):
     return _cache[s]
 
 
-def vertex_normals(v, f, eps=1e-10):
+def vertex_normals(v, f, eps=1e-10, reference_semantics=False):
+    """Area-weighted vertex normals (the generate.py:20-43 recipe, eps clip).
+
+    reference_semantics=True reproduces what generate.py:36-38 actually computes: `v_normals[faces[:, c], :] += f_normals` is a
+    buffered fancy-index update, so a vertex that is corner `c` of several faces receives only the LAST of them -- each vertex
+    normal is the sum of at most three face normals (one per corner slot), not of all its faces.  The published dataset's normal
+    targets were made that way (generate.py:194); on a smooth level-3 mesh the two differ by 2.4 degrees on average.  The default
+    is the true accumulation (what the loss's compute_vertex_normals restatement and the CUDA kernel compute)."""
     fn = np.cross(v[f[:, 1]] - v[f[:, 0]], v[f[:, 2]] - v[f[:, 0]])
     vn = np.zeros_like(v)
     for c in range(3):
-        np.add.at(vn, f[:, c], fn)
+        if reference_semantics:
+            last = np.zeros_like(v)
+            last[f[:, c]] = fn                       # plain assignment: the last face per vertex wins, as in the reference
+            vn += last
+        else:
+            np.add.at(vn, f[:, c], fn)
     return vn / np.clip(np.sqrt((vn ** 2).sum(1)), eps, None)[:, None]
 
 

@@ -43,7 +43,7 @@ def reference_modules(*names):
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from oracle.install import install_oracle_modules
     touched = ['natsort', 'kaolin', 'matplotlib', 'matplotlib.pyplot', 'torch_utils', 'python_utils', 'torchsummary',
-               'ico_utils', 'data', 'losses', 'models', 'run']
+               'ico_utils', 'data', 'losses', 'models', 'run', 'generate']
     before = {k: sys.modules.get(k) for k in touched}
     saved_oracle = install_oracle_modules()
     had_inf = hasattr(np, 'Inf')

@@ -139,3 +139,19 @@ def test_checkpoints_interoperate_with_reference_run_py(tmp_path):
         for fn in (rr.loadMultiModel, ck.loadMultiModel):
             with pytest.raises(ValueError):
                 fn(p_our, ma, [77], ['ico2ico'])
+
+
+def test_target_normals_against_reference_generate_py():
+    """generate.py:20-43 mesh_vertexnormals made the dataset's normal targets.  Its fancy-index `+=` keeps one face per corner slot
+    (numpy does not accumulate repeated indices), which data.vertex_normals(reference_semantics=True) reproduces exactly; the
+    default (true area-weighted accumulation, what the loss kernels compute for the OUTPUT mesh) differs measurably."""
+    verts = gd.synthetic_mesh(3, 5)[1][:3].T.numpy().astype(np.float64)
+    faces = gd._topology(3)[1]
+    with ri.reference_modules('generate') as rg:
+        n_ref = rg.mesh_vertexnormals(verts, faces)
+        c_ref, s_ref = rg.get_normalize_unitsphere(verts)
+    assert np.array_equal(gd.vertex_normals(verts, faces, reference_semantics=True), n_ref)
+    n_true = gd.vertex_normals(verts, faces)
+    angle = np.degrees(np.arccos(np.clip((n_ref * n_true).sum(1), -1.0, 1.0)))
+    assert 0.5 < angle.mean() < 10.0 and np.allclose(np.linalg.norm(n_true, axis=1), 1.0)
+    assert np.allclose(c_ref, verts.mean(0)) and np.isclose(s_ref, np.linalg.norm(verts - verts.mean(0), axis=1).max())
