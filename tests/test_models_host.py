@@ -170,3 +170,21 @@ def test_golden_fixture_regenerates_from_the_reference():
         else:
             assert a == b, (path, a, b)
     compare(GOLD, fresh, '')
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='the reference checkout exists only in the build container')
+@pytest.mark.parametrize('name', ['ico2ico', 'ico2enc', 'enc2ico', 'ico2ico_vae', 'ico2enc_vae', 'enc2ico_vae'])
+def test_every_model_class_has_the_reference_state_dict(name):
+    """All six model classes of the reference's models.py (imported unchanged over the oracle layers), including the encoder-only
+    and decoder-only splits the app uses (models.py:234-252,302-340): same state-dict keys in the same order, same shapes."""
+    from oracle.install import import_reference
+    ref_models = import_reference('models')
+    base = 'ico2ico_vae' if name.endswith('_vae') else 'ico2ico'
+    params = gm.default_params(base)
+    params['model_name'] = name
+    params[name] = dict(params[base])
+    ref = getattr(ref_models, name)(params)
+    ours = getattr(gm, name)(params)
+    want = [(k, tuple(v.shape)) for k, v in ref.state_dict().items()]
+    got = [(k, tuple(v.shape)) for k, v in ours.state_dict().items()]
+    assert got == want
