@@ -36,7 +36,7 @@ def parse():
     ap.add_argument('--no-graph', action='store_true', help='issue every launch from Python instead of replaying one CUDA graph per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-table', action='store_true')
-    ap.add_argument('--cpu-batch', type=int, default=4)
+    ap.add_argument('--cpu-batch', type=int, default=None, help='batch of the CPU arm / cpu_baseline (default: the per-GPU batch)')
     return ap.parse_args()
 
 
@@ -84,34 +84,38 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------- CPU arm
+def workload_config(model, level, B):
+    """The `config` object both arms print (the reference arm measures the same workload on the host cores)."""
+    act_gb = 12.0 * B / 36 * (4 ** (level - 5))
+    return {'workload': '%s I%d train step (fwd+loss+bwd+allreduce+Adam), batch %d/GPU' % (model, level, B),
+            'l2': 'no flush: one step streams ~%.0f GB of activations, far beyond the 126 MB L2' % act_gb}
+
+
 def cpu_reference_step_time(model_name, level, batch, steps, warmup, anomaly=False):
-    """The reference's CPU path: models.<name> graph over the oracle icocnn port + losses (fp32, all host threads).
-    anomaly=True wraps the loop in torch.autograd.detect_anomaly() as the reference's train() does (run.py:237)."""
+    """The reference's CPU path: the ico2ico / ico2ico_vae graph and losses restated in oracle/models_ref.py over the oracle
+    icocnn port (fp32, PyTorch CPU, every host core).  Imports NOTHING from geniconet_b200 -- the product library is not
+    mapped into this process.  anomaly=True wraps the loop in torch.autograd.detect_anomaly() as the reference's train() does
+    (run.py:237).  Returns (median seconds per step, threads used)."""
     import contextlib
-    import torch
-    sys.path.insert(0, os.path.join(ROOT, 'tests'))
-    import oracle_models as om
-    from geniconet_b200 import models as gm, data
-    params = gm.default_params(model_name, level)
-    torch.manual_seed(0)
-    model = om.build_oracle_model(model_name, params)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
-    x, tgt = data.synthetic_batch(level, 0, batch)
-    f = (params['ico']['factor_pos'], params['ico']['factor_nor'], params['ico']['factor_lap'])
-    times = []
     import warnings
+    import torch
+    from oracle import models_ref, synth_ref
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)        # torchrun exports OMP_NUM_THREADS=1: without this the arm would run on one core
+    torch.manual_seed(0)
+    model = models_ref.build(model_name, level)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    x, tgt = synth_ref.synthetic_batch(level, 0, min(batch, 4))
+    reps = (batch + x.shape[0] - 1) // x.shape[0]                # distinct meshes cost host time to generate, not to train on
+    x, tgt = x.repeat(reps, 1, 1, 1)[:batch].contiguous(), tgt.repeat(reps, 1, 1)[:batch].contiguous()
+    times = []
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
         with (torch.autograd.detect_anomaly() if anomaly else contextlib.nullcontext()):
             for i in range(warmup + steps):
                 t0 = time.perf_counter()
                 opt.zero_grad()
-                out = model(x)
-                if model_name == 'ico2ico_vae':
-                    rec, mu, lv = out
-                    loss = om.ref_p2p_loss(level, rec, tgt, *f)[0] + om.ref_kld(mu, lv)
-                else:
-                    loss = om.ref_p2p_loss(level, out, tgt, *f)[0]
+                loss = models_ref.training_loss(model_name, level, model(x), tgt)
                 loss.backward()
                 opt.step()
                 float(loss)
@@ -124,21 +128,21 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    import torch
-    batch = args.cpu_batch
-    steps = max(1, min(args.steps, 5))
-    warmup = max(1, min(args.warmup, 2))
-    t, threads = cpu_reference_step_time(args.model, args.level, batch, steps, warmup)
-    t_anom, _ = cpu_reference_step_time(args.model, args.level, batch, min(steps, 3), 1, anomaly=True)   # as run.py:237 trains
-    val = batch / t
     B = args.batch or (36 if args.level == 5 else 16)
+    batch = args.cpu_batch or B                      # default: the arm's real per-GPU batch
+    steps = max(1, min(args.steps, 4))               # bounded: a batch-36 step is seconds of CPU time
+    warmup = max(1, min(args.warmup, 1))
+    t, threads = cpu_reference_step_time(args.model, args.level, batch, steps, warmup)
+    t_anom, _ = cpu_reference_step_time(args.model, args.level, batch, 1, 0, anomaly=True)   # as run.py:237 trains
+    val = batch / t
     line = {'impl': 'reference', 'metric': 'train_meshes_per_sec', 'value': val, 'unit': 'meshes/s', 'n_gpus': args.gpus,
             'steps': steps, 'warmup': warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': '%s I%d train step (fwd+loss+bwd+Adam), batch %d/GPU' % (args.model, args.level, B)},
+            'config': workload_config(args.model, args.level, B),
             'cpu_baseline': {'value': val, 'unit': 'meshes/s', 'cores': threads, 'kind': 'port',
-                             'sample': 'batch %d per step, median of %d steps after %d warm-up; oracle port of icocnn under the '
-                                       'reference graph, PyTorch CPU (oneDNN), fp32' % (batch, steps, warmup),
+                             'sample': 'one host process, batch %d per step, median of %d steps after %d warm-up; oracle/models_ref.py '
+                                       '(reference graph + losses restated) over the oracle icocnn port, PyTorch CPU (oneDNN), fp32, '
+                                       'torch.set_num_threads(os.cpu_count()=%d)' % (batch, steps, warmup, threads),
                              'with_detect_anomaly': batch / t_anom},
             'e2e': {'value': val, 'unit': 'meshes/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
@@ -174,8 +178,9 @@ def conv_calls(model, fused):
 
 def kernel_table(model, B, level, peaks, steps=5, fused=True):
     """Per-problem CUDA-event timings of the hex-conv kernels through the C ABI on activations of the real shapes (the problems
-    of conv_calls).  The `l2` column says for which of them input + output exceed the 126 MB L2 (back-to-back launches of the
-    others are L2-resident, as they largely are inside the real step)."""
+    of conv_calls).  Every problem runs on ROTATING buffer sets whose combined size exceeds twice the 126 MB L2, so a launch
+    never finds the operands of an earlier launch in L2 (`sets` in each row); launches are replayed as one CUDA graph and
+    timed with events on the replaying stream."""
     import torch
     from geniconet_b200 import _lib
     from geniconet_b200.ico_conv import get_plan
@@ -185,52 +190,55 @@ def kernel_table(model, B, level, peaks, steps=5, fused=True):
         n = 2 ** lvl
         Pin, Pout = 10 * 4 ** lvl, 10 * 4 ** lvl // (stride ** 2)
         lvl_out = lvl - (1 if stride == 2 else 0)
-        x = torch.randn(B, 5 * n, 2 * n, Ci, device='cuda').permute(0, 3, 1, 2)
-        dy = torch.randn(B, 5 * n // stride, 2 * n // stride, Co, device='cuda').permute(0, 3, 1, 2)
+        plan = get_plan(_lib.PLAN_HEXCONV, lvl, stride, cm, 'cuda')
+        st = torch.cuda.current_stream().cuda_stream
         w = torch.randn(Co, Ci, 7, device='cuda') * 0.05
         bias = torch.zeros(Co, device='cuda')
-        y = torch.empty_like(dy)
-        dx = torch.empty_like(x)
+        packed = torch.empty(L.gin_hexconv_packed_bytes(Ci, Co), dtype=torch.uint8, device='cuda')
+        _lib.check(L.gin_hexconv_pack_weights(w.data_ptr(), packed.data_ptr(), Ci, Co, st))
         dW = torch.empty(Co, Ci, 7, device='cuda')
         ws = torch.empty(L.gin_hexconv_wgrad_ws_bytes(Ci, Co), dtype=torch.uint8, device='cuda')
-        plan = get_plan(_lib.PLAN_HEXCONV, lvl, stride, cm, 'cuda')
-        packed = torch.empty(L.gin_hexconv_packed_bytes(Ci, Co), dtype=torch.uint8, device='cuda')
-        st = torch.cuda.current_stream().cuda_stream
-        _lib.check(L.gin_hexconv_pack_weights(w.data_ptr(), packed.data_ptr(), Ci, Co, st))
-        xb = torch.empty(L.gin_cast_bf16_bytes(B, lvl, Ci) // 2, dtype=torch.bfloat16, device='cuda')
-        dyb = torch.empty(L.gin_cast_bf16_bytes(B, lvl_out, Co) // 2, dtype=torch.bfloat16, device='cuda')
-        _lib.check(L.gin_cast_bf16(plan.host_ptr, plan.dev_ptr, 0, x.data_ptr(), xb.data_ptr(), B, Ci, st))
-        _lib.check(L.gin_cast_bf16(plan.host_ptr, plan.dev_ptr, 1, dy.data_ptr(), dyb.data_ptr(), B, Co, st))
+        set_bytes = B * (6.0 * Ci * Pin + 6.0 * Co * Pout)           # bf16 copy + fp32 map on either side
+        nsets = int(min(8, max(2, -(-2 * 126e6 // set_bytes) + 1)))
+        sets = []
+        for _ in range(nsets):
+            x = torch.randn(B, 5 * n, 2 * n, Ci, device='cuda').permute(0, 3, 1, 2)
+            dy = torch.randn(B, 5 * n // stride, 2 * n // stride, Co, device='cuda').permute(0, 3, 1, 2)
+            xb = torch.empty(L.gin_cast_bf16_bytes(B, lvl, Ci) // 2, dtype=torch.bfloat16, device='cuda')
+            dyb = torch.empty(L.gin_cast_bf16_bytes(B, lvl_out, Co) // 2, dtype=torch.bfloat16, device='cuda')
+            _lib.check(L.gin_cast_bf16(plan.host_ptr, plan.dev_ptr, 0, x.data_ptr(), xb.data_ptr(), B, Ci, st))
+            _lib.check(L.gin_cast_bf16(plan.host_ptr, plan.dev_ptr, 1, dy.data_ptr(), dyb.data_ptr(), B, Co, st))
+            sets.append((xb, dyb, torch.empty_like(dy), torch.empty_like(x)))
+            del x, dy
 
-        def fwd():
-            _lib.check(L.gin_hexconv_fwd_bf16(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), packed.data_ptr(), bias.data_ptr(), y.data_ptr(), B, Ci, Co, st))
+        def fwd(b, s):
+            _lib.check(L.gin_hexconv_fwd_bf16(plan.host_ptr, plan.dev_ptr, b[0].data_ptr(), packed.data_ptr(), bias.data_ptr(), b[2].data_ptr(), B, Ci, Co, s))
 
-        def dgrad():
-            _lib.check(L.gin_hexconv_dgrad_bf16(plan.host_ptr, plan.dev_ptr, dyb.data_ptr(), packed.data_ptr(), dx.data_ptr(), B, Ci, Co, st))
+        def dgrad(b, s):
+            _lib.check(L.gin_hexconv_dgrad_bf16(plan.host_ptr, plan.dev_ptr, b[1].data_ptr(), packed.data_ptr(), b[3].data_ptr(), B, Ci, Co, s))
 
-        def wgrad():
-            _lib.check(L.gin_hexconv_wgrad_bf16(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), dyb.data_ptr(), None, dW.data_ptr(), None, ws.data_ptr(),
-                                                B, Ci, Co, st))
+        def wgrad(b, s):
+            _lib.check(L.gin_hexconv_wgrad_bf16(plan.host_ptr, plan.dev_ptr, b[0].data_ptr(), b[1].data_ptr(), None, dW.data_ptr(), None, ws.data_ptr(),
+                                                B, Ci, Co, s))
         flops = 2.0 * 7 * Ci * Co * Pout * B
         # algorithmic bytes of one pass: bf16 operand copy read once + fp32 result written once (fwd, dgrad); both copies read (wgrad)
         by = {'fwd': B * (2.0 * Ci * Pin + 4.0 * Co * Pout), 'dgrad': B * (2.0 * Co * Pout + 4.0 * Ci * Pin),
               'wgrad': B * (2.0 * Ci * Pin + 2.0 * Co * Pout) + 28.0 * Ci * Co}
         ent = {'layer': name, 'cin': Ci, 'cout': Co, 'stride': stride, 'level': lvl, 'count': count, 'gflop': flops / 1e9,
-               'l2': 'exceeds' if by['fwd'] > 126e6 else 'fits'}
+               'sets': nsets, 'set_mbytes': set_bytes / 1e6}
+        nl = max(steps, nsets) * 2
         for tag, fn in (('fwd', fwd), ('dgrad', dgrad), ('wgrad', wgrad)):
-            for _ in range(2):
-                fn()
+            for b in sets[:2]:
+                fn(b, st)
             torch.cuda.synchronize()
-            # device time only: `steps` back-to-back calls replayed as one CUDA graph (issued from Python a call costs
+            # device time only: `nl` back-to-back calls replayed as one CUDA graph (issued from Python a call costs
             # 20-30 us of host time, more than several of these kernels run)
             side = torch.cuda.Stream()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.stream(side):
-                st_saved, st = st, side.cuda_stream
                 with torch.cuda.graph(graph, stream=side):
-                    for _ in range(steps):
-                        fn()
-                st = st_saved
+                    for i in range(nl):
+                        fn(sets[i % nsets], side.cuda_stream)
             graph.replay()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -238,13 +246,58 @@ def kernel_table(model, B, level, peaks, steps=5, fused=True):
             graph.replay()
             e1.record()
             torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / steps
+            ms = e0.elapsed_time(e1) / nl
             ent[tag + '_us'] = ms * 1e3
             ent[tag + '_tflops'] = flops / (ms * 1e-3) / 1e12
             ent[tag + '_mbytes'] = by[tag] / 1e6
             ent[tag + '_gbs'] = by[tag] / (ms * 1e-3) / 1e9
         rows.append(ent)
+        del sets
     return rows
+
+
+def conv_roofline(table, peaks, args, B):
+    """`roofline` object: the tcgen05 hex-conv kernel family (cv2::patch_conv_kernel [+ pair variant] forward and dgrad,
+    wg2::wgrad_patch_kernel [+ reduce]) over ALL launches of one training step -- forward + dgrad + wgrad of every problem.
+    achieved = sum of algorithmic FLOPs / sum of measured durations; the per-pass aggregates stay in `passes`."""
+    hbm = peaks.get('hbm_gbs', 6650.0)
+    tf_burst = peaks.get('bf16_tflops', 1590.0)
+    ridge = tf_burst * 1e12 / (hbm * 1e9)
+    tags = ('fwd', 'dgrad', 'wgrad')
+    nl = 3 * sum(r['count'] for r in table)
+    gflop1 = sum(r['gflop'] * r['count'] for r in table)
+    gflop = 3 * gflop1
+    mbytes = sum(r[t + '_mbytes'] * r['count'] for r in table for t in tags)
+    us = sum(r[t + '_us'] * r['count'] for r in table for t in tags)
+    ai = gflop * 1e9 / (mbytes * 1e6)
+    if ai >= ridge:
+        roof = {'bound': 'tensor', 'achieved': gflop / 1e3 / (us * 1e-6), 'peak': tf_burst, 'unit': 'TFLOP/s'}
+    else:
+        roof = {'bound': 'hbm', 'achieved': mbytes / 1e3 / (us * 1e-6), 'peak': hbm, 'unit': 'GB/s'}
+    roof['frac'] = roof['achieved'] / roof['peak']
+    roof['traffic'] = None
+    try:          # ncu dram__bytes_read.sum + dram__bytes_write.sum of exactly this launch set (tools/measure_traffic.py)
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))
+        if tr.get('launches') == nl and args.model == 'ico2ico' and args.level == 5 and B == 36:
+            roof['traffic'] = tr['dram_bytes_per_launch'] / 1e6
+            roof['traffic_unit'] = 'MB per launch (dram__bytes_read.sum + dram__bytes_write.sum, L2 flushed before every launch)'
+    except Exception:
+        pass
+    roof['kernel'] = 'tcgen05 hex-conv kernels (cv2::patch_conv*, wg2::wgrad_patch*): the %d fwd + dgrad + wgrad calls of one step' % nl
+    roof['peak_source'] = ('measured' if peaks else 'fallback') + ' (MEASURED_PEAKS.json burst figure: kernels timed alone, back to back)'
+    roof['timing'] = 'CUDA events around a replayed CUDA graph of back-to-back launches over rotating buffer sets > 2x L2'
+    roof['algorithmic'] = {'gflop_per_launch': gflop / nl, 'mbytes_per_launch': mbytes / nl, 'us_per_launch': us / nl,
+                           'arithmetic_intensity': ai, 'ridge': ridge}
+    roof['passes'] = {}
+    for tag in tags:
+        t_us = sum(r[tag + '_us'] * r['count'] for r in table)
+        roof['passes'][tag] = {'us_per_step': t_us, 'tflops': gflop1 / 1e3 / (t_us * 1e-6),
+                               'frac_of_peak': gflop1 / 1e3 / (t_us * 1e-6) / tf_burst}
+    allp = [(r[t + '_tflops'], t, r) for r in table for t in tags]
+    lo, hi = min(allp, key=lambda v: v[0]), max(allp, key=lambda v: v[0])
+    fmt = lambda v: '%s %d->%d s%d L%d: %.0f TFLOP/s' % (v[1], v[2]['cin'], v[2]['cout'], v[2]['stride'], v[2]['level'], v[0])
+    roof['range'] = {'best': fmt(hi), 'worst': fmt(lo)}
+    return roof
 
 
 def run_ours(args):
@@ -386,73 +439,27 @@ def run_ours(args):
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         except Exception:
             pass
-        hbm = peaks.get('hbm_gbs', 6650.0)
-        tf_burst = peaks.get('bf16_tflops', 1590.0)
-        src = 'measured' if peaks else 'fallback'
         if not args.no_kernel_table:
             from geniconet_b200 import models as _gm
             table = kernel_table(model, B, args.level, peaks, fused=_gm._FUSED)
-            # The dominant kernel FUNCTION of the step is cv2::patch_conv_kernel (profiles/r01_launch_list_final_step.txt: 30 % of
-            # the device time with its pair variant, ahead of wg2::wgrad_patch_kernel with 14 %): it runs every hex-conv forward and every in-chart
-            # dgrad.  Its launches differ in shape, so the roofline is the launch-weighted aggregate over the forward launches of
-            # one step: achieved = sum of algorithmic work / sum of durations (equivalently per-launch averages of both).
-            ridge = tf_burst * 1e12 / (hbm * 1e9)
-            nl = sum(r['count'] for r in table)
-            gflop = sum(r['gflop'] * r['count'] for r in table)
-            mbytes = sum(r['fwd_mbytes'] * r['count'] for r in table)
-            us = sum(r['fwd_us'] * r['count'] for r in table)
-            ai = gflop * 1e9 / (mbytes * 1e6)
-            if ai >= ridge:
-                roof = {'bound': 'tensor', 'achieved': gflop / 1e3 / (us * 1e-6), 'peak': tf_burst, 'unit': 'TFLOP/s'}
-            else:
-                roof = {'bound': 'hbm', 'achieved': mbytes / 1e3 / (us * 1e-6), 'peak': hbm, 'unit': 'GB/s'}
-            roof['frac'] = roof['achieved'] / roof['peak']
-            # dram__bytes_read.sum + dram__bytes_write.sum of `ncu --set full` captures of this kernel (profiles/r01_ncu_conv_kernels.txt)
-            # exist for single shapes, not for the launch mix of a step: fwd 128->64 @I5 94.6 + 50.5 MB against 94.4 + 94.4 MB
-            # algorithmic (the unread part of the output still sits in L2 when the kernel ends), fwd 256->128 @I4 47.8 + 6.1 MB
-            # against 47.2 + 47.2 MB.  No re-reads from DRAM in either.
-            roof['traffic'] = None
-            try:          # the ncu measurement of exactly this launch set (tools/measure_traffic.py), committed under profiles/
-                tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
-                if tr.get('launches') == nl and args.model == 'ico2ico' and args.level == 5 and B == 36:
-                    roof['traffic'] = tr['dram_bytes_per_launch'] / 1e6
-                    roof['traffic_unit'] = 'MB per launch (dram__bytes_read.sum + dram__bytes_write.sum, L2 flushed before every launch; compare ' \
-                                           'algorithmic.mbytes_per_launch -- part of the fp32 output is still in L2 when a kernel ends)'
-            except Exception:
-                pass
-            roof['kernel'] = 'cv2::patch_conv_kernel, the %d forward launches of one step (tcgen05 implicit-GEMM hex-conv)' % nl
-            roof['peak_source'] = src + ' (MEASURED_PEAKS.json burst figure: kernels timed alone, back to back)' if peaks else 'fallback 6650 GB/s / 1590 TFLOP/s'
-            roof['algorithmic'] = {'gflop_per_launch': gflop / nl, 'mbytes_per_launch': mbytes / nl, 'us_per_launch': us / nl,
-                                   'arithmetic_intensity': ai, 'ridge': ridge}
-            # the same aggregate for the three passes as the C ABI exposes them (dgrad = in-chart pass + cross-seam pass, wgrad =
-            # split-K kernel + reduction)
-            roof['passes'] = {}
-            for tag in ('fwd', 'dgrad', 'wgrad'):
-                t_us = sum(r[tag + '_us'] * r['count'] for r in table)
-                roof['passes'][tag] = {'us_per_step': t_us, 'tflops': gflop / 1e3 / (t_us * 1e-6),
-                                       'frac_of_peak': gflop / 1e3 / (t_us * 1e-6) / tf_burst}
-            worst = min(((r['fwd_tflops'], r) for r in table), key=lambda t: t[0])[1]
-            best = max(((r['fwd_tflops'], r) for r in table), key=lambda t: t[0])[1]
-            roof['range'] = {'best': '%d->%d s%d L%d: %.0f TFLOP/s' % (best['cin'], best['cout'], best['stride'], best['level'], best['fwd_tflops']),
-                             'worst': '%d->%d s%d L%d: %.0f TFLOP/s' % (worst['cin'], worst['cout'], worst['stride'], worst['level'], worst['fwd_tflops'])}
+            roof = conv_roofline(table, peaks, args, B)
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        t_cpu, threads = cpu_reference_step_time(args.model, args.level, args.cpu_batch, 3, 1)
-        cpu = {'value': args.cpu_batch / t_cpu, 'unit': 'meshes/s', 'cores': threads, 'kind': 'port',
-               'sample': 'batch %d train step (fwd+loss+bwd+Adam), median of 3 after 1 warm-up; oracle port of icocnn under the '
-                         'reference graph on PyTorch CPU fp32' % args.cpu_batch}
+        cb = args.cpu_batch or B
+        t_cpu, threads = cpu_reference_step_time(args.model, args.level, cb, 2, 1)
+        cpu = {'value': cb / t_cpu, 'unit': 'meshes/s', 'cores': threads, 'kind': 'port',
+               'sample': 'batch %d train step (fwd+loss+bwd+Adam), median of 2 after 1 warm-up; oracle/models_ref.py over the oracle '
+                         'icocnn port on PyTorch CPU fp32, torch.set_num_threads(os.cpu_count()=%d)' % (cb, threads)}
     if rank == 0:
         meshes = B * world
-        act_gb = 12.0 * B / 36 * (4 ** (args.level - 5))
         line = {'metric': 'train_meshes_per_sec', 'value': meshes / (ms_step * 1e-3), 'unit': 'meshes/s', 'n_gpus': world,
                 'steps': args.steps, 'warmup': W, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'bf16 operands / f32 accumulate (tcgen05); f32 activations, BN, loss, Adam',
                 'data': 'synthetic',
-                'config': {'workload': '%s I%d train step (fwd+loss+bwd+allreduce+Adam), batch %d/GPU' % (args.model, args.level, B),
-                           'conv_impl': args.conv_impl, 'parallelism': 'dp%d' % world,
-                           'launch': 'one CUDA graph replay per step' if use_graph else 'eager (one launch per kernel)',
-                           'l2': 'no flush: one step streams ~%.0f GB of activations, far beyond the 126 MB L2' % act_gb},
+                'config': workload_config(args.model, args.level, B),
+                'details': {'conv_impl': args.conv_impl, 'parallelism': 'dp%d' % world,
+                            'launch': 'one CUDA graph replay per step' if use_graph else 'eager (one launch per kernel)'},
                 'e2e': {'value': meshes / (ms_e2e * 1e-3), 'unit': 'meshes/s', 'ms_per_step': ms_e2e,
                         'h2d_bytes_per_step': x_host.numel() * 4 + t_host.numel() * 4, 'd2h_bytes_per_step': 4},
                 'gpu_launches': int(launches), 'clocks': clk, 'loss': final_loss,

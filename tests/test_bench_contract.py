@@ -25,6 +25,20 @@ def test_reference_arm_prints_one_json_line():
     assert 'workload' in d['config'] and d['vs_baseline'] is None
 
 
+def test_reference_arm_uses_all_cores_and_never_maps_the_product_library():
+    """Under torchrun OMP_NUM_THREADS=1 is exported: the arm must still use every host core.  It runs oracle/ only, so neither the
+    product package nor libgeniconet_b200.so may appear in the process."""
+    code = ("import os, sys, json; sys.path.insert(0, %r); import bench; "
+            "t, threads = bench.cpu_reference_step_time('ico2ico', 5, 1, 1, 0); "
+            "maps = open('/proc/self/maps').read(); "
+            "print(json.dumps({'threads': threads, 'so': 'libgeniconet' in maps, "
+            "'mods': [m for m in sys.modules if m.startswith('geniconet_b200')]}))" % ROOT)
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS='1'))
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d['threads'] == (os.cpu_count() or 1) and not d['so'] and not d['mods'], d
+
+
 def test_reference_arm_other_ranks_exit_quietly():
     r = _run(['--impl', 'reference', '--gpus', '2'], env={'RANK': '1', 'WORLD_SIZE': '2', 'LOCAL_RANK': '1'})
     assert r.returncode == 0 and r.stdout.strip() == ''

@@ -190,3 +190,16 @@ def test_eval_helpers_refuse_cpu_tensors():
         iu.point_to_mesh_distance(torch.zeros(1, 4, 3), torch.zeros(1, 3, 3), torch.tensor([[0, 1, 2]]))
     with pytest.raises(ValueError):
         iu.point_to_mesh_distance(torch.zeros(1, 4, 2), torch.zeros(1, 3, 3), torch.tensor([[0, 1, 2]]))
+
+
+def test_oracle_synthetic_meshes_match_the_product_generator():
+    """oracle/synth_ref.py (what the CPU arm of bench.py trains on, no product import) and geniconet_b200.data.synthetic_mesh
+    state the same SURVEY 8d recipe over two independent geometry builders (numpy oracle vs the C ABI's host tables)."""
+    import torch
+    from oracle import synth_ref
+    from geniconet_b200 import data
+    for level, idx in ((2, 0), (4, 7)):
+        xo, to = synth_ref.synthetic_mesh(level, idx)
+        xp, tp = data.synthetic_mesh(level, idx)
+        assert xo.shape == xp.shape and to.shape == tp.shape
+        assert torch.allclose(xo, xp, rtol=0, atol=2e-6) and torch.allclose(to, tp, rtol=0, atol=2e-5)

@@ -1,6 +1,6 @@
 """Host-side logic that needs no GPU: model assembly mirrors the reference (state-dict keys and shapes), the golden
-fixture made from the reference's own models.py/losses.py over the oracle is reproduced by OUR graphs over the oracle
-layers, and the product refuses to run on the CPU."""
+fixture made from the reference's own models.py/losses.py over the oracle layers is reproduced by the oracle's restated
+graphs (oracle/models_ref.py -- this is what pins that restatement), and the product refuses to run on the CPU."""
 import json
 import os
 
@@ -35,6 +35,23 @@ def test_state_dict_matches_reference(name):
     assert n_param == {'ico2ico': 4627715, 'ico2ico_vae': 6004739}[name]
 
 
+@pytest.mark.parametrize('name', ['ico2ico', 'ico2ico_vae'])
+def test_oracle_graph_has_the_reference_state_dict(name):
+    """oracle/models_ref.py (self-contained, no product import) carries the reference's keys and shapes in order."""
+    m = om.build_oracle_model(name, level=5)
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == GOLD[name]['state_dict']
+    assert list(m.state_dict()) == list(GOLD[name]['state_dict'])
+
+
+def test_oracle_modules_do_not_import_the_product():
+    """The CPU arm of bench.py must not map libgeniconet_b200.so: the oracle package imports nothing from geniconet_b200."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path[:0] = [%r, %r]; import oracle_models, oracle.synth_ref, oracle.models_ref; "
+            "bad = [m for m in sys.modules if m.startswith('geniconet_b200')]; assert not bad, bad" % (os.path.dirname(HERE), HERE))
+    subprocess.run([sys.executable, '-c', code], check=True)
+
+
 def test_split_models_share_keys():
     p = gm.default_params('ico2ico')
     full = set(gm.ico2ico(p).state_dict())
@@ -45,7 +62,7 @@ def test_split_models_share_keys():
 
 
 def test_our_graph_over_oracle_reproduces_reference_golden():
-    """reference models.py + losses.py over the oracle (golden)  ==  geniconet_b200.models over the oracle."""
+    """reference models.py + losses.py over the oracle layers (golden)  ==  oracle/models_ref.py."""
     g = GOLD['ico2ico']
     x, tgt = _inputs(5, g['batch'], g['input_seed'])
     m = om.fill_params_deterministic(om.build_oracle_model('ico2ico', gm.default_params('ico2ico')))
@@ -63,14 +80,9 @@ def test_our_graph_over_oracle_reproduces_reference_golden():
 def test_vae_graph_over_oracle_reproduces_reference_golden():
     g = GOLD['ico2ico_vae']
     x, tgt = _inputs(5, g['batch'], g['input_seed'])
-    orig = gm._reparameterize
-    gm._reparameterize = lambda mu, lv: torch.randn_like(lv) * torch.exp(0.5 * lv) + mu      # models.py:89-92 on the CPU generator
-    try:
-        m = om.fill_params_deterministic(om.build_oracle_model('ico2ico_vae', gm.default_params('ico2ico_vae')))
-        torch.manual_seed(g['eps_seed'])
-        rec, mu, lv = m(x)
-    finally:
-        gm._reparameterize = orig
+    m = om.fill_params_deterministic(om.build_oracle_model('ico2ico_vae', gm.default_params('ico2ico_vae')))
+    torch.manual_seed(g['eps_seed'])                     # eps = torch.randn_like(std) on the CPU generator (models.py:89-92)
+    rec, mu, lv = m(x)
     loss = om.ref_p2p_loss(5, rec, tgt, 0.6, 0.2, 0.2)[0] + om.ref_kld(mu, lv)
     assert abs(loss.item() - g['loss']) <= 1e-5 * abs(g['loss'])
     assert torch.allclose(_sample(mu), torch.tensor(g['mu_sample']), rtol=1e-4, atol=1e-5)
