@@ -85,6 +85,8 @@ _SIGS = {
     'gin_point_mesh_distance': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'gin_vertex_normals_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     'gin_laplacian_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
+    'gin_ring_ops_ws_bytes': (_sz, [_i, _i]),
+    'gin_ring_ops_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     'gin_p2p_ws_bytes': (_sz, [_i, _i]),
     'gin_p2p_loss_fwd': (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _f, _f, _f, _vp, _vp, _i, _vp]),
     'gin_p2p_loss_bwd': (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _f, _f, _f, _vp, _vp, _vp, _i, _vp]),

@@ -704,6 +704,27 @@ int gin_laplacian_fwd(const void* plan_host, const void* plan_dev, const float* 
   return check_launch("laplacian_fwd");
 }
 
+size_t gin_ring_ops_ws_bytes(int B, int level) {
+  if (B < 0 || level < 0 || level > 9) return 0;
+  return (size_t)B * ((size_t)(10 << (2 * level)) + 2) * 6 * 4;
+}
+
+int gin_ring_ops_bwd(const void* plan_host, const void* plan_dev, const float* v, const float* g_nrm, const float* g_lap, float* dv, void* ws, int B,
+                     void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!v || (!g_nrm && !g_lap) || !dv || !ws || B < 0) return fail(GIN_ERR_ARG, "gin_ring_ops_bwd: bad argument");
+  const GinLossPlanHdr* h;
+  int rc = loss_hdr(plan_host, plan_dev, &h);
+  if (rc) return rc;
+  if (B == 0) return GIN_OK;
+  const long long BV = (long long)B * h->V;
+  float* g = reinterpret_cast<float*>(ws);
+  gin::ring_ops_bwd_vertex_kernel<<<grid_for(BV, 256), 256, 0, st>>>(plan_words(plan_dev), v, g_nrm, g_lap, g, dv, B);
+  if ((rc = check_launch("ring_ops_bwd_vertex"))) return rc;
+  gin::p2p_bwd_gather_kernel<<<grid_for(BV, 256), 256, 0, st>>>(plan_words(plan_dev), v, g, dv, B);
+  return check_launch("ring_ops_bwd_gather");
+}
+
 // workspace layout: [v: B*V*3 f32][g: B*V*6 f32][dv: B*V*3 f32][partials: 1024*3 f64]
 size_t gin_p2p_ws_bytes(int B, int level) {
   if (B < 0 || level < 0 || level > 9) return 0;

@@ -226,6 +226,36 @@ p2p_bwd_vertex_kernel(const int32_t* __restrict__ plan, const float* __restrict_
   }
 }
 
+// Backward of compute_vertex_normals / compute_laplacian_batch as plain ops (mesh.utils shim): upstream cotangents gn [B][V][3]
+// (w.r.t. the unit normals, may be null) and gl [B][V][3] (w.r.t. the Laplacian, may be null) -> per-vertex cotangents in the
+// layout p2p_bwd_gather_kernel reads, and the direct term -gl into dv.  The gather pass then finishes dv.
+__global__ void __launch_bounds__(256)
+ring_ops_bwd_vertex_kernel(const int32_t* __restrict__ plan, const float* __restrict__ v, const float* __restrict__ gn_in,
+                           const float* __restrict__ gl_in, float* __restrict__ g, float* __restrict__ dv, int B) {
+  const GinLossPlanHdr* h = reinterpret_cast<const GinLossPlanHdr*>(plan);
+  const int V = h->V;
+  const int32_t* nbt = plan + h->ring_off;
+  const long long total = (long long)B * V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int u = (int)(i % V);
+    const float* vb = v + (size_t)(i / V) * V * 3;
+    F3 graw = f3(0.f, 0.f, 0.f), gl = f3(0.f, 0.f, 0.f);
+    if (gn_in) {
+      const RingGeom rg = ring_geom(vb, nbt + (size_t)u * 6);
+      const F3 gn = ldv(gn_in, i);
+      const float len = sqrtf(dot(rg.nraw, rg.nraw));
+      if (len > kNormalEps) {                       // n = nraw / |nraw|
+        const F3 n = (1.0f / len) * rg.nraw;
+        graw = (1.0f / len) * (gn - dot(gn, n) * n);
+      } else graw = (1.0f / kNormalEps) * gn;       // clamped: n = nraw / eps
+    }
+    if (gl_in) gl = ldv(gl_in, i);
+    float* gi = g + (size_t)i * 6;
+    gi[0] = graw.x; gi[1] = graw.y; gi[2] = graw.z; gi[3] = gl.x; gi[4] = gl.y; gi[5] = gl.z;
+    stv(dv, i, -1.0f * gl);
+  }
+}
+
 // backward pass B: gather the ring contributions.
 //   nraw_w = sum_i r_i x r_{i+1}  =>  d/d(u) over all w with u in ring(w):  sum_i g_{s_i} x (s_{i+1} - s_{i-1}),  s = ring(u)
 //   lap_w  = mean(ring(w)) - w    =>  + sum_i gl_{s_i} / deg(s_i)

@@ -191,6 +191,12 @@ int gin_pole_vertices_bwd(const void* plan_host, const void* plan_dev, const flo
 /* compute_vertex_normals / compute_laplacian_batch (mesh.utils; losses.py:54,57). */
 int gin_vertex_normals_fwd(const void* plan_host, const void* plan_dev, const float* v, float* nrm, int B, void* stream);
 int gin_laplacian_fwd(const void* plan_host, const void* plan_dev, const float* v, float* lap, int B, void* stream);
+/* Their backward (autograd through losses.py:54,57 when the reference's unmodified losses.py runs over the `mesh` shim):
+ * g_nrm / g_lap [B][P+2][3] are the cotangents of the two outputs (either may be NULL), dv [B][P+2][3] receives the vertex
+ * gradient.  ws: gin_ring_ops_ws_bytes(B, level). */
+size_t gin_ring_ops_ws_bytes(int B, int level);
+int gin_ring_ops_bwd(const void* plan_host, const void* plan_dev, const float* v, const float* g_nrm, const float* g_lap, float* dv,
+                     void* ws, int B, void* stream);
 /* Point2Point_Loss.forward (losses.py:47-82), row a8, fused: out[0..3] = l_pos, l_nor, l_lap,
  * f_pos*l_pos + f_nor*l_nor + f_lap*l_lap.  target [B][9][P+2] (generate.py:200-203).
  * ws: gin_p2p_ws_bytes(B, level). The backward re-derives everything from x/target. */

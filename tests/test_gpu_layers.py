@@ -401,3 +401,43 @@ def test_decoder_head_matches_float64(level, B):
     hooked[1].register_forward_hook(lambda m, i, o: None)
     assert not fused.head_supported(hooked, x)
     assert not fused.head_supported(torch.nn.Sequential(torch.nn.Conv2d(32, 3, kernel_size=(1, 1)), torch.nn.Tanh()).cuda(), x)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('level,B', [(2, 3), (4, 2)])
+def test_mesh_shim_ops_are_differentiable_and_match_oracle(level, B):
+    """mesh.utils as the reference's unmodified losses.py calls it (losses.py:39,54,57,71-80): forward values and the gradient
+    that flows back through compute_vertex_normals / compute_laplacian_batch, against the CPU oracle's autograd."""
+    import mesh.utils as mu                               # the product's shim package
+    from oracle import mesh_ref, ico_geometry_ref as geo
+    faces = torch.from_numpy(geo.get_ico_faces(level))
+    V = int(faces.max()) + 1
+    g = torch.Generator().manual_seed(17 + level)
+    base = torch.from_numpy(geo.get_icosahedral_grid(level)[0]).float()
+    v0 = (base[None] * (0.5 + 0.1 * torch.rand(B, V, 1, generator=g)) + 0.02 * torch.randn(B, V, 3, generator=g))
+    tgt = torch.randn(B, V, 9, generator=g) * 0.5
+    adj_ref = mesh_ref.compute_adjacency_matrix_sparse(V, faces)
+    adj = mu.compute_adjacency_matrix_sparse(V, faces)
+    assert adj.is_sparse and torch.equal(adj.indices(), adj_ref.indices())
+    crit = torch.nn.Module()
+    crit.register_buffer('adj_mat', adj)                  # losses.py:40
+    crit = crit.cuda()
+
+    def loss_of(v, t, nrm_fn, lap_fn, a, f):
+        nrm, lap = nrm_fn(v, f), lap_fn(v, a)
+        l_nor = torch.mean(1 - torch.nn.functional.cosine_similarity(nrm, t[:, :, 3:6], dim=2))
+        l_lap = torch.nn.functional.mse_loss(lap, t[:, :, 6:9])
+        return 0.6 * torch.nn.functional.mse_loss(v, t[:, :, :3]) + 0.2 * l_nor + 0.2 * l_lap, nrm, lap
+    vr = v0.clone().requires_grad_(True)
+    lr, nr, lapr = loss_of(vr, tgt, mesh_ref.compute_vertex_normals, mesh_ref.compute_laplacian_batch, adj_ref, faces)
+    lr.backward()
+    vc = v0.clone().cuda().requires_grad_(True)
+    lc, nc, lapc = loss_of(vc, tgt.cuda(), mu.compute_vertex_normals, mu.compute_laplacian_batch, crit.adj_mat, faces.cuda())
+    lc.backward()
+    assert torch.allclose(nc.detach().cpu(), nr.detach(), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(lapc.detach().cpu(), lapr.detach(), rtol=1e-4, atol=1e-6)
+    assert abs(lc.item() - lr.item()) <= 1e-5 * abs(lr.item())
+    gc, gr = vc.grad.cpu(), vr.grad
+    assert (gc - gr).norm() <= 1e-4 * gr.norm(), ((gc - gr).norm() / gr.norm()).item()
+    with pytest.raises(ValueError):
+        mu.compute_vertex_normals(vc, faces[:-1])

@@ -126,6 +126,35 @@ def test_reference_files_import_over_the_shim_packages():
         assert list(m.state_dict()) == list(GOLD['ico2ico']['state_dict'])
 
 
+def test_reference_losses_construct_over_the_mesh_shim():
+    """The reference's UNMODIFIED losses.py over the product's `icocnn` / `mesh` shim packages: losses.py:39-40 registers the
+    adjacency matrix as a buffer, so compute_adjacency_matrix_sparse must hand back a real tensor (build container only)."""
+    ref_losses = '/root/reference/losses.py'
+    if not os.path.exists(ref_losses):
+        pytest.skip('needs /root/reference')
+    import importlib.util
+    import mesh.utils                                     # noqa: F401  (the product shim, not the oracle)
+    spec = importlib.util.spec_from_file_location('_ref_losses_over_product', ref_losses)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    import geniconet_b200.mesh_utils as mu
+    assert mod.compute_vertex_normals is mu.compute_vertex_normals and mod.compute_laplacian_batch is mu.compute_laplacian_batch
+    for crit in (mod.P2P_Loss(5, 1., 0., 0.), mod.P2PKLD_Loss(5, 0.6, 0.2, 0.2, 1.0)):
+        adj = dict(crit.named_buffers())['adj_mat']
+        assert adj.is_sparse and tuple(adj.shape) == (10242, 10242) and adj._nnz() == 2 * 30 * 4 ** 5      # one entry per directed edge
+        assert tuple(crit.ico_faces.shape) == (20480, 3)
+        crit.to('cpu')                                    # run.py:456 moves the criterion with .to(device)
+        # no CPU path: the forward must refuse rather than fall back
+        x = torch.zeros(1, 3, 160, 64)
+        t = torch.zeros(1, 9, 10242)
+        with pytest.raises(RuntimeError):
+            crit((x, x, x), t) if isinstance(crit, mod.P2PKLD_Loss) else crit(x, t)
+    from oracle import mesh_ref, ico_geometry_ref as geo
+    want = mesh_ref.compute_adjacency_matrix_sparse(642, torch.from_numpy(geo.get_ico_faces(3)))
+    got = mu.compute_adjacency_matrix_sparse(642, torch.from_numpy(geo.get_ico_faces(3)))
+    assert torch.equal(want.indices(), got.indices()) and torch.equal(want.values(), got.values())
+
+
 def test_no_cpu_fallback():
     from geniconet_b200 import losses
     from geniconet_b200.ico_conv import IcoConvS2S, IcoUpsampleS2S
