@@ -21,9 +21,13 @@ class GinError(RuntimeError):
 
 
 def _load():
-    if not os.path.exists(LIB_PATH):
+    # A missing library is built here; a library that is OLDER than its sources (digest stamp mismatch) is rebuilt when nvcc is
+    # available and otherwise refused -- never loaded silently.  The build itself runs under a file lock, so the ranks of a
+    # torchrun job do not race on the same output file.
+    if not os.environ.get('GIN_LIB'):
         from . import build as _build
-        _build.build()
+        if not os.path.exists(LIB_PATH) or not _build.is_current():
+            _build.build()
     try:
         return ctypes.CDLL(LIB_PATH)
     except OSError as e:  # pragma: no cover

@@ -36,22 +36,37 @@ def _digest():
     return h.hexdigest()
 
 
+def is_current():
+    """True when the built library carries the digest of the sources and flags it would be built from now."""
+    try:
+        return os.path.exists(LIB) and open(STAMP).read().strip() == _digest()
+    except OSError:
+        return False
+
+
 def build(force=False, verbose=False):
-    dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
-        return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ['-o', LIB]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
-    with open(os.path.join(CSRC, '.build_log.txt'), 'w') as f:
-        f.write(' '.join(cmd) + '\n' + log)
-    if res.returncode != 0:
-        sys.stderr.write(log)
-        raise RuntimeError('nvcc failed building libgeniconet_b200.so')
-    if verbose:
-        print(log)
-    with open(STAMP, 'w') as f:
-        f.write(dig)
+    import fcntl
+    with open(os.path.join(HERE, '.build_lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)                 # one builder at a time (ranks of one job, parallel test workers)
+        dig = _digest()
+        if not force and is_current():
+            return LIB
+        tmp = LIB + '.tmp.%d' % os.getpid()
+        cmd = [_nvcc()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ['-o', tmp]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        log = res.stdout + res.stderr
+        with open(os.path.join(CSRC, '.build_log.txt'), 'w') as f:
+            f.write(' '.join(cmd) + '\n' + log)
+        if res.returncode != 0:
+            sys.stderr.write(log)
+            if os.path.exists(tmp):
+                os.remove(tmp)
+            raise RuntimeError('nvcc failed building libgeniconet_b200.so')
+        os.replace(tmp, LIB)                             # readers never see a half-written library
+        if verbose:
+            print(log)
+        with open(STAMP, 'w') as f:
+            f.write(dig)
     return LIB
 
 

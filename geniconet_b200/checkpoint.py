@@ -14,7 +14,11 @@ import os
 import torch
 
 from .data import natural_key
-from .ico_utils import getEpochNumber
+
+
+def _epoch_number(epoch):
+    """Checkpoint tags are the epoch itself or a one-letter prefix + epoch ('B12' for best models, run.py:326)."""
+    return epoch if isinstance(epoch, int) else int(str(epoch)[1:])
 
 
 def _model_path(params, modelName, epoch):
@@ -33,7 +37,7 @@ def saveModel(params, model, optimizer, epoch, modelName, val_loss, misc):
         print('%s model with %s epochs, already exists at %s, aborting saving !!' % (modelName, str(epoch), path))
         return False
     torch.save({'model_state_dict': model.state_dict(), 'optimizer_state_dict': optimizer.state_dict(),
-                'epoch': getEpochNumber(epoch), 'loss': val_loss, 'misc': misc}, path)
+                'epoch': _epoch_number(epoch), 'loss': val_loss, 'misc': misc}, path)
     return True
 
 

@@ -566,7 +566,7 @@ int gin_bn_stats(const float* y, int64_t ld, int64_t rows, int C, const float* g
   return check_launch("bn_stats_final");
 }
 
-size_t gin_hexconv_stats_ws_bytes(int Cout) { return Cout <= 0 ? 0 : (size_t)148 * 2 * Cout * 4; }
+size_t gin_hexconv_stats_ws_bytes(int Cout) { return Cout <= 0 ? 0 : (size_t)gin::kMaxSMs * 2 * Cout * 4; }   // one row per persistent CTA
 
 int gin_bn_stats_from_parts(const float* parts, int nparts, int64_t ld, int64_t rows, int C, const float* gamma, const float* beta, float eps,
                             float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked, float* stat, void* stream) {

@@ -22,6 +22,26 @@ struct GinSrcView {      // a gathered fp32 tensor with arbitrary element stride
 };
 
 namespace gin {
+// Per-device host state: function attributes (dynamic shared-memory size) are per context, so "configured once" must be
+// tracked per device; persistent grids size themselves from the device's SM count (148 on B200; capped there because the
+// per-CTA workspaces are sized for 148).
+constexpr int kMaxDevices = 64, kMaxSMs = 148;
+inline int current_device() { int d = 0; cudaGetDevice(&d); return d & (kMaxDevices - 1); }
+inline int num_sms() {
+  static int n[kMaxDevices] = {};
+  const int d = current_device();
+  if (!n[d]) {
+    int v = kMaxSMs;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || v <= 0) v = kMaxSMs;
+    n[d] = v < kMaxSMs ? v : kMaxSMs;
+  }
+  return n[d];
+}
+struct PerDeviceFlag {
+  bool done[kMaxDevices] = {};
+  bool& here() { return done[current_device()]; }
+};
+
 inline bool pdl_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("GIN_PDL"); v = (e && e[0] == '1') ? 1 : 0; }

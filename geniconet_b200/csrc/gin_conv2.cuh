@@ -489,7 +489,8 @@ template <int N_TILE>
 int launch(Params p, cudaStream_t st) {
   int smem_total = 0;
   if (!plan_smem(N_TILE, p.K, p.U, p.ntiles, p.Q, p, smem_total)) return -4;
-  static bool configured = false;
+  static PerDeviceFlag configured_on;
+  bool& configured = configured_on.here();
   if (!configured) {
     if (cudaFuncSetAttribute(patch_conv_kernel<N_TILE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
         cudaFuncSetAttribute(patch_conv_kernel<N_TILE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
@@ -499,7 +500,8 @@ int launch(Params p, cudaStream_t st) {
   }
   p.n_blocks = p.N / N_TILE;
   const long long items = (long long)p.total_tiles * p.n_blocks;
-  int grid = (int)(items < 148 ? items : 148);
+  const int sms = num_sms();
+  int grid = (int)(items < sms ? items : sms);
   grid -= grid % p.n_blocks;                         // every CTA keeps one n-block
   if (grid < p.n_blocks) grid = p.n_blocks;
   const bool stats = p.stats != nullptr && !p.flush_each;
@@ -532,7 +534,8 @@ inline int cv2_pick_ntile(long long tiles, int N) {
   for (int nt : {256, 128, 64}) {
     if (N % nt) continue;
     const long long items = tiles * (N / nt);
-    int ctas = (int)(items < 148 ? items : 148);
+    const int sms = num_sms();
+    int ctas = (int)(items < sms ? items : sms);
     ctas -= ctas % (N / nt);
     if (ctas < N / nt) ctas = N / nt;
     const long long rounds = (items + ctas - 1) / ctas;
@@ -551,7 +554,8 @@ inline bool cv2_pair_ok(const cv2::Params& p, int nt) {
   const int ntp = nt < 128 ? nt : 128;
   if (7 * (p.K / 64) * ntp * 128 <= 114688) return false;                   // the weights fit: the resident single-tile kernel is better
   auto rounds = [&](long long items, int n_blocks) {
-    int ctas = (int)(items < 148 ? items : 148);
+    const int sms = num_sms();
+    int ctas = (int)(items < sms ? items : sms);
     ctas -= ctas % n_blocks;
     if (ctas < n_blocks) ctas = n_blocks;
     return (items + ctas - 1) / ctas;

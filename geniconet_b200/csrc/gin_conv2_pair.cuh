@@ -315,7 +315,8 @@ int launch_pair(Params p, cudaStream_t st) {
   const int fixed = STAGE_BYTES + TAB_SLOTS * TAB_ROWS * 4 + BAR_BYTES + p.ntiles * p.Q * 4 + 16;
   const int smem_total = p.a_stages * p.a_stage_bytes + p.b_stages * N_TILE * 128 + fixed + 1024;
   if (smem_total > SMEM_LIMIT) return -4;
-  static bool configured = false;
+  static PerDeviceFlag configured_on;
+  bool& configured = configured_on.here();
   if (!configured) {
     if (cudaFuncSetAttribute(patch_conv_pair_kernel<N_TILE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
         cudaFuncSetAttribute(patch_conv_pair_kernel<N_TILE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -3;
@@ -323,7 +324,8 @@ int launch_pair(Params p, cudaStream_t st) {
   }
   p.n_blocks = p.N / N_TILE;
   const long long items = (long long)((p.total_tiles + 1) / 2) * p.n_blocks;
-  int grid = (int)(items < 148 ? items : 148);
+  const int sms = num_sms();
+  int grid = (int)(items < sms ? items : sms);
   grid -= grid % p.n_blocks;
   if (grid < p.n_blocks) grid = p.n_blocks;
   const bool stats = p.stats != nullptr;

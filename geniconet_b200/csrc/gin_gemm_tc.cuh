@@ -333,7 +333,8 @@ template <int N_TILE, int STAGES>
 int launch(const Params& p, int ntiles, cudaStream_t st) {
   using L = Smem<N_TILE, STAGES>;
   auto kern = gather_gemm_tc_kernel<N_TILE, STAGES>;
-  static bool configured = false;
+  static PerDeviceFlag configured_on;
+  bool& configured = configured_on.here();
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) return -3;
     configured = true;
@@ -573,7 +574,8 @@ template <int N_BLK, int NPAIRS, int STAGES>
 int launch(Params p, cudaStream_t st) {
   using L = Smem<N_BLK, NPAIRS, STAGES>;
   auto kern = wgrad_tc_kernel<N_BLK, NPAIRS, STAGES>;
-  static bool configured = false;
+  static PerDeviceFlag configured_on;
+  bool& configured = configured_on.here();
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) return -3;
     configured = true;

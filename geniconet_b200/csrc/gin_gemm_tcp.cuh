@@ -223,7 +223,8 @@ template <int N_TILE, int B_STAGES>
 int launch(const Params& p, cudaStream_t st) {
   using L = Smem<N_TILE, B_STAGES>;
   auto kern = patch_gemm_tc_kernel<N_TILE, B_STAGES>;
-  static bool configured = false;
+  static PerDeviceFlag configured_on;
+  bool& configured = configured_on.here();
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) return -3;
     configured = true;

@@ -30,7 +30,7 @@ constexpr int MAX_STAGES = 4;
 constexpr int TAB_SLOTS = 8, TAB_SRC = 256, TAB_ROWS = TAB_SRC + BM, TAB_BATCH = 4;
 constexpr int ATOM = BM * 128;               // one 64-channel atom of the dY tile: 128 pixel rows x 128 bytes
 constexpr int SMEM_LIMIT = 227 * 1024;
-constexpr int MAX_CTAS = 148;
+constexpr int MAX_CTAS = kMaxSMs;
 
 // A tile is `nplanes` stages (gin_conv2.cuh: Params): stride 1 has one image and four tap pairs, stride 2 has one image per
 // parity plane of the fine input and ONE tap pair per plane (taps {1,2} {5,6} {0,0} {3,4}); either way four accumulators.
@@ -282,7 +282,8 @@ wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, i
 template <int N_BLK>
 int launch(Params p, float* dW, cudaStream_t st) {
   auto kern = wgrad_patch_kernel<N_BLK>;
-  static bool configured = false;
+  static PerDeviceFlag configured_on;
+  bool& configured = configured_on.here();
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -3;
     configured = true;
@@ -295,7 +296,7 @@ int launch(Params p, float* dW, cudaStream_t st) {
   if (p.stages < 2) return -4;
   p.n_cblk = p.Cin / 64;
   const int units = p.n_cblk * (p.Cout / N_BLK);
-  int slices = MAX_CTAS / units;
+  int slices = num_sms() / units;              // <= MAX_CTAS / units: the partial-sum workspace is sized for MAX_CTAS
   if (slices > p.total_tiles) slices = p.total_tiles;
   if (slices < 1) slices = 1;
   p.slices = slices;

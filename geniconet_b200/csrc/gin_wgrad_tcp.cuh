@@ -189,7 +189,8 @@ template <int N_BLK>
 int launch(Params p, cudaStream_t st) {
   using L = Smem<N_BLK>;
   auto kern = wgrad_patch_tc_kernel<N_BLK>;
-  static bool configured = false;
+  static PerDeviceFlag configured_on;
+  bool& configured = configured_on.here();
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) return -3;
     configured = true;

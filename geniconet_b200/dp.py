@@ -110,5 +110,8 @@ def shard_sample_ids(step, rank, world, batch):
 
 
 def broadcast_parameters(model, src=0, process_group=None):
-    for t in list(model.parameters()) + list(model.buffers()):
-        dist.broadcast(t.data, src=src, group=process_group)
+    """Rank `src`'s parameters and buffers everywhere.  Written in place under no_grad (not through `.data`), so each
+    Parameter's version counter moves and weight-derived caches (IcoConvS2S._packed_weights) see the change."""
+    with torch.no_grad():
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t, src=src, group=process_group)

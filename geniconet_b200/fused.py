@@ -205,7 +205,7 @@ class _Chain(torch.autograd.Function):
                                          y.data_ptr(), B, 3, C, _lib.IMPL_AUTO, _stream()), 'gin_hexconv_fwd')
             stat = _bn_stats(y, 0, C, B * _P(level), C, bn)
             act_b, _ = _bn_act(y, 0, C, stat, None, 0, 0, None, B, level, C)
-            saved.append(dict(kind='stem', plan=plan, xs=xs, strides=(sb, sp, sc), y=y, stat=stat, out_b=act_b, C=C, level=level))
+            saved.append(dict(kind='stem', plan=plan, xs=xs, strides=(sb, sp, sc), y=y, stat=stat, out_b=act_b, C=C, level=level, packed=packed))
             i = 3
         else:                                                                # ---- chain starts on an fp32 map: make the operand copy
             blk = mods[0]
@@ -315,8 +315,12 @@ class _Chain(torch.autograd.Function):
                 _lib.check(L.gin_hexconv_wgrad(plan.host_ptr, plan.dev_ptr, st['xs'].data_ptr(), sb, sp, sc, dy_f.data_ptr(), dW.data_ptr(), db.data_ptr(),
                                                ws.data_ptr(), B, 3, C, _lib.IMPL_AUTO, _stream()), 'gin_hexconv_wgrad')
                 grads += [bs[:C], bs[C:2 * C], db, dW]
-                if ctx.x_needs_grad:
-                    raise RuntimeError('fused chain: gradient with respect to the xyz input is not provided (train with requires_grad=False inputs)')
+                if ctx.x_needs_grad:                     # gradient of the xyz input (exact fp32 gather-GEMM: 3 output channels)
+                    n = 2 ** lvl
+                    dxs = torch.empty((B * _P(lvl), 3), dtype=torch.float32, device=d.device)
+                    _lib.check(L.gin_hexconv_dgrad(plan.host_ptr, plan.dev_ptr, dy_f.data_ptr(), st['packed'].data_ptr(), dxs.data_ptr(), B, 3, C,
+                                                   _lib.IMPL_SIMT, _stream()), 'gin_hexconv_dgrad')
+                    dx = dxs.view(B, 5 * n, 2 * n, 3).permute(0, 3, 1, 2)
             else:   # 'input': gradient of the fp32 map the chain started from
                 n = 2 ** st['level']
                 dx = d.view(B, 5 * n, 2 * n, st['C']).permute(0, 3, 1, 2)

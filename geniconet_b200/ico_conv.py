@@ -82,25 +82,45 @@ def _new_map(B, C, H, W, device):
 
 
 class _CastCache:
-    """Last few bf16 activation copies, keyed by the identity of the fp32 tensor: the two sibling convolutions of a
-    residual block (conv00 / conv10, models.py:25-33) read the same input, so it is cast once."""
+    """Short-lived sharing of a derived tensor between two consumers of the SAME input tensor: the bf16 operand copy for the
+    sibling convolutions of a residual block (conv00 / conv10, models.py:25-33) and the upsampled map for upsample00 /
+    upsample10 (models.py:59-60).  An entry is keyed by the identity, version counter AND storage address of the input and by
+    the version counter of the cached output, so an in-place change of either between the two uses is a miss; entries whose
+    input tensor has died are purged on every access, `take=True` removes an entry on its first hit (the second consumer is the
+    last one), and clear_caches() drops everything (e.g. at the end of a step)."""
 
     def __init__(self, size=3):
         self.size, self.items = size, []
 
-    def get(self, t, key):
-        for ref, ver, k, out in self.items:
-            if ref() is t and ver == t._version and k == key:
+    def _purge(self):
+        self.items = [it for it in self.items if it[0]() is not None]
+
+    def get(self, t, key, take=False):
+        self._purge()
+        for i, (ref, ver, ptr, k, out, out_ver) in enumerate(self.items):
+            if ref() is t and ver == t._version and ptr == t.data_ptr() and k == key and out._version == out_ver:
+                if take:
+                    del self.items[i]
                 return out
         return None
 
     def put(self, t, key, out):
-        self.items.append((weakref.ref(t), t._version, key, out))
+        self._purge()
+        self.items.append((weakref.ref(t), t._version, t.data_ptr(), key, out, out._version))
         del self.items[:-self.size]
+
+    def clear(self):
+        self.items = []
 
 
 _cast_cache = _CastCache()
 _upsample_cache = _CastCache(size=2)
+
+
+def clear_caches():
+    """Drop the sibling-sharing caches (they hold at most a few tensors of the last forward)."""
+    _cast_cache.clear()
+    _upsample_cache.clear()
 
 
 def cast_bf16(x_cl, plan, which, level, use_cache=False, colsum=None):
@@ -109,7 +129,7 @@ def cast_bf16(x_cl, plan, which, level, use_cache=False, colsum=None):
     B, C = x_cl.shape[0], x_cl.shape[1]
     key = (plan.dev_ptr, which)
     if use_cache:
-        hit = _cast_cache.get(x_cl, key)
+        hit = _cast_cache.get(x_cl, key, take=True)
         if hit is not None:
             return hit
     out = torch.empty((_lib.lib.gin_cast_bf16_bytes(B, level, C) // 2,), dtype=torch.bfloat16, device=x_cl.device)
@@ -303,11 +323,12 @@ class IcoUpsampleS2S(torch.nn.Module):
         # (upsample00 / upsample10 of a BasicIcoS2SUpBlock, models.py:59-60) produce the same map: the second call returns
         # the first one's output (autograd adds the two incoming gradients before the single backward).
         key = (self.subdivisions, self.corner_mode)
-        hit = _upsample_cache.get(x, key)
-        if hit is not None and hit.requires_grad == (x.requires_grad and torch.is_grad_enabled()):
+        want_grad = x.requires_grad and torch.is_grad_enabled()
+        hit = _upsample_cache.get(x, (key, want_grad), take=True)
+        if hit is not None:
             return hit
         y = _UpsampleFn.apply(x, self)
-        _upsample_cache.put(x, key, y)
+        _upsample_cache.put(x, (key, want_grad), y)
         return y
 
     def extra_repr(self):

@@ -4,13 +4,12 @@ output2vertices     grid -> vertex list with averaged poles, on the GPU (gin_pol
 computeDistance     mode 'point2mesh': mean squared point-to-surface distance of the output vertices to the reference mesh
                     (ico_utils.py:26-44 over kaolin 0.9.1 point_to_mesh_distance), on the GPU (gin_point_mesh_distance)
 point_to_mesh_distance   the batched primitive underneath, same return convention as kaolin's (distance, face index)
-saveDistance, getEpochNumber, get_input_shape, get_output_shape, save_to_file   host helpers (ico_utils.py:46-103)
+
+The reference's logging / file helpers (saveDistance, getEpochNumber, save_to_file, get_*_shape; ico_utils.py:46-103) are host
+utilities outside the hot path and are not provided.
 
 No CPU fallback: CPU tensors raise RuntimeError.
 """
-import os
-
-import numpy as np
 import torch
 
 from . import _lib
@@ -67,62 +66,3 @@ def computeDistance(outvertices, refvertices, reffaces, f, mode='point2point', w
         dist, _ = point_to_mesh_distance(outvertices[None, :, :], refvertices[None, :, :], reffaces)
         return torch.mean(dist).cpu().numpy()
     return None
-
-
-def saveDistance(nameDistPair, path):
-    """ico_utils.py:46-65: '<path>.csv' with Name,Distance rows and the summary line; the histogram .png is written only when
-    matplotlib is importable."""
-    names, distances = [], []
-    with open(path + '.csv', 'w') as fh:
-        fh.write('Name,Distance\n')
-        for name, dist in nameDistPair:
-            fh.write('%s,%f\n' % (name, dist))
-            names.append(name)
-            distances.append(float(dist))
-    try:
-        import matplotlib
-        matplotlib.use('Agg')
-        import matplotlib.pyplot as plt
-        plt.figure()
-        plt.hist(distances, label=names)
-        plt.xlabel('Distance')
-        plt.xticks(rotation=30)
-        plt.ylabel('Frequency (total=%d)' % len(distances))
-        plt.title('Histogram of %s\n(%0.8f ± %0.8f) (Median: %0.8f))' % (os.path.basename(path), np.mean(distances), np.std(distances),
-                                                                             np.median(distances)))
-        plt.savefig(path + '.png')
-    except ImportError:
-        pass
-    print('%s: %0.8f +- %0.8f, Median: %0.8f' % (os.path.basename(path), np.mean(distances), np.std(distances), np.median(distances)))
-
-
-def getEpochNumber(epoch):
-    """ico_utils.py:68-74: 7 -> 7, 'B7' -> 7."""
-    if type(epoch) is int:
-        return epoch
-    if type(epoch) is str:
-        return int(epoch[1:])
-    raise ValueError('epoch type not specified')          # the reference builds this error without raising it (ico_utils.py:74)
-
-
-def get_input_shape(dataset):
-    return dataset.__getitem__(0)[0].shape
-
-
-def get_output_shape(model, dataset):
-    """ico_utils.py:81-95: shape of model(dataset[0]) without the batch dimension."""
-    dev = next(model.parameters()).device
-    item = dataset.__getitem__(0)
-    with torch.no_grad():
-        output = model(torch.as_tensor(item[0]).unsqueeze(0).to(dev))
-    return output.shape[1:]
-
-
-def save_to_file(file, *args, **kwds):
-    ext = os.path.splitext(file)[1]
-    if ext == '.npz':
-        np.savez_compressed(file, *args, **kwds)
-    elif ext == '.pt':
-        torch.save(*args, file)
-    else:
-        raise ValueError('File format %s not specified for save_to_file' % ext)

@@ -441,3 +441,39 @@ def test_mesh_shim_ops_are_differentiable_and_match_oracle(level, B):
     assert (gc - gr).norm() <= 1e-4 * gr.norm(), ((gc - gr).norm() / gr.norm()).item()
     with pytest.raises(ValueError):
         mu.compute_vertex_normals(vc, faces[:-1])
+
+
+@pytest.mark.gpu
+def test_upsample_sharing_survives_in_place_ops():
+    """upsample00 / upsample10 of an Up block read the same tensor (models.py:59-60) and share one kernel launch; an in-place
+    operation on the first result, or on the input, between the two calls must not leak into the second result."""
+    from geniconet_b200.ico_conv import IcoUpsampleS2S, clear_caches
+    clear_caches()
+    up0, up1 = IcoUpsampleS2S(8, 2, 'average'), IcoUpsampleS2S(8, 2, 'average')
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 8, 20, 8, generator=g).cuda()
+    want = up0(x.clone()).clone()
+    clear_caches()
+    a = up0(x)
+    b = up1(x)
+    assert b is a                                       # shared: same input, nothing changed in between
+    assert up1(x) is not a                              # the entry is handed out once
+    clear_caches()
+    a = up0(x)
+    a.mul_(2.0)                                         # consumer modifies its map in place
+    b = up1(x)
+    assert b is not a and torch.equal(b, want)
+    clear_caches()
+    a = up0(x)
+    x.add_(1.0)                                         # the input changes in place
+    b = up1(x)
+    assert b is not a and torch.equal(b, up0(x.clone()))
+    clear_caches()
+    xg = x.clone().requires_grad_(True)
+    a, b = up0(xg), up1(xg)
+    (a.sum() + 2 * b.sum()).backward()                  # autograd adds both consumers' gradients before the single backward
+    xr = x.clone().requires_grad_(True)
+    clear_caches()
+    (3 * up0(xr).sum()).backward()
+    assert torch.allclose(xg.grad, xr.grad)
+    clear_caches()
