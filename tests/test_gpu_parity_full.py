@@ -1,0 +1,172 @@
+"""Oracle parity of the path bench.py times -- fused chains + tcgen05 kernels -- at the BASELINE.json configurations
+(`north_star`: "ico2ico forward+backward at I5 with batch 36/GPU reproduces the reference's losses within tolerance"):
+
+    ico2ico      I5  B=36   P2P_Loss(1, 0, 0)                     (configs[1])
+    ico2ico_vae  I5  B=36   P2PKLD_Loss(0.6, 0.2, 0.2, 1)         (configs[2], the reference's real factors, run.py:693-696)
+    ico2ico      I6  B=16                                         (configs[3])
+
+against oracle/models_ref.py on the CPU (fp32): the same weights (name-keyed deterministic fill), the same synthetic meshes, the
+same reparameterisation noise.  Tolerances are the ones SURVEY 9.7 / VERDICT r01 state for bf16 operands with fp32 accumulation,
+written down BEFORE measuring: loss and per-term losses 2e-2 relative, output 5e-2 relative L2, per-parameter gradient cosine
+>= 0.99 (position loss; and any loss on a conditioned state).  The measured numbers go to gpurun_out/parity_full_configs.json.
+"""
+import json
+import os
+
+import pytest
+import torch
+
+import oracle_models as om
+from oracle import models_ref, synth_ref
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LOSS_TOL, OUT_TOL, COS_MIN = 2e-2, 5e-2, 0.99
+
+
+def _record(key, value):
+    path = os.path.join(ROOT, 'gpurun_out', 'parity_full_configs.json')
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    try:
+        data = json.load(open(path))
+    except Exception:
+        data = {}
+    data[key] = value
+    with open(path, 'w') as fh:
+        json.dump(data, fh, indent=1)
+
+
+def _cuda_step(name, level, state, x, t, factors, seed=42):
+    """One fused training step (forward + loss + backward) from `state`; returns loss, per-term tuple, grads, output, eps."""
+    from geniconet_b200 import models as gm, losses, reparam
+    gm.set_fused(True, True)
+    mod = getattr(gm, name)(gm.default_params(name, level))
+    mod.load_state_dict(state)
+    mod = mod.cuda().train()
+    crit = losses.P2PKLD_Loss(level, *factors, 1.0) if name == 'ico2ico_vae' else losses.P2P_Loss(level, *factors)
+    box = {}
+    orig = gm._reparameterize
+
+    def capture(mu, lv):
+        z, eps = reparam.reparameterize(mu, lv, seed=seed, offset=1, return_eps=True)
+        box['eps'] = eps.detach().cpu()
+        return z
+    gm._reparameterize = capture
+    try:
+        out = mod(x.cuda())
+    finally:
+        gm._reparameterize = orig
+    loss = crit(out, t.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    rec = out[0] if name == 'ico2ico_vae' else out
+    return (loss.item(), crit.get_last_losses(), {k: p.grad.detach().double().cpu().flatten() for k, p in mod.named_parameters()},
+            rec.detach().cpu(), box.get('eps'))
+
+
+def _oracle_step(name, level, state, x, t, factors, eps):
+    ref = models_ref.build(name, level)
+    ref.load_state_dict(state)
+    ref.train()
+    torch.set_num_threads(os.cpu_count() or 1)
+    out = ref(x, eps=eps) if name == 'ico2ico_vae' else ref(x)
+    rec = out[0] if name == 'ico2ico_vae' else out
+    recon, parts = models_ref.p2p_loss(level, rec, t, *factors)
+    kld = models_ref.kld_loss(out[1], out[2]) if name == 'ico2ico_vae' else None
+    loss = recon + kld if kld is not None else recon
+    loss.backward()
+    return (loss.item(), [float(p) for p in parts] + ([float(kld)] if kld is not None else []),
+            {k: p.grad.detach().double().flatten() for k, p in ref.named_parameters()}, rec.detach())
+
+
+def _cosines(gc, gr):
+    rows = {}
+    for k, b in gr.items():
+        if b.norm() < 1e-6:              # a conv bias in front of a BatchNorm: the true gradient is zero, both sides are rounding noise
+            continue
+        a = gc[k]
+        rows[k] = (a @ b / (a.norm() * b.norm() + 1e-300)).item()
+    return rows
+
+
+def _init_state(name, level):
+    return {k: v.detach().clone() for k, v in om.fill_params_deterministic(models_ref.build(name, level)).state_dict().items()}
+
+
+def _inputs(level, B, first):
+    x, t = synth_ref.synthetic_batch(level, first, min(B, 12))           # 12 distinct meshes, repeated to the batch size
+    reps = (B + x.shape[0] - 1) // x.shape[0]
+    return x.repeat(reps, 1, 1, 1)[:B].contiguous(), t.repeat(reps, 1, 1)[:B].contiguous()
+
+
+@pytest.mark.parametrize('name,level,B', [('ico2ico', 5, 36), ('ico2ico_vae', 5, 36), ('ico2ico', 6, 16)])
+def test_fused_step_matches_oracle_at_baseline_config(name, level, B):
+    factors = models_ref.LOSS_FACTORS[name]
+    state = _init_state(name, level)
+    x, t = _inputs(level, B, 300)
+    lc, parts_c, gc, out_c, eps = _cuda_step(name, level, state, x, t, factors)
+    lr, parts_r, gr, out_r = _oracle_step(name, level, state, x, t, factors, eps)
+    cos = _cosines(gc, gr)
+    out_rel = ((out_c - out_r).norm() / out_r.norm()).item()
+    rec = {'loss_cuda': lc, 'loss_oracle': lr, 'loss_rel': abs(lc - lr) / abs(lr), 'terms_cuda': [float(v) for v in parts_c], 'terms_oracle': parts_r,
+           'output_rel_l2': out_rel, 'grad_cos_min': min(cos.values()), 'grad_cos_mean': sum(cos.values()) / len(cos),
+           'grad_cos_worst_param': min(cos, key=cos.get), 'grad_cos': cos, 'state': 'random init (deterministic fill)', 'factors': factors}
+    _record('%s_I%d_B%d' % (name, level, B), rec)
+    assert abs(lc - lr) <= LOSS_TOL * abs(lr), (lc, lr)
+    assert out_rel <= OUT_TOL, out_rel
+    if name == 'ico2ico_vae':
+        # get_last_losses of P2PKLD_Loss: (recons, 0, 0, -kld, total)
+        recon_r = sum(f * p for f, p in zip(factors, parts_r[:3]))
+        assert abs(parts_c[0] - recon_r) <= LOSS_TOL * abs(recon_r) and abs(-parts_c[3] - parts_r[3]) <= LOSS_TOL * abs(parts_r[3]) + 1e-6
+        # The gradient of the normal / Laplacian terms on the crumpled mesh a random-init network emits is not a usable parity
+        # signal (profiles/r01_vae_grad_conditioning.txt); the cosines are recorded above and asserted on a conditioned state in
+        # test_conditioned_state_gradients_match_oracle.
+        assert all(torch.isfinite(g).all() for g in gc.values())
+    else:
+        for a, b in zip(parts_c[:3], parts_r[:3]):
+            assert abs(a - b) <= LOSS_TOL * abs(b) + 1e-6, (parts_c, parts_r)
+        assert min(cos.values()) >= COS_MIN, (min(cos, key=cos.get), min(cos.values()))
+
+
+@pytest.mark.parametrize('name', ['ico2ico', 'ico2ico_vae'])
+def test_conditioned_state_gradients_match_oracle(name):
+    """100 Adam steps of the fused bf16 path on synthetic meshes (so the network emits smooth meshes and the normal / Laplacian
+    terms are well conditioned), then ONE held-out batch: loss, per-term losses and every parameter's gradient against the CPU
+    oracle from the same weights, with the reference's real loss factors."""
+    from geniconet_b200 import models as gm, losses, reparam
+    level, B, steps = 5, 36, 100
+    factors = models_ref.LOSS_FACTORS[name]
+    gm.set_fused(True, True)
+    mod = getattr(gm, name)(gm.default_params(name, level))
+    mod.load_state_dict(_init_state(name, level))
+    mod = mod.cuda().train()
+    crit = losses.P2PKLD_Loss(level, *factors, 1.0) if name == 'ico2ico_vae' else losses.P2P_Loss(level, *factors)
+    opt = torch.optim.Adam(mod.parameters(), lr=3e-4)
+    pool = [tuple(v.cuda() for v in _inputs(level, B, 2000 + 12 * i)) for i in range(3)]
+    reparam.manual_seed(5)
+    first = last = None
+    for i in range(steps):
+        xb, tb = pool[i % len(pool)]
+        opt.zero_grad(set_to_none=True)
+        loss = crit(mod(xb), tb)
+        loss.backward()
+        opt.step()
+        if i == 0:
+            first = loss.item()
+    last = loss.item()
+    assert last < first, (first, last)
+    state = {k: v.detach().cpu().clone() for k, v in mod.state_dict().items()}
+    del mod, opt, pool
+    torch.cuda.empty_cache()
+    x, t = _inputs(level, B, 9000)
+    lc, parts_c, gc, out_c, eps = _cuda_step(name, level, state, x, t, factors)
+    lr, parts_r, gr, out_r = _oracle_step(name, level, state, x, t, factors, eps)
+    cos = _cosines(gc, gr)
+    out_rel = ((out_c - out_r).norm() / out_r.norm()).item()
+    _record('%s_I5_B36_conditioned' % name, {'train_loss_first': first, 'train_loss_after_100': last, 'loss_cuda': lc, 'loss_oracle': lr,
+                                             'loss_rel': abs(lc - lr) / abs(lr), 'terms_cuda': [float(v) for v in parts_c], 'terms_oracle': parts_r,
+                                             'output_rel_l2': out_rel, 'grad_cos_min': min(cos.values()), 'grad_cos_mean': sum(cos.values()) / len(cos),
+                                             'grad_cos_worst_param': min(cos, key=cos.get), 'grad_cos': cos, 'factors': factors})
+    assert abs(lc - lr) <= LOSS_TOL * abs(lr), (lc, lr)
+    assert out_rel <= OUT_TOL, out_rel
+    assert min(cos.values()) >= COS_MIN, (min(cos, key=cos.get), min(cos.values()))
