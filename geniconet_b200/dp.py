@@ -5,6 +5,12 @@ BatchNorm statistics stay per replica, and the only exchange is one gradient all
 (4.63 M fp32 = 18.5 MB for ico2ico).  Gradients are gathered into a few flat bucket buffers; a
 bucket's all-reduce is launched from autograd hooks as soon as its last gradient of the step has
 arrived, so the exchange overlaps the rest of backward.
+
+Two sources feed the buckets: (1) autograd's post-accumulate hooks (module-by-module path: gradients appear layer by layer);
+(2) the fused chains (geniconet_b200/fused.py), whose ONE autograd Function only returns its gradients when the whole chain's
+backward has run -- they hand every residual block's gradients to `early_grads()` as soon as the block's wgrad kernels are
+enqueued, so a bucket can start its all-reduce (NCCL enqueues on its own stream, also under CUDA-graph capture) while the
+remaining blocks are still being differentiated.
 """
 import torch
 import torch.distributed as dist
@@ -20,7 +26,10 @@ class GradBuckets:
     p.grad at the reduced views.  With world_size 1 nothing is copied or exchanged at all.
     """
 
-    def __init__(self, params, world_size, bucket_bytes=8 << 20, process_group=None):
+    def __init__(self, params, world_size, bucket_bytes=None, process_group=None):
+        import os
+        if bucket_bytes is None:
+            bucket_bytes = int(float(os.environ.get('GIN_DP_BUCKET_MB', '8')) * (1 << 20))
         self.world = int(world_size)
         self.group = process_group
         # reverse registration order ~ the order gradients become ready in backward
@@ -37,6 +46,7 @@ class GradBuckets:
             self._seal(cur)
         self._pending = [0] * len(self.buckets)
         self._handles = []
+        self._early = set()          # id(param) of gradients that arrived through early_grads() this step
         self._bucket_of = {}
         for bi, (_, ps, _) in enumerate(self.buckets):
             for p in ps:
@@ -61,18 +71,47 @@ class GradBuckets:
                 p.grad = None
             self._pending[bi] = len(ps)
         self._handles = []
+        self._early = set()
+        if self.world > 1:
+            from . import fused
+            fused.set_grad_sink(self.early_grads)
 
     def _on_grad(self, p):
+        if id(p) in self._early:                         # already counted (and copied) when the fused chain produced it
+            return
         bi = self._bucket_of[p]
         self._pending[bi] -= 1
         if self._pending[bi] == 0:
             self._launch(bi)
 
+    def early_grads(self, pairs):
+        """(parameter, gradient) pairs whose gradient kernels are enqueued on the current stream although autograd has not
+        assigned p.grad yet.  Each gradient is copied into its bucket slot now; a bucket whose last gradient arrives this way
+        starts its all-reduce immediately.  Parameters of other models (not in any bucket) are ignored."""
+        if self.world <= 1:
+            return
+        by_bucket = {}
+        for p, g in pairs:
+            bi = self._bucket_of.get(p)
+            if bi is None or id(p) in self._early or g is None:
+                continue
+            self._early.add(id(p))
+            by_bucket.setdefault(bi, []).append((p, g))
+        for bi, items in by_bucket.items():
+            flat, ps, views = self.buckets[bi]
+            slot = {id(p): v for p, v in zip(ps, views)}
+            torch._foreach_copy_([slot[id(p)] for p, _ in items], [g.view_as(p) for p, g in items])
+            self._pending[bi] -= len(items)
+            if self._pending[bi] == 0:
+                self._launch(bi)
+
     def _launch(self, bi):
         flat, ps, views = self.buckets[bi]
-        have = [(v, p.grad) for v, p in zip(views, ps) if p.grad is not None]
-        if len(have) < len(ps):
-            flat.zero_()                                 # parameters that got no gradient this step contribute zeros
+        have = [(v, p.grad) for v, p in zip(views, ps) if p.grad is not None and id(p) not in self._early]
+        if len(have) + sum(1 for p in ps if id(p) in self._early) < len(ps):
+            # parameters that got no gradient this step contribute zeros (their slots may hold last step's averages)
+            missing = [v for v, p in zip(views, ps) if p.grad is None and id(p) not in self._early]
+            torch._foreach_zero_(missing)
         if have:
             torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
         if dist.get_backend(self.group) == 'nccl':
@@ -98,6 +137,8 @@ class GradBuckets:
         for _, ps, views in self.buckets:
             for p, v in zip(ps, views):
                 p.grad = v
+        from . import fused
+        fused.set_grad_sink(None)
 
     def total_bytes(self):
         return sum(f.numel() * 4 for f, _, _ in self.buckets)

@@ -133,6 +133,15 @@ def _conv_wgrad(plan, xb, dyb, B, cin, cout, side=None):
 
 
 _side_streams = {}
+_grad_sink = None
+
+
+def set_grad_sink(fn):
+    """fn(list of (parameter, gradient)) is called from inside a chain's backward as soon as a block's gradients are enqueued
+    (data-parallel training: geniconet_b200.dp.GradBuckets starts the all-reduce of a complete bucket right there); None
+    removes it.  The chain still returns the same gradients to autograd afterwards."""
+    global _grad_sink
+    _grad_sink = fn
 
 
 def _wgrad_stream(dev):
@@ -259,6 +268,7 @@ class _Chain(torch.autograd.Function):
             saved.append(st)
             act_b, level, C = out_b, lvl, cout
         ctx.saved, ctx.B, ctx.nparams = saved, B, len(params)
+        ctx.mods = mods
         n = 2 ** level
         return out_f.view(B, 5 * n, 2 * n, C).permute(0, 3, 1, 2)
 
@@ -273,7 +283,9 @@ class _Chain(torch.autograd.Function):
         grads = []                # filled back to front, reversed at the end
         dx = None
         side = _wgrad_stream(d.device)
+        plist = chain_params(ctx.mods)          # the Parameter objects, in the order of the gradients this function returns
         for st in reversed(saved):
+            n_before = len(grads)
             if st['kind'] in ('down', 'up'):
                 cin, cout, lvl = st['cin'], st['cout'], st['level']
                 dev = d.device
@@ -324,6 +336,9 @@ class _Chain(torch.autograd.Function):
             else:   # 'input': gradient of the fp32 map the chain started from
                 n = 2 ** st['level']
                 dx = d.view(B, 5 * n, 2 * n, st['C']).permute(0, 3, 1, 2)
+            if _grad_sink is not None and side is None and len(grads) > n_before:
+                # grads[k] (appended back to front) belongs to plist[nparams - 1 - k]
+                _grad_sink([(plist[ctx.nparams - 1 - k], grads[k]) for k in range(n_before, len(grads))])
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)      # the weight gradients are consumed (optimizer, all-reduce) on the main stream
         grads.reverse()

@@ -54,6 +54,93 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+class _LateChain(torch.autograd.Function):
+    """Stand-in for geniconet_b200.fused._Chain: ONE Function over several parameters that hands its gradients to the
+    data-parallel sink while its backward is still running and returns them to autograd only at the end."""
+
+    @staticmethod
+    def forward(ctx, x, w1, w2, holder):
+        ctx.save_for_backward(x, w1, w2)
+        ctx.holder = holder
+        return (x @ w1.t()).relu() @ w2.t()
+
+    @staticmethod
+    def backward(ctx, dy):
+        from geniconet_b200 import fused
+        x, w1, w2 = ctx.saved_tensors
+        h = (x @ w1.t()).relu()
+        dw2 = dy.t() @ h
+        if fused._grad_sink is not None:
+            fused._grad_sink([(ctx.holder[1], dw2)])              # the "last block" is differentiated first
+        dh = (dy @ w2) * (h > 0)
+        dw1 = dh.t() @ x
+        if fused._grad_sink is not None:
+            fused._grad_sink([(ctx.holder[0], dw1)])
+        return dh @ w1, dw1, dw2, None
+
+
+def _worker_early(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from geniconet_b200.dp import GradBuckets
+    torch.manual_seed(7)
+    w1, w2 = torch.nn.Parameter(torch.randn(32, 16) * 0.2), torch.nn.Parameter(torch.randn(4, 32) * 0.2)
+    tail = torch.nn.Linear(4, 2)                                 # an ordinary module after the chain: arrives through autograd's hook
+    params = [w1, w2] + list(tail.parameters())
+    buckets = GradBuckets(params, world, bucket_bytes=64)        # one bucket per parameter
+    launched = []
+    orig = buckets._launch
+    buckets._launch = lambda bi: (launched.append(bi), orig(bi))[1]
+    x = torch.randn(6, 16, generator=torch.Generator().manual_seed(50 + rank))
+    outs = []
+    for it in range(2):
+        buckets.reset()
+        launched.clear()
+        tail(_LateChain.apply(x, w1, w2, (w1, w2))).pow(2).mean().backward()
+        order = list(launched)
+        buckets.finish()
+        outs.append([p.grad.detach().clone().numpy() for p in params])
+    # the purely local gradient, no communication
+    lw1, lw2 = w1.detach().clone().requires_grad_(True), w2.detach().clone().requires_grad_(True)
+    import copy
+    ltail = copy.deepcopy(tail)
+    for p in ltail.parameters():
+        p.grad = None
+    ltail((x @ lw1.t()).relu() @ lw2.t()).pow(2).mean().backward()
+    local = [lw1.grad.numpy(), lw2.grad.numpy()] + [p.grad.numpy() for p in ltail.parameters()]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local)
+    q.put((rank, outs, gathered, order, [buckets._bucket_of[p] for p in params]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_early_gradients_from_a_fused_chain_are_averaged_once():
+    """Gradients handed over from INSIDE a chain's backward (fused.set_grad_sink) start their bucket's all-reduce before autograd
+    has assigned p.grad; the later post-accumulate hook must not count them twice, and the result is still the rank mean."""
+    import numpy as np
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_early, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, outs0, gath, order, bucket_of), (_, outs1, _, _, _) = res
+    for step in range(2):
+        for k in range(len(outs0[step])):
+            want = (gath[0][k] + gath[1][k]) / 2
+            assert np.allclose(outs0[step][k], want, atol=1e-6) and np.allclose(outs1[step][k], want, atol=1e-6), (step, k)
+    # the tail module's buckets go first (autograd reaches it first), then w2's, then w1's -- each exactly once
+    assert len(order) == len(set(order)) == len(set(bucket_of))
+    assert order.index(bucket_of[1]) < order.index(bucket_of[0])
+
+
 def test_grad_buckets_average_over_two_ranks():
     import numpy as np
     world = 2
