@@ -40,6 +40,7 @@ _vp, _i, _i64, _u64, _f, _sz = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, c
                                 ctypes.c_size_t)
 _SIGS = {
     'gin_version': (_i, []),
+    'gin_forward_operand_is_fp16': (_i, []),
     'gin_last_error': (ctypes.c_char_p, []),
     'gin_launch_count': (_i64, []),
     'gin_index_map_len': (_i, [_i]),
@@ -104,6 +105,12 @@ for _name, (_res, _args) in _SIGS.items():
 def check(rc, what=''):
     if rc != 0:
         raise GinError('%s failed (%d): %s' % (what or 'geniconet_b200 call', rc, lib.gin_last_error().decode()))
+
+
+def forward_operand_dtype():
+    """torch dtype of the forward-side 16-bit operand copies (fp16 by default, bf16 under GIN_FWD_FP16=0)."""
+    import torch
+    return torch.float16 if lib.gin_forward_operand_is_fp16() else torch.bfloat16
 
 
 def launch_count():

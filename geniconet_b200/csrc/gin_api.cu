@@ -113,6 +113,8 @@ int run_gemm_tc(const int32_t* plan_dev, const GinConvPlanHdr* h, const void* Xb
   const void* wb = packed + (dgrad ? packed_off_bd(Cin, Cout) : packed_off_bf(Cin, Cout));
   const GinPSide& ps = dgrad ? h->pdg : h->pfwd;
   int rc;
+  // forward: activation copy x forward weight tiles (both the forward format); dgrad: dy copy x dgrad weight tiles (both bf16)
+  gin::set_operand_formats(dgrad || !gin::fwd_fp16(), dgrad || !gin::fwd_fp16());
   if (h->stride == 1 && patch_mode_enabled() && gin::tcp_supported(ps, K, N)) {
     if (tc_mode() == 2 && gin::cv2_supported(ps, K, N))
       rc = gin::launch_patch_conv2(plan_dev, ps, h->group, side.P_dst, 2 << h->level_in, Xb, wb, bias, Y, B, K, N, dgrad ? 1 : 0, st, dgrad ? nullptr : stats,
@@ -159,7 +161,8 @@ int run_gemm_tc(const int32_t* plan_dev, const GinConvPlanHdr* h, const void* Xb
 
 extern "C" {
 
-int gin_version(void) { return 100; }
+int gin_version(void) { return 200; }
+int gin_forward_operand_is_fp16(void) { return gin::fwd_fp16() ? 1 : 0; }
 const char* gin_last_error(void) { return g_err; }
 int64_t gin_launch_count(void) { return (int64_t)g_launches.load(); }
 
@@ -175,7 +178,7 @@ int gin_hexconv_pack_weights(const float* weight, void* packed, int Cin, int Cou
   gin::pack_weights_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
       weight, reinterpret_cast<float*>(pk + packed_off_wf(Cin, Cout)), reinterpret_cast<float*>(pk + packed_off_wd(Cin, Cout)),
       reinterpret_cast<unsigned short*>(pk + packed_off_bf(Cin, Cout)), reinterpret_cast<unsigned short*>(pk + packed_off_bd(Cin, Cout)),
-      Cin, Cout);
+      Cin, Cout, (int)gin::fwd_fp16());
   return check_launch("pack_weights");
 }
 
@@ -187,7 +190,7 @@ int gin_hexconv_pack_weights_bf16(const float* w0, int Cout0, const float* w1, i
   const long long n = 7LL * Cin * Cout;
   gin::launch_pdl(gin::pack_weights_bf16_kernel, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, 
       w0, Cout0, w1, reinterpret_cast<unsigned short*>(pk + packed_off_bf(Cin, Cout)), reinterpret_cast<unsigned short*>(pk + packed_off_bd(Cin, Cout)),
-      Cin, Cout);
+      Cin, Cout, (int)gin::fwd_fp16());
   return check_launch("pack_weights_bf16");
 }
 
@@ -250,6 +253,7 @@ static int wgrad_common(const GinConvPlanHdr* h, const void* plan_dev, const flo
                         int impl = GIN_IMPL_SIMT) {
   float* dWp = reinterpret_cast<float*>(ws);
   int rc;
+  gin::set_operand_formats(!gin::fwd_fp16(), true);        // wgrad: A = the forward activation copy, B = the bf16 dy copy
   const bool wg2_s1 = h->stride == 1 && gin::wg2_supported(h->pfwd, Cin, Cout), wg2_s2 = h->stride == 2 && gin::wg2_supported(h->p2, Cin, Cout);
   if (xb && B > 0 && tc_mode() == 2 && (wg2_s1 || wg2_s2)) {
     // second-generation patch wgrad: split-K partials in the workspace, reduced (and laid out as dW[Cout][Cin][7]) by a second kernel
@@ -344,7 +348,7 @@ int gin_cast_bf16(const void* plan_host, const void* plan_dev, int which, const 
   const GinSide& side = which == 0 ? h->fwd : h->dg;      // the gathered tensor of the forward / of dgrad
   const long long n8 = (long long)B * side.P_src * (C / 8) + 2LL * B * (C / 8);
   gin::cast_bf16_kernel<<<grid_for(n8, 256, 16), 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(xb), plan_words(plan_dev) + side.ring_off,
-                                                                B, side.P_src, C);
+                                                                B, side.P_src, C, (int)(which == 0 && gin::fwd_fp16()));
   return check_launch("cast_bf16");
 }
 
@@ -364,7 +368,7 @@ int gin_cast_bf16_colsum(const void* plan_host, const void* plan_dev, int which,
   int ctas = grid_for(n8, 256, 2);
   if (ctas > gin::CAST_COLSUM_MAX_CTAS) ctas = gin::CAST_COLSUM_MAX_CTAS;
   gin::cast_bf16_colsum_kernel<<<ctas, 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(xb), plan_words(plan_dev) + side.ring_off, B,
-                                                      side.P_src, C, reinterpret_cast<float*>(ws));
+                                                      side.P_src, C, reinterpret_cast<float*>(ws), (int)(which == 0 && gin::fwd_fp16()));
   if ((rc = check_launch("cast_bf16_colsum"))) return rc;
   gin::colsum_final_kernel<<<(C + 7) / 8, 256, 0, st>>>(reinterpret_cast<const float*>(ws), colsum, C, ctas);
   return check_launch("colsum_final");
@@ -585,8 +589,9 @@ int gin_bn_act_fwd(const float* y1, int64_t ld1, const float* stat1, const float
   const int n = 1 << level, P = 10 << (2 * level);
   const int ctas = gin::bn::grid_for_rows(((long long)B * P + 2LL * B) * (C >> 3));
   const gin::bn::Src s1{y1, (long long)ld1}, s2{y2, (long long)ld2};
-  if (y2) gin::launch_pdl(gin::bn::act_fwd_kernel<true>, dim3(ctas), dim3(256), 0, st, s1, stat1, s2, stat2, relu, reinterpret_cast<__nv_bfloat16*>(out_b), out_f, n, B, P, C);
-  else gin::launch_pdl(gin::bn::act_fwd_kernel<false>, dim3(ctas), dim3(256), 0, st, s1, stat1, s2, stat2, relu, reinterpret_cast<__nv_bfloat16*>(out_b), out_f, n, B, P, C);
+  const int f16 = (int)gin::fwd_fp16();          // out_b is the next convolution's FORWARD operand copy
+  if (y2) gin::launch_pdl(gin::bn::act_fwd_kernel<true>, dim3(ctas), dim3(256), 0, st, s1, stat1, s2, stat2, relu, reinterpret_cast<__nv_bfloat16*>(out_b), out_f, n, B, P, C, f16);
+  else gin::launch_pdl(gin::bn::act_fwd_kernel<false>, dim3(ctas), dim3(256), 0, st, s1, stat1, s2, stat2, relu, reinterpret_cast<__nv_bfloat16*>(out_b), out_f, n, B, P, C, f16);
   return check_launch("bn_act_fwd");
 }
 
@@ -642,8 +647,9 @@ int gin_upsample_bf16(const void* plan_host, const void* plan_dev, const void* i
   if (rc) return rc;
   const int ctas = gin::bn::grid_for_rows(((long long)B * h->Pf + 2LL * B) * (C >> 3));
   const int grid = ctas * 4 > 148 * 8 ? 148 * 8 : ctas * 4;
-  if (in_is_f32) gin::launch_pdl(gin::bn::upsample_bf16_kernel<true>, dim3(grid), dim3(256), 0, st, plan_words(plan_dev), in, reinterpret_cast<__nv_bfloat16*>(out_b), 2 << h->level, B, C);
-  else gin::launch_pdl(gin::bn::upsample_bf16_kernel<false>, dim3(grid), dim3(256), 0, st, plan_words(plan_dev), in, reinterpret_cast<__nv_bfloat16*>(out_b), 2 << h->level, B, C);
+  const int f16 = (int)gin::fwd_fp16();          // both the source copy (when 16-bit) and the result are forward operands
+  if (in_is_f32) gin::launch_pdl(gin::bn::upsample_bf16_kernel<true>, dim3(grid), dim3(256), 0, st, plan_words(plan_dev), in, reinterpret_cast<__nv_bfloat16*>(out_b), 2 << h->level, B, C, f16);
+  else gin::launch_pdl(gin::bn::upsample_bf16_kernel<false>, dim3(grid), dim3(256), 0, st, plan_words(plan_dev), in, reinterpret_cast<__nv_bfloat16*>(out_b), 2 << h->level, B, C, f16);
   return check_launch("upsample_bf16");
 }
 

@@ -15,6 +15,7 @@
 // for every grid-stride iteration.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 
@@ -49,6 +50,30 @@ GIN_DEVINL void st8_bf16(__nv_bfloat16* p, const float v[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
   *reinterpret_cast<uint4*>(p) = *reinterpret_cast<uint4*>(h);
+}
+// 8 values as a 16-byte group of forward operands (fp16 or bf16)
+GIN_DEVINL void st8_op(__nv_bfloat16* p, const float v[8], int f16) {
+  uint4 o;
+  o.x = pack2_op(v[0], v[1], f16); o.y = pack2_op(v[2], v[3], f16); o.z = pack2_op(v[4], v[5], f16); o.w = pack2_op(v[6], v[7], f16);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+// ReLU mask from an activation copy in EITHER 16-bit format: value > 0  <=>  sign bit clear and any other bit set
+GIN_DEVINL void ld8_mask(const __nv_bfloat16* p, bool m[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m[2 * i] = (w[i] & 0x8000u) == 0 && (w[i] & 0x7fffu) != 0;
+    m[2 * i + 1] = (w[i] & 0x80000000u) == 0 && (w[i] & 0x7fff0000u) != 0;
+  }
+}
+// 8 operands of either format -> fp32
+GIN_DEVINL void ld8_op(const __nv_bfloat16* p, float v[8], int f16) {
+  if (!f16) { ld8_bf16(p, v); return; }
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
 }
 GIN_DEVINL void st8(float* p, const float v[8]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
@@ -168,7 +193,7 @@ GIN_DEVINL void apply_row(const Src& y1, const Src& y2, long long r, int c, cons
 template <bool TWO>
 __global__ void __launch_bounds__(256)
 act_fwd_kernel(Src y1, const float* __restrict__ stat1, Src y2, const float* __restrict__ stat2, int relu, __nv_bfloat16* __restrict__ out_b,
-               float* __restrict__ out_f, int nlat, int B, int P, int C) {
+               float* __restrict__ out_f, int nlat, int B, int P, int C, int f16) {
   GIN_PDL_SYNC();
   const int C8 = C >> 3;
   const long long rows = (long long)B * P, n_main = rows * C8, n_all = n_main + 2LL * B * C8;
@@ -194,7 +219,7 @@ act_fwd_kernel(Src y1, const float* __restrict__ stat1, Src y2, const float* __r
         for (int k = 0; k < 8; ++k) o[k] = fmaf(0.2f, t[k], o[k]);
       }
     }
-    if (out_b) st8_bf16(out_b + (i / C8) * C + c, o);
+    if (out_b) st8_op(out_b + (i / C8) * C + c, o, f16);
   }
 }
 
@@ -204,10 +229,10 @@ GIN_DEVINL void grad_row(const float* __restrict__ dout, long long ldg, const __
                          int C, const float mean[8], const float invstd[8], float g[8], float yh[8]) {
   ld8(dout + r * ldg + c, g);
   if (mask) {
-    float m[8];
-    ld8_bf16(mask + r * C + c, m);
+    bool m[8];
+    ld8_mask(mask + r * C + c, m);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) g[k] = m[k] > 0.f ? g[k] : 0.f;
+    for (int k = 0; k < 8; ++k) g[k] = m[k] ? g[k] : 0.f;
   }
   float v[8];
   ld8(y.p + r * y.ld + c, v);
@@ -287,7 +312,7 @@ bwd_apply_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloa
 // operand copy [B*Pc + 2B][C] (coarse pole means taken from its pole rows).
 template <bool F32>
 GIN_DEVINL void up_fetch_any(const void* __restrict__ xin, const int32_t* __restrict__ cring, long long sample, int B, int Pc, int code, int C, int c,
-                             float v[8]) {
+                             float v[8], int f16) {
   if (code == GIN_SRC_ZERO) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = 0.f;
@@ -307,25 +332,25 @@ GIN_DEVINL void up_fetch_any(const void* __restrict__ xin, const int32_t* __rest
     }
   } else {
     const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(xin);
-    if (code >= 0) ld8_bf16(x + ((size_t)sample * Pc + code) * C + c, v);
-    else ld8_bf16(x + ((size_t)B * Pc + 2 * sample + ((-2 - code) & 1)) * C + c, v);     // the coarse pole-mean row
+    if (code >= 0) ld8_op(x + ((size_t)sample * Pc + code) * C + c, v, f16);
+    else ld8_op(x + ((size_t)B * Pc + 2 * sample + ((-2 - code) & 1)) * C + c, v, f16);     // the coarse pole-mean row
   }
 }
 template <bool F32>
 GIN_DEVINL void up_pixel(const int32_t* __restrict__ src, const void* __restrict__ xin, const int32_t* __restrict__ cring, long long sample, int B,
-                         int Pc, int f, int C, int c, float o[8]) {
+                         int Pc, int f, int C, int c, float o[8], int f16) {
   const int s0 = src[2 * f], s1 = src[2 * f + 1];
-  up_fetch_any<F32>(xin, cring, sample, B, Pc, s0, C, c, o);
+  up_fetch_any<F32>(xin, cring, sample, B, Pc, s0, C, c, o, f16);
   if (s0 != s1) {
     float t[8];
-    up_fetch_any<F32>(xin, cring, sample, B, Pc, s1, C, c, t);
+    up_fetch_any<F32>(xin, cring, sample, B, Pc, s1, C, c, t, f16);
 #pragma unroll
     for (int k = 0; k < 8; ++k) o[k] = 0.5f * (o[k] + t[k]);
   }
 }
 template <bool F32>
 __global__ void __launch_bounds__(256)
-upsample_bf16_kernel(const int32_t* __restrict__ plan, const void* __restrict__ xin, __nv_bfloat16* __restrict__ out, int nfine, int B, int C) {
+upsample_bf16_kernel(const int32_t* __restrict__ plan, const void* __restrict__ xin, __nv_bfloat16* __restrict__ out, int nfine, int B, int C, int f16) {
   GIN_PDL_SYNC();
   const GinUpPlanHdr* h = reinterpret_cast<const GinUpPlanHdr*>(plan);
   const int Pc = h->Pc, Pf = h->Pf, C8 = C >> 3;
@@ -337,7 +362,7 @@ upsample_bf16_kernel(const int32_t* __restrict__ plan, const void* __restrict__ 
     const long long row = i / C8;
     float o[8];
     if (i < n_main) {
-      up_pixel<F32>(src, xin, cring, row / Pf, B, Pc, (int)(row % Pf), C, c, o);
+      up_pixel<F32>(src, xin, cring, row / Pf, B, Pc, (int)(row % Pf), C, c, o, f16);
     } else {
       const long long j = row - (long long)B * Pf;
       const int pole = (int)(j & 1);
@@ -345,12 +370,12 @@ upsample_bf16_kernel(const int32_t* __restrict__ plan, const void* __restrict__ 
       for (int k = 0; k < 8; ++k) o[k] = 0.f;
       for (int e = 0; e < 5; ++e) {
         float t[8];
-        up_pixel<F32>(src, xin, cring, j >> 1, B, Pc, ring_pixel(nfine, pole, e), C, c, t);
+        up_pixel<F32>(src, xin, cring, j >> 1, B, Pc, ring_pixel(nfine, pole, e), C, c, t, f16);
 #pragma unroll
         for (int k = 0; k < 8; ++k) o[k] = fmaf(0.2f, t[k], o[k]);
       }
     }
-    st8_bf16(out + row * C + c, o);
+    st8_op(out + row * C + c, o, f16);
   }
 }
 

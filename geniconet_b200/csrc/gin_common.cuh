@@ -42,6 +42,22 @@ struct PerDeviceFlag {
   bool& here() { return done[current_device()]; }
 };
 
+// 16-bit operand formats of the tcgen05 path.  FORWARD-side operands (activation copies, forward weight tiles) are fp16 by
+// default: post-BatchNorm activations and weights are O(1), far inside fp16's range (conversions saturate to +-65504 anyway),
+// and its 10-bit mantissa leaves 1/8 of bf16's rounding noise in the network output -- which is what the normal / Laplacian
+// loss terms differentiate (profiles/r02_precision_study.md).  GRADIENT-side operands (dy copies, dgrad weight tiles) stay
+// bf16: their magnitudes span many decades.  GIN_FWD_FP16=0 switches the forward side back to bf16 (A/B experiments).
+// kind::f16 MMAs take the A and B formats independently (instruction-descriptor bits 7-9 / 10-12: 0 = fp16, 1 = bf16).
+inline bool fwd_fp16() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GIN_FWD_FP16"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+inline uint32_t& fmt_bits_ref() { static thread_local uint32_t bits = (1u << 7) | (1u << 10); return bits; }
+// set by the C-ABI entry points right before a tcgen05 launch: are the A / B operands of this launch bf16 (else fp16)?
+inline void set_operand_formats(bool a_bf16, bool b_bf16) { fmt_bits_ref() = ((uint32_t)a_bf16 << 7) | ((uint32_t)b_bf16 << 10); }
+inline uint32_t operand_format_bits() { return fmt_bits_ref(); }
+
 inline bool pdl_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("GIN_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -74,6 +90,20 @@ GIN_DEVINL __host__ size_t packed_off_wd(int Cin, int Cout) { return (size_t)28 
 GIN_DEVINL __host__ size_t packed_off_bf(int Cin, int Cout) { return (size_t)56 * Cin * Cout; }
 GIN_DEVINL __host__ size_t packed_off_bd(int Cin, int Cout) { return (size_t)70 * Cin * Cout; }
 GIN_DEVINL __host__ size_t packed_total(int Cin, int Cout) { return (size_t)84 * Cin * Cout; }
+
+// two fp32 -> one packed pair of 16-bit operands: fp16 (round to nearest, saturating to the largest finite value) or bf16
+GIN_DEVINL uint32_t pack2_f16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+GIN_DEVINL uint32_t pack2_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+GIN_DEVINL uint32_t pack2_op(float lo, float hi, int f16) { return f16 ? pack2_f16(lo, hi) : pack2_bf16(lo, hi); }
+GIN_DEVINL unsigned short cvt_op(float v, int f16) { return (unsigned short)(pack2_op(v, 0.f, f16) & 0xffffu); }
 
 GIN_DEVINL float warp_sum(float v) {
 #pragma unroll

@@ -52,6 +52,7 @@ constexpr int MAX_PLANES = 16;
 // output, each its own output tile (flush_each) gathered from the same coarse dy image.  (gin_plan.h: GinPSide / GinP2Side.)
 struct Params {
   const int32_t* plan;
+  uint32_t fmt;               // operand-format bits of the instruction descriptor (gin_common.cuh: operand_format_bits)
   int U, Q, ntiles;           // patch rows per image, octets per patch row, tiles per sample group
   int group, B, K, N;
   int P_src, P_dst;           // pixels per sample of the gathered / written map
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
     // =========================================================== MMA issuer
     // The whole warp runs this loop in lock step (addresses, descriptors and counters stay in uniform registers);
     // only the elected lane issues tcgen05.mma / tcgen05.commit.
-    constexpr uint32_t idesc = make_idesc_bf16(N_TILE);
+    const uint32_t idesc = make_idesc_f16kind(N_TILE) | p.fmt;
     const bool leader = elect_one();
     int s = 0, bs = 0;
     uint32_t ph = 0, bph = 0, wc = 0;
@@ -589,7 +590,7 @@ inline int launch_patch_conv2(const int32_t* plan_dev, const GinPSide& ps, int g
                               int* stats_parts = nullptr) {
   cv2::Params p{};
   p.stats = stats; p.stats_parts = stats_parts;
-  p.plan = plan_dev; p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P; p.P_dst = P;
+  p.plan = plan_dev; p.fmt = operand_format_bits(); p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P; p.P_dst = P;
   p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.Wt = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = bias; p.Y = Y;
   p.nplanes = 1; p.flush_each = 0; p.ntaps[0] = 7; p.group_bytes = 1280; p.dst_tab_off = -1;
   for (int t = 0; t < 7; ++t) {
@@ -614,7 +615,7 @@ inline int launch_patch_conv2_s2_fwd(const int32_t* plan_dev, const GinP2Side& p
                                      int* stats_parts = nullptr) {
   cv2::Params p{};
   p.stats = stats; p.stats_parts = stats_parts;
-  p.plan = plan_dev; p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P_f; p.P_dst = P_c;
+  p.plan = plan_dev; p.fmt = operand_format_bits(); p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P_f; p.P_dst = P_c;
   p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.Wt = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = bias; p.Y = Y;
   p.nplanes = 4; p.flush_each = 0; p.group_bytes = 1280; p.dst_tab_off = -1;
   for (int t = 0; t < 7; ++t) {
@@ -632,7 +633,7 @@ inline int launch_patch_conv2_s2_fwd(const int32_t* plan_dev, const GinP2Side& p
 inline int launch_patch_conv2_s2_dgrad(const int32_t* plan_dev, const GinP2Side& ps, int group, int P_f, int P_c, int Wf, const void* dYb,
                                        const void* Wb, float* dX, int B, int K, int N, cudaStream_t st) {
   cv2::Params p{};
-  p.plan = plan_dev; p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P_c; p.P_dst = P_f;
+  p.plan = plan_dev; p.fmt = operand_format_bits(); p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P_c; p.P_dst = P_f;
   p.X = reinterpret_cast<const __nv_bfloat16*>(dYb); p.Wt = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = nullptr; p.Y = dX;
   p.nplanes = 4; p.flush_each = 1; p.group_bytes = 1280; p.dst_tab_off = -1;
   for (int t = 0; t < 7; ++t) {
@@ -655,7 +656,7 @@ inline bool cv2_seam_supported(const GinPxSide& px, int K, int N) {
 inline int launch_patch_conv2_seam(const int32_t* plan_dev, const GinPxSide& px, int group, int P_src, int P_dst, const void* dYb, const void* Wb,
                                    float* dX, int B, int K, int N, cudaStream_t st) {
   cv2::Params p{};
-  p.plan = plan_dev; p.U = GIN_TILE_M; p.Q = 1; p.ntiles = px.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P_src; p.P_dst = P_dst;
+  p.plan = plan_dev; p.fmt = operand_format_bits(); p.U = GIN_TILE_M; p.Q = 1; p.ntiles = px.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P_src; p.P_dst = P_dst;
   p.X = reinterpret_cast<const __nv_bfloat16*>(dYb); p.Wt = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = nullptr; p.Y = dX;
   p.nplanes = px.nslots; p.flush_each = 0; p.group_bytes = 1024; p.accumulate = 1; p.dst_tab_off = px.dst_off;
   for (int s = 0; s < px.nslots; ++s) { p.ntaps[s] = 1; p.tap_id[s][0] = px.tap[s]; p.tap_row[s][0] = 0; }

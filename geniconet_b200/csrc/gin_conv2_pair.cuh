@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_pair_kernel(const Para
       }
   } else if (warp == W_MMA) {
     // =========================================================== MMA issuer: every weight tile is applied to both tiles of the pair
-    constexpr uint32_t idesc = make_idesc_bf16(N_TILE);
+    const uint32_t idesc = make_idesc_f16kind(N_TILE) | p.fmt;
     const bool leader = elect_one();
     int s = 0, bs = 0;
     uint32_t ph = 0, bph = 0, wc = 0;

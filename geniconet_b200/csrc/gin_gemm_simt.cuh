@@ -279,15 +279,15 @@ bias_grad_kernel(const float* __restrict__ dY, float* __restrict__ db, long long
 
 // weight [Cout][Cin][7] -> wf[7][Cin][Cout], wd[7][Cout][Cin] (fp32) and bf16 K-major copies
 __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ wf, float* __restrict__ wd,
-                                    unsigned short* __restrict__ bf, unsigned short* __restrict__ bd, int Cin, int Cout) {
+                                    unsigned short* __restrict__ bf, unsigned short* __restrict__ bd, int Cin, int Cout, int fwd_f16) {
   const long long n = (long long)Cin * Cout * 7;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     int t = (int)(i % 7);
     long long r = i / 7;
     int ci = (int)(r % Cin), co = (int)(r / Cin);
     float v = w[i];
-    unsigned int u = __float_as_uint(v);
-    unsigned short h = (unsigned short)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);  // round-to-nearest-even bf16
+    const unsigned short h = cvt_op(v, 0);                      // dgrad tiles: bf16
+    const unsigned short hf = cvt_op(v, fwd_f16);               // forward tiles: the forward operand format
     wf[((size_t)t * Cin + ci) * Cout + co] = v;
     wd[((size_t)t * Cout + co) * Cin + ci] = v;
     // tcgen05 B operand tiles, stored exactly as the smem image: [tap][k/64][n][64] with the 16-byte chunk index
@@ -295,7 +295,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
     if ((Cin & 63) == 0 && (Cout & 63) == 0) {
       {  // forward: n = co, k = ci
         const int kc = ci >> 6, c = (ci >> 3) & 7, e = ci & 7;
-        bf[((((size_t)t * (Cin >> 6) + kc) * Cout + co) << 6) + (((c ^ (co & 7)) << 3) | e)] = h;
+        bf[((((size_t)t * (Cin >> 6) + kc) * Cout + co) << 6) + (((c ^ (co & 7)) << 3) | e)] = hf;
       }
       {  // dgrad: n = ci, k = co
         const int kc = co >> 6, c = (co >> 3) & 7, e = co & 7;
@@ -308,7 +308,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
 // Only the tcgen05 tile images (see pack_weights_kernel) of the weight [w0; w1] concatenated along Cout -- what the fused
 // chains need: two sibling convolutions become one GEMM without materialising the concatenation.
 __global__ void pack_weights_bf16_kernel(const float* __restrict__ w0, int Cout0, const float* __restrict__ w1, unsigned short* __restrict__ bf,
-                                         unsigned short* __restrict__ bd, int Cin, int Cout) {
+                                         unsigned short* __restrict__ bd, int Cin, int Cout, int fwd_f16) {
   GIN_PDL_SYNC();
   const long long n = (long long)Cin * Cout * 7;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -316,11 +316,10 @@ __global__ void pack_weights_bf16_kernel(const float* __restrict__ w0, int Cout0
     const long long r = i / 7;
     const int ci = (int)(r % Cin), co = (int)(r / Cin);
     const float v = co < Cout0 ? w0[i] : w1[i - (long long)Cout0 * Cin * 7];
-    const unsigned int u = __float_as_uint(v);
-    const unsigned short h = (unsigned short)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
+    const unsigned short h = cvt_op(v, 0), hf = cvt_op(v, fwd_f16);
     {
       const int kc = ci >> 6, c = (ci >> 3) & 7, e = ci & 7;
-      bf[((((size_t)t * (Cin >> 6) + kc) * Cout + co) << 6) + (((c ^ (co & 7)) << 3) | e)] = h;
+      bf[((((size_t)t * (Cin >> 6) + kc) * Cout + co) << 6) + (((c ^ (co & 7)) << 3) | e)] = hf;
     }
     {
       const int kc = co >> 6, c = (co >> 3) & 7, e = co & 7;

@@ -118,10 +118,14 @@ GIN_DEVINL uint64_t make_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: bf16 x bf16 -> f32, both operands K-major, M = 128
+// kind::f16 instruction descriptor WITHOUT the operand-format bits (those come from Params::fmt, see gin_common.cuh
+// operand_format_bits): D = f32, M = 128, operands K-major unless flagged
+__host__ __device__ constexpr uint32_t make_idesc_f16kind(int n, int a_mn_major = 0, int b_mn_major = 0) {
+  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+// bf16 x bf16 (experiments under tools/exp)
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int n, int a_mn_major = 0, int b_mn_major = 0) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  return make_idesc_f16kind(n, a_mn_major, b_mn_major) | (1u << 7) | (1u << 10);
 }
 
 GIN_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
@@ -165,6 +169,7 @@ GIN_DEVINL int resolve_row(int code, long long base, long long total_pix, int sa
 
 struct Params {
   const int32_t* plan;
+  uint32_t fmt;               // operand-format bits of the instruction descriptor (gin_common.cuh: operand_format_bits)
   GinSide side;
   int group, B, K, N;
   const __nv_bfloat16* X;    // [B*P_src + 2B][K] bf16 (pixels, then pole-mean rows)
@@ -288,7 +293,7 @@ __global__ void __launch_bounds__(THREADS2, (N_TILE <= 128 ? 2 : 1)) gather_gemm
     tc_fence_before();
   } else if (warp == PRODUCER_WARPS) {
     // =========================================================== MMA issuer (one elected thread)
-    constexpr uint32_t idesc = make_idesc_bf16(N_TILE);
+    const uint32_t idesc = make_idesc_f16kind(N_TILE) | p.fmt;
     if (lane == 0) {
       for (int it = 0; it < total_stages; ++it) {
         const int s = it % STAGES;
@@ -351,7 +356,7 @@ inline bool tc_supported(int K, int N) { return K % 64 == 0 && N % 64 == 0 && K 
 inline int launch_gather_gemm_tc(const int32_t* plan_dev, const GinSide& side, int group, const void* Xb, const void* Wb,
                                  const float* bias, float* Y, int B, int K, int N, int ntiles, cudaStream_t st, int accumulate = 0) {
   tc::Params p;
-  p.plan = plan_dev; p.side = side; p.group = group; p.B = B; p.K = K; p.N = N;
+  p.plan = plan_dev; p.fmt = operand_format_bits(); p.side = side; p.group = group; p.B = B; p.K = K; p.N = N;
   p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.W = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = bias; p.Y = Y;
   p.accumulate = accumulate;
   if ((long long)B * side.P_src + 2LL * B >= 0x7fffffffLL) return -4;
@@ -374,6 +379,7 @@ using namespace tc;
 
 struct Params {
   const int32_t* plan;
+  uint32_t fmt;               // operand-format bits of the instruction descriptor (gin_common.cuh: operand_format_bits)
   GinSide side;
   int group, B, Cin, Cout;
   const __nv_bfloat16* X;     // [B*P_src + 2B][Cin]
@@ -536,7 +542,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const Params p) {
     }
     tc_fence_before();
   } else {
-    constexpr uint32_t idesc = make_idesc_bf16(N_BLK, 1, 1);
+    const uint32_t idesc = make_idesc_f16kind(N_BLK, 1, 1) | p.fmt;
     if (lane == 0) {
       uint32_t it = 0;
       for (int ti = 0; ti < ntile; ++ti) {
@@ -598,7 +604,7 @@ inline bool tc_wgrad_supported(int Cin, int Cout) { return Cin % 64 == 0 && Cout
 inline int launch_wgrad_tc(const int32_t* plan_dev, const GinSide& side, int group, const void* Xb, const void* dYb, float* dWp,
                            int B, int Cin, int Cout, int total_tiles, cudaStream_t st) {
   tcw::Params p;
-  p.plan = plan_dev; p.side = side; p.group = group; p.B = B; p.Cin = Cin; p.Cout = Cout;
+  p.plan = plan_dev; p.fmt = operand_format_bits(); p.side = side; p.group = group; p.B = B; p.Cin = Cin; p.Cout = Cout;
   p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.dY = reinterpret_cast<const __nv_bfloat16*>(dYb); p.dWp = dWp;
   p.total_tiles = total_tiles; p.tiles_per_cta = 1; p.units_m = 1;
   if ((long long)B * side.P_src + 2LL * B >= 0x7fffffffLL) return -4;

@@ -28,6 +28,7 @@ constexpr int MAX_ITEMS = 8;                     // source rows per producer thr
 
 struct Params {
   const int32_t* plan;
+  uint32_t fmt;               // operand-format bits of the instruction descriptor (gin_common.cuh: operand_format_bits)
   GinPSide ps;
   int group, B, K, N, P;      // P = pixels per sample (stride 1: same on both sides)
   const __nv_bfloat16* X;     // [B*P + 2B][K] bf16 (pixels, then pole-mean rows)
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_gemm_tc_kernel(const Params
     }
   } else if (warp == PRODUCER_WARPS) {
     // =========================================================== MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(N_TILE);
+    const uint32_t idesc = make_idesc_f16kind(N_TILE) | p.fmt;
     if (lane == 0) {
       uint32_t ac = 0, bc = 0, wc = 0;
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++wc) {
@@ -243,7 +244,7 @@ inline bool tcp_supported(const GinPSide& ps, int K, int N) {
 inline int launch_patch_gemm_tc(const int32_t* plan_dev, const GinPSide& ps, int group, int P, const void* Xb, const void* Wb,
                                 const float* bias, float* Y, int B, int K, int N, int mirror, cudaStream_t st) {
   tcp::Params p;
-  p.plan = plan_dev; p.ps = ps; p.group = group; p.B = B; p.K = K; p.N = N; p.P = P;
+  p.plan = plan_dev; p.fmt = operand_format_bits(); p.ps = ps; p.group = group; p.B = B; p.K = K; p.N = N; p.P = P;
   p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.W = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = bias; p.Y = Y; p.mirror = mirror;
   if ((long long)B * P + 2LL * B >= 0x7fffffffLL) return -4;
   const int groups = (B + group - 1) / group;

@@ -71,10 +71,10 @@ upsample_bwd_kernel(const int32_t* __restrict__ plan, const float* __restrict__ 
   }
 }
 
-// fp32 [B*P][C] -> bf16 [B*P + 2B][C].  The 2B extra rows are the per-sample pole means (mean of the pole's five ring
+// fp32 [B*P][C] -> 16-bit operand copy [B*P + 2B][C] (f16 != 0: fp16, else bf16; gin_common.cuh).  The 2B extra rows are the per-sample pole means (mean of the pole's five ring
 // pixels), so that the tcgen05 producers can fetch a pole cell like any other row.  One thread = 8 channels.
 __global__ void __launch_bounds__(256)
-cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, const int32_t* __restrict__ ring, int B, int P, int C) {
+cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, const int32_t* __restrict__ ring, int B, int P, int C, int f16) {
   const int C8 = C >> 3;
   const long long n_main = (long long)B * P * C8, n_all = n_main + 2LL * B * C8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_all; i += (long long)gridDim.x * blockDim.x) {
@@ -94,11 +94,8 @@ cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, co
         b = fma4(0.2f, ld4(src + 4), b);
       }
     }
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
-    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
     uint4 o;
-    o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
-    o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+    o.x = pack2_op(a.x, a.y, f16); o.y = pack2_op(a.z, a.w, f16); o.z = pack2_op(b.x, b.y, f16); o.w = pack2_op(b.z, b.w, f16);
     *reinterpret_cast<uint4*>(xb + i * 8) = o;
   }
 }
@@ -112,7 +109,7 @@ constexpr int CAST_COLSUM_MAX_CTAS = 148 * 2;
 
 __global__ void __launch_bounds__(256)
 cast_bf16_colsum_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, const int32_t* __restrict__ ring, int B, int P, int C,
-                        float* __restrict__ ws) {
+                        float* __restrict__ ws, int f16) {
   __shared__ float part[256][9];
   const int C8 = C >> 3;
   const long long n_main = (long long)B * P * C8, n_all = n_main + 2LL * B * C8;
@@ -135,11 +132,8 @@ cast_bf16_colsum_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__
         b = fma4(0.2f, ld4(src + 4), b);
       }
     }
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
-    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
     uint4 o;
-    o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
-    o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+    o.x = pack2_op(a.x, a.y, f16); o.y = pack2_op(a.z, a.w, f16); o.z = pack2_op(b.x, b.y, f16); o.w = pack2_op(b.z, b.w, f16);
     *reinterpret_cast<uint4*>(xb + i * 8) = o;
   }
   // channel group of this thread: (threadIdx.x % C8) because C8 | 256 | grid stride

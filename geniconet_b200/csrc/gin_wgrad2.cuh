@@ -36,6 +36,7 @@ constexpr int MAX_CTAS = kMaxSMs;
 // parity plane of the fine input and ONE tap pair per plane (taps {1,2} {5,6} {0,0} {3,4}); either way four accumulators.
 struct Params {
   const int32_t* plan;
+  uint32_t fmt;               // operand-format bits of the instruction descriptor (gin_common.cuh: operand_format_bits)
   int U, Q, ntiles;
   int group, B, Cin, Cout;
   int P_src, P_dst;            // pixels per sample of the x map / of the dy map
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_patch_kernel(const Params p
     tc_fence_before();
   } else if (warp == W_MMA) {
     // =========================================================== MMA issuer (warp-uniform loop, one elected lane issues)
-    constexpr uint32_t idesc = make_idesc_bf16(N_BLK, 1, 1);
+    const uint32_t idesc = make_idesc_f16kind(N_BLK, 1, 1) | p.fmt;
     const bool leader = elect_one();
     int s = 0;
     uint32_t ph = 0;
@@ -340,7 +341,7 @@ inline int launch_wgrad_patch2(const int32_t* plan_dev, const GinPSide& ps, int 
                                float* dW, int B, int Cin, int Cout, cudaStream_t st) {
   static const int pairs[4][2] = {{1, 5}, {3, 0}, {4, 6}, {2, 2}};
   wg2::Params p{};
-  p.plan = plan_dev; p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.Cin = Cin; p.Cout = Cout; p.P_src = P; p.P_dst = P;
+  p.plan = plan_dev; p.fmt = operand_format_bits(); p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.Cin = Cin; p.Cout = Cout; p.P_src = P; p.P_dst = P;
   p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.dY = reinterpret_cast<const __nv_bfloat16*>(dYb); p.partial = partial;
   p.nplanes = 1; p.npairs[0] = 4;
   for (int j = 0; j < 4; ++j) {
@@ -359,7 +360,7 @@ inline int launch_wgrad_patch2_s2(const int32_t* plan_dev, const GinP2Side& ps, 
                                   float* partial, float* dW, int B, int Cin, int Cout, cudaStream_t st) {
   static const int pairs[4][2] = {{1, 2}, {5, 6}, {0, 0}, {3, 4}};
   wg2::Params p{};
-  p.plan = plan_dev; p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.Cin = Cin; p.Cout = Cout; p.P_src = P_f; p.P_dst = P_c;
+  p.plan = plan_dev; p.fmt = operand_format_bits(); p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.Cin = Cin; p.Cout = Cout; p.P_src = P_f; p.P_dst = P_c;
   p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.dY = reinterpret_cast<const __nv_bfloat16*>(dYb); p.partial = partial;
   p.nplanes = 4;
   for (int pl = 0; pl < 4; ++pl) {

@@ -23,6 +23,7 @@ constexpr int MAX_ITEMS = tcp::MAX_ITEMS;
 
 struct Params {
   const int32_t* plan;
+  uint32_t fmt;               // operand-format bits of the instruction descriptor (gin_common.cuh: operand_format_bits)
   GinPSide ps;
   int group, B, Cin, Cout, P;
   const __nv_bfloat16* X;      // [B*P + 2B][Cin] bf16
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_patch_tc_kernel(const Params
     }
     tc_fence_before();
   } else {
-    constexpr uint32_t idesc = make_idesc_bf16(N_BLK, 1, 1);
+    const uint32_t idesc = make_idesc_f16kind(N_BLK, 1, 1) | p.fmt;
     if (lane == 0) {
       for (int ti = 0; ti < ntile; ++ti) {
         const int s = ti & 1;
@@ -213,7 +214,7 @@ inline bool tcwp_supported(const GinPSide& ps, int Cin, int Cout) { return tcp_s
 inline int launch_wgrad_patch_tc(const int32_t* plan_dev, const GinPSide& ps, int group, int P, const void* Xb, const void* dYb,
                                  float* dWp, int B, int Cin, int Cout, cudaStream_t st) {
   tcwp::Params p;
-  p.plan = plan_dev; p.ps = ps; p.group = group; p.B = B; p.Cin = Cin; p.Cout = Cout; p.P = P;
+  p.plan = plan_dev; p.fmt = operand_format_bits(); p.ps = ps; p.group = group; p.B = B; p.Cin = Cin; p.Cout = Cout; p.P = P;
   p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.dY = reinterpret_cast<const __nv_bfloat16*>(dYb); p.dWp = dWp;
   const int groups = (B + group - 1) / group;
   p.total_tiles = groups * ps.ntiles;

@@ -50,6 +50,9 @@ enum { GIN_IMPL_AUTO = 0, GIN_IMPL_SIMT = 1, GIN_IMPL_TC = 2 };
 enum { GIN_CORNER_ZEROS = 0, GIN_CORNER_AVERAGE = 1 };
 
 int gin_version(void);
+/* 1: forward-side 16-bit operands (activation copies, forward weight tiles) are fp16 (default), 0: bf16 (GIN_FWD_FP16=0).
+ * Gradient-side operands are always bf16.  A checker needs this to round its operands the same way. */
+int gin_forward_operand_is_fp16(void);
 const char* gin_last_error(void);
 
 /* ------------------------------------------------------------------ host: geometry -- */

@@ -5,14 +5,16 @@ from oracle import icocnn_ref
 from geniconet_b200.ico_conv import IcoConvS2S
 cin, cout, stride, level, B = [int(a) for a in sys.argv[1:6]]
 torch.manual_seed(2)
+from geniconet_b200 import _lib
+FWD = _lib.forward_operand_dtype()                       # forward-side operands: fp16 (default) or bf16; gradient side: bf16
 ref = icocnn_ref.IcoConvS2S(cin, cout, stride, True, level, 'average')
 with torch.no_grad():
-    ref.weight.copy_(ref.weight.to(torch.bfloat16).float())
+    ref.weight.copy_(ref.weight.to(torch.float16).to(torch.bfloat16).float())      # exactly representable in both formats
 mod = IcoConvS2S(cin, cout, stride, True, level, 'average', impl='tc').cuda()
 mod.load_state_dict(ref.state_dict())
 n = 2 ** level
 g = torch.Generator().manual_seed(9)
-x = torch.randn(B, cin, 5 * n, 2 * n, generator=g).to(torch.bfloat16).float()
+x = torch.randn(B, cin, 5 * n, 2 * n, generator=g).to(FWD).float()
 xr = x.clone().requires_grad_(True)
 yr = ref(xr); gy = torch.randn(yr.shape, generator=g).to(torch.bfloat16).float(); yr.backward(gy)
 xc = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)

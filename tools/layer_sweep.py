@@ -57,7 +57,7 @@ def main():
                     packed = torch.empty(L.gin_hexconv_packed_bytes(ci, co), dtype=torch.uint8, device='cuda')
                     st = [torch.cuda.current_stream().cuda_stream]
                     _lib.check(L.gin_hexconv_pack_weights(w.data_ptr(), packed.data_ptr(), ci, co, st[0]))
-                    xb = (torch.randn(B * Pin + 2 * B, ci, device='cuda') * 0.5).to(torch.bfloat16)
+                    xb = (torch.randn(B * Pin + 2 * B, ci, device='cuda') * 0.5).to(_lib.forward_operand_dtype())
                     dyb = (torch.randn(B * Pout + 2 * B, co, device='cuda') * 0.5).to(torch.bfloat16)
                     y = torch.empty(B * Pout, co, device='cuda')
                     dx = torch.empty(B * Pin, ci, device='cuda')

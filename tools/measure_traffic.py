@@ -25,7 +25,7 @@ for name, ci, co, stride, lvl, cm, count in bench.conv_calls(model, True):
     packed = torch.empty(L.gin_hexconv_packed_bytes(ci, co), dtype=torch.uint8, device='cuda')
     st = torch.cuda.current_stream().cuda_stream
     _lib.check(L.gin_hexconv_pack_weights(w.data_ptr(), packed.data_ptr(), ci, co, st))
-    xb = (torch.randn(B * Pin + 2 * B, ci, device='cuda') * 0.5).to(torch.bfloat16)
+    xb = (torch.randn(B * Pin + 2 * B, ci, device='cuda') * 0.5).to(_lib.forward_operand_dtype())
     y = torch.empty(B * Pout, co, device='cuda')
     flush = torch.empty(64 << 20, dtype=torch.float32, device='cuda')
     for _ in range(count):
