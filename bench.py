@@ -455,7 +455,7 @@ def run_ours(args):
         meshes = B * world
         line = {'metric': 'train_meshes_per_sec', 'value': meshes / (ms_step * 1e-3), 'unit': 'meshes/s', 'n_gpus': world,
                 'steps': args.steps, 'warmup': W, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
-                'vs_baseline': None, 'dtype': 'bf16 operands / f32 accumulate (tcgen05); f32 activations, BN, loss, Adam',
+                'vs_baseline': None, 'dtype': '%s forward operands, bf16 gradient operands, f32 accumulate (tcgen05 kind::f16); f32 activations, BN, loss, Adam' % ('fp16' if _lib.lib.gin_forward_operand_is_fp16() else 'bf16'),
                 'data': 'synthetic',
                 'config': workload_config(args.model, args.level, B),
                 'details': {'conv_impl': args.conv_impl, 'parallelism': 'dp%d' % world,

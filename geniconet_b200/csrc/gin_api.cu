@@ -253,7 +253,7 @@ static int wgrad_common(const GinConvPlanHdr* h, const void* plan_dev, const flo
                         int impl = GIN_IMPL_SIMT) {
   float* dWp = reinterpret_cast<float*>(ws);
   int rc;
-  gin::set_operand_formats(!gin::fwd_fp16(), true);        // wgrad: A = the forward activation copy, B = the bf16 dy copy
+  gin::set_operand_formats(true, true);                    // wgrad: A = the bf16 twin of the forward activation copy, B = the bf16 dy copy
   const bool wg2_s1 = h->stride == 1 && gin::wg2_supported(h->pfwd, Cin, Cout), wg2_s2 = h->stride == 2 && gin::wg2_supported(h->p2, Cin, Cout);
   if (xb && B > 0 && tc_mode() == 2 && (wg2_s1 || wg2_s2)) {
     // second-generation patch wgrad: split-K partials in the workspace, reduced (and laid out as dW[Cout][Cin][7]) by a second kernel
@@ -340,12 +340,12 @@ size_t gin_cast_bf16_bytes(int B, int level, int C) {
 
 int gin_cast_bf16(const void* plan_host, const void* plan_dev, int which, const float* x, void* xb, int B, int C, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (!x || !xb || B < 0 || C <= 0 || (C & 7) || (which != 0 && which != 1)) return fail(GIN_ERR_ARG, "gin_cast_bf16: bad argument (C must be a multiple of 8)");
+  if (!x || !xb || B < 0 || C <= 0 || (C & 7) || which < 0 || which > 2) return fail(GIN_ERR_ARG, "gin_cast_bf16: bad argument (C must be a multiple of 8)");
   const GinConvPlanHdr* h;
   int rc = conv_hdr(plan_host, plan_dev, &h);
   if (rc) return rc;
   if (B == 0) return GIN_OK;
-  const GinSide& side = which == 0 ? h->fwd : h->dg;      // the gathered tensor of the forward / of dgrad
+  const GinSide& side = which != 1 ? h->fwd : h->dg;      // the gathered tensor of the forward / of dgrad
   const long long n8 = (long long)B * side.P_src * (C / 8) + 2LL * B * (C / 8);
   gin::cast_bf16_kernel<<<grid_for(n8, 256, 16), 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(xb), plan_words(plan_dev) + side.ring_off,
                                                                 B, side.P_src, C, (int)(which == 0 && gin::fwd_fp16()));
@@ -582,16 +582,16 @@ int gin_bn_stats_from_parts(const float* parts, int nparts, int64_t ld, int64_t 
 }
 
 int gin_bn_act_fwd(const float* y1, int64_t ld1, const float* stat1, const float* y2, int64_t ld2, const float* stat2, int relu, void* out_b,
-                   float* out_f, int B, int level, int C, void* stream) {
+                   float* out_f, void* out_w, int B, int level, int C, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (!y1 || !stat1 || (y2 && !stat2) || (!out_b && !out_f) || B <= 0 || level < 0 || level > 9 || !bn_shape_ok(C))
+  if (!y1 || !stat1 || (y2 && !stat2) || (!out_b && !out_f && !out_w) || B <= 0 || level < 0 || level > 9 || !bn_shape_ok(C))
     return fail(GIN_ERR_ARG, "gin_bn_act_fwd: bad argument");
   const int n = 1 << level, P = 10 << (2 * level);
   const int ctas = gin::bn::grid_for_rows(((long long)B * P + 2LL * B) * (C >> 3));
   const gin::bn::Src s1{y1, (long long)ld1}, s2{y2, (long long)ld2};
   const int f16 = (int)gin::fwd_fp16();          // out_b is the next convolution's FORWARD operand copy
-  if (y2) gin::launch_pdl(gin::bn::act_fwd_kernel<true>, dim3(ctas), dim3(256), 0, st, s1, stat1, s2, stat2, relu, reinterpret_cast<__nv_bfloat16*>(out_b), out_f, n, B, P, C, f16);
-  else gin::launch_pdl(gin::bn::act_fwd_kernel<false>, dim3(ctas), dim3(256), 0, st, s1, stat1, s2, stat2, relu, reinterpret_cast<__nv_bfloat16*>(out_b), out_f, n, B, P, C, f16);
+  if (y2) gin::launch_pdl(gin::bn::act_fwd_kernel<true>, dim3(ctas), dim3(256), 0, st, s1, stat1, s2, stat2, relu, reinterpret_cast<__nv_bfloat16*>(out_b), out_f, n, B, P, C, f16, reinterpret_cast<__nv_bfloat16*>(out_w));
+  else gin::launch_pdl(gin::bn::act_fwd_kernel<false>, dim3(ctas), dim3(256), 0, st, s1, stat1, s2, stat2, relu, reinterpret_cast<__nv_bfloat16*>(out_b), out_f, n, B, P, C, f16, reinterpret_cast<__nv_bfloat16*>(out_w));
   return check_launch("bn_act_fwd");
 }
 
@@ -639,7 +639,7 @@ int gin_bn_act_bwd_pair(const float* dout, int64_t ldg, const void* mask_b, cons
 
 static int up_hdr(const void* plan_host, const void* plan_dev, const GinUpPlanHdr** out);
 
-int gin_upsample_bf16(const void* plan_host, const void* plan_dev, const void* in, int in_is_f32, void* out_b, int B, int C, void* stream) {
+int gin_upsample_bf16(const void* plan_host, const void* plan_dev, const void* in, int in_is_f32, void* out_b, void* out_w, int B, int C, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (!in || !out_b || B <= 0 || C <= 0 || (C & 7)) return fail(GIN_ERR_ARG, "gin_upsample_bf16: bad argument (C must be a multiple of 8)");
   const GinUpPlanHdr* h;
@@ -648,8 +648,8 @@ int gin_upsample_bf16(const void* plan_host, const void* plan_dev, const void* i
   const int ctas = gin::bn::grid_for_rows(((long long)B * h->Pf + 2LL * B) * (C >> 3));
   const int grid = ctas * 4 > 148 * 8 ? 148 * 8 : ctas * 4;
   const int f16 = (int)gin::fwd_fp16();          // both the source copy (when 16-bit) and the result are forward operands
-  if (in_is_f32) gin::launch_pdl(gin::bn::upsample_bf16_kernel<true>, dim3(grid), dim3(256), 0, st, plan_words(plan_dev), in, reinterpret_cast<__nv_bfloat16*>(out_b), 2 << h->level, B, C, f16);
-  else gin::launch_pdl(gin::bn::upsample_bf16_kernel<false>, dim3(grid), dim3(256), 0, st, plan_words(plan_dev), in, reinterpret_cast<__nv_bfloat16*>(out_b), 2 << h->level, B, C, f16);
+  if (in_is_f32) gin::launch_pdl(gin::bn::upsample_bf16_kernel<true>, dim3(grid), dim3(256), 0, st, plan_words(plan_dev), in, reinterpret_cast<__nv_bfloat16*>(out_b), 2 << h->level, B, C, f16, reinterpret_cast<__nv_bfloat16*>(out_w));
+  else gin::launch_pdl(gin::bn::upsample_bf16_kernel<false>, dim3(grid), dim3(256), 0, st, plan_words(plan_dev), in, reinterpret_cast<__nv_bfloat16*>(out_b), 2 << h->level, B, C, f16, reinterpret_cast<__nv_bfloat16*>(out_w));
   return check_launch("upsample_bf16");
 }
 

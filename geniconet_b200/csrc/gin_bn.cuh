@@ -193,7 +193,7 @@ GIN_DEVINL void apply_row(const Src& y1, const Src& y2, long long r, int c, cons
 template <bool TWO>
 __global__ void __launch_bounds__(256)
 act_fwd_kernel(Src y1, const float* __restrict__ stat1, Src y2, const float* __restrict__ stat2, int relu, __nv_bfloat16* __restrict__ out_b,
-               float* __restrict__ out_f, int nlat, int B, int P, int C, int f16) {
+               float* __restrict__ out_f, int nlat, int B, int P, int C, int f16, __nv_bfloat16* __restrict__ out_w) {
   GIN_PDL_SYNC();
   const int C8 = C >> 3;
   const long long rows = (long long)B * P, n_main = rows * C8, n_all = n_main + 2LL * B * C8;
@@ -220,6 +220,7 @@ act_fwd_kernel(Src y1, const float* __restrict__ stat1, Src y2, const float* __r
       }
     }
     if (out_b) st8_op(out_b + (i / C8) * C + c, o, f16);
+    if (out_w) st8_op(out_w + (i / C8) * C + c, o, 0);          // the bf16 twin wgrad reads (and the ReLU mask of the backward)
   }
 }
 
@@ -350,7 +351,8 @@ GIN_DEVINL void up_pixel(const int32_t* __restrict__ src, const void* __restrict
 }
 template <bool F32>
 __global__ void __launch_bounds__(256)
-upsample_bf16_kernel(const int32_t* __restrict__ plan, const void* __restrict__ xin, __nv_bfloat16* __restrict__ out, int nfine, int B, int C, int f16) {
+upsample_bf16_kernel(const int32_t* __restrict__ plan, const void* __restrict__ xin, __nv_bfloat16* __restrict__ out, int nfine, int B, int C, int f16,
+                     __nv_bfloat16* __restrict__ out_w) {
   GIN_PDL_SYNC();
   const GinUpPlanHdr* h = reinterpret_cast<const GinUpPlanHdr*>(plan);
   const int Pc = h->Pc, Pf = h->Pf, C8 = C >> 3;
@@ -376,6 +378,7 @@ upsample_bf16_kernel(const int32_t* __restrict__ plan, const void* __restrict__ 
       }
     }
     st8_op(out + row * C + c, o, f16);
+    if (out_w) st8_op(out_w + row * C + c, o, 0);
   }
 }
 

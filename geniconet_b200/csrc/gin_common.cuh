@@ -47,7 +47,10 @@ struct PerDeviceFlag {
 // and its 10-bit mantissa leaves 1/8 of bf16's rounding noise in the network output -- which is what the normal / Laplacian
 // loss terms differentiate (profiles/r02_precision_study.md).  GRADIENT-side operands (dy copies, dgrad weight tiles) stay
 // bf16: their magnitudes span many decades.  GIN_FWD_FP16=0 switches the forward side back to bf16 (A/B experiments).
-// kind::f16 MMAs take the A and B formats independently (instruction-descriptor bits 7-9 / 10-12: 0 = fp16, 1 = bf16).
+// The instruction descriptor carries the A and B formats separately (bits 7-9 / 10-12: 0 = fp16, 1 = bf16), but a kind::f16 MMA
+// whose two operands differ in format traps as an illegal instruction on sm_100a (measured, r02).  wgrad multiplies a forward
+// activation by a gradient, so every forward activation copy is ALSO written in bf16 by its producer (2 more bytes per element);
+// wgrad sums over ~10^5 pixels, so the rounding of that copy averages out -- the forward pass is where the mantissa matters.
 inline bool fwd_fp16() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("GIN_FWD_FP16"); v = (e && e[0] == '0') ? 0 : 1; }

@@ -171,14 +171,23 @@ def _bn_stats(y, col0, ld, rows, C, bn, parts=None):
     return stat
 
 
-def _bn_act(y1, col1, ld1, stat1, y2, col2, ld2, stat2, B, level, C, want_b=True, want_f=False):
+_DUAL = bool(L.gin_forward_operand_is_fp16())        # forward operands fp16: every activation copy also exists in bf16 for wgrad
+
+
+def _bn_act(y1, col1, ld1, stat1, y2, col2, ld2, stat2, B, level, C, want_b=True, want_f=False, want_w=True):
+    """Returns (out_b: the next conv's forward operand copy, out_f: fp32 map, out_w: its bf16 twin = wgrad operand and ReLU mask;
+    out_w is out_b itself when the forward format is bf16).  16-bit copies are allocated as torch.bfloat16 containers."""
     dev = y1.device
     out_b = _empty(((B * _P(level) + 2 * B), C), torch.bfloat16, dev) if want_b else None
     out_f = _empty((B * _P(level), C), torch.float32, dev) if want_f else None
+    out_w = _empty(((B * _P(level) + 2 * B), C), torch.bfloat16, dev) if (want_w and (_DUAL or not want_b)) else None
     _lib.check(L.gin_bn_act_fwd(y1.data_ptr() + 4 * col1, ld1, stat1.data_ptr(),
                                 (y2.data_ptr() + 4 * col2) if y2 is not None else None, ld2, stat2.data_ptr() if stat2 is not None else None, 1,
-                                out_b.data_ptr() if want_b else None, out_f.data_ptr() if want_f else None, B, level, C, _stream()), 'gin_bn_act_fwd')
-    return out_b, out_f
+                                out_b.data_ptr() if want_b else None, out_f.data_ptr() if want_f else None,
+                                out_w.data_ptr() if out_w is not None else None, B, level, C, _stream()), 'gin_bn_act_fwd')
+    if want_w and out_w is None:
+        out_w = out_b
+    return out_b, out_f, out_w
 
 
 def _bn_bwd(dout, mask_b, y, col0, ld, stat, B, level, C, dy_b=None, dy_b_col=0, ldo=0, want_f=False):
@@ -213,8 +222,8 @@ class _Chain(torch.autograd.Function):
             _lib.check(L.gin_hexconv_fwd(plan.host_ptr, plan.dev_ptr, xs.data_ptr(), sb, sp, sc, packed.data_ptr(), conv.bias.data_ptr(),
                                          y.data_ptr(), B, 3, C, _lib.IMPL_AUTO, _stream()), 'gin_hexconv_fwd')
             stat = _bn_stats(y, 0, C, B * _P(level), C, bn)
-            act_b, _ = _bn_act(y, 0, C, stat, None, 0, 0, None, B, level, C)
-            saved.append(dict(kind='stem', plan=plan, xs=xs, strides=(sb, sp, sc), y=y, stat=stat, out_b=act_b, C=C, level=level, packed=packed))
+            act_b, _, act_w = _bn_act(y, 0, C, stat, None, 0, 0, None, B, level, C)
+            saved.append(dict(kind='stem', plan=plan, xs=xs, strides=(sb, sp, sc), y=y, stat=stat, out_b=act_w, C=C, level=level, packed=packed))
             i = 3
         else:                                                                # ---- chain starts on an fp32 map: make the operand copy
             blk = mods[0]
@@ -222,6 +231,7 @@ class _Chain(torch.autograd.Function):
             plan = get_plan(_lib.PLAN_HEXCONV, level, 1, blk.conv00.corner_mode, dev)
             from .ico_conv import as_channels_last, cast_bf16
             act_b = cast_bf16(as_channels_last(x), plan, 0, level)
+            act_w = cast_bf16(as_channels_last(x), plan, 2, level) if _DUAL else act_b
             saved.append(dict(kind='input', level=level, C=C))
         ctx.in_shape = tuple(x.shape)
         act_f = None
@@ -238,14 +248,16 @@ class _Chain(torch.autograd.Function):
             if blk._down:
                 lvl = level - 1
                 plan_a = get_plan(_lib.PLAN_HEXCONV, level, 2, cm, dev)
-                a_b = act_b
+                a_b, a_w = act_b, act_w
             else:
                 lvl = level + 1
                 up_plan = get_plan(_lib.PLAN_UPSAMPLE, level, 1, blk.upsample00.corner_mode, dev)
                 plan_a = get_plan(_lib.PLAN_HEXCONV, lvl, 1, cm, dev)
                 # upsample straight into the operand copy of the fine level, from the fp32 coarse map (one rounding)
                 a_b = _empty((B * _P(lvl) + 2 * B, cin), torch.bfloat16, dev)
-                _lib.check(L.gin_upsample_bf16(up_plan.host_ptr, up_plan.dev_ptr, act_f.data_ptr(), 1, a_b.data_ptr(), B, cin, _stream()), 'gin_upsample_bf16')
+                a_w = _empty((B * _P(lvl) + 2 * B, cin), torch.bfloat16, dev) if _DUAL else a_b
+                _lib.check(L.gin_upsample_bf16(up_plan.host_ptr, up_plan.dev_ptr, act_f.data_ptr(), 1, a_b.data_ptr(), a_w.data_ptr() if _DUAL else None,
+                                               B, cin, _stream()), 'gin_upsample_bf16')
                 st['up_plan'] = up_plan
             plan_b = get_plan(_lib.PLAN_HEXCONV, lvl, 1, cm, dev)
             rows = B * _P(lvl)
@@ -254,19 +266,21 @@ class _Chain(torch.autograd.Function):
             ycat, pcat = _conv_fwd(plan_a, a_b, pk_cat, bcat, B, cin, 2 * cout, _P(lvl))    # [rows][conv00 | conv10]
             stat00 = _bn_stats(ycat, 0, 2 * cout, rows, cout, blk.icobn00, pcat)
             stat10 = _bn_stats(ycat, cout, 2 * cout, rows, cout, blk.icobn10, pcat)
-            h_b, _ = _bn_act(ycat, 0, 2 * cout, stat00, None, 0, 0, None, B, lvl, cout)
+            h_b, _, h_w = _bn_act(ycat, 0, 2 * cout, stat00, None, 0, 0, None, B, lvl, cout)
             pk01 = _pack_bf16(blk.conv01.weight.detach().contiguous(), None, cout)
             y01, p01 = _conv_fwd(plan_b, h_b, pk01, blk.conv01.bias.detach(), B, cout, cout, _P(lvl))
             stat01 = _bn_stats(y01, 0, cout, rows, cout, blk.icobn01, p01)
             is_last = j == last
             keep_f = is_last or not mods[j + 1]._down         # an Up block upsamples from the fp32 map (one rounding instead of two)
             # the bf16 copy of the block output is the ReLU mask of the backward, so it is always produced
-            out_b, out_f = _bn_act(y01, 0, cout, stat01, ycat, cout, 2 * cout, stat10, B, lvl, cout, want_b=True, want_f=keep_f)
+            # the forward copy of the last block's output has no consumer; its bf16 twin is still the ReLU mask of the backward
+            out_b, out_f, out_w = _bn_act(y01, 0, cout, stat01, ycat, cout, 2 * cout, stat10, B, lvl, cout, want_b=not is_last or not _DUAL, want_f=keep_f)
             act_f = out_f
-            st.update(plan_a=plan_a, plan_b=plan_b, a_b=a_b, pk_cat=pk_cat, pk01=pk01, ycat=ycat, y01=y01, h_b=h_b, out_b=out_b,
+            # saved for backward: the bf16 twins (wgrad operands / ReLU masks); the forward-format copies die with the forward pass
+            st.update(plan_a=plan_a, plan_b=plan_b, a_b=a_w, pk_cat=pk_cat, pk01=pk01, ycat=ycat, y01=y01, h_b=h_w, out_b=out_w,
                       stat00=stat00, stat01=stat01, stat10=stat10, level=lvl)
             saved.append(st)
-            act_b, level, C = out_b, lvl, cout
+            act_b, act_w, level, C = out_b, out_w, lvl, cout
         ctx.saved, ctx.B, ctx.nparams = saved, B, len(params)
         ctx.mods = mods
         n = 2 ** level

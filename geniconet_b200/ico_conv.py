@@ -124,8 +124,10 @@ def clear_caches():
 
 
 def cast_bf16(x_cl, plan, which, level, use_cache=False, colsum=None):
-    """bf16 copy [B*P + 2B, C] of a channels-last fp32 map (pixels, then the per-sample pole means).  `colsum` [C]
-    (optional) receives the per-channel sums over all pixels from the same pass (the conv bias gradient)."""
+    """16-bit operand copy [B*P + 2B, C] of a channels-last fp32 map (pixels, then the per-sample pole means), held in a
+    torch.bfloat16 container: `which` = 0 forward operand (fp16 by default), 1 gradient dy (bf16), 2 forward tensor in bf16 for
+    wgrad (include/geniconet_b200.h: gin_cast_bf16).  `colsum` [C] (optional) receives the per-channel sums over all pixels
+    from the same pass (the conv bias gradient)."""
     B, C = x_cl.shape[0], x_cl.shape[1]
     key = (plan.dev_ptr, which)
     if use_cache:
@@ -166,7 +168,11 @@ class _HexConvFn(torch.autograd.Function):
             if B > 0:
                 _lib.check(_lib.lib.gin_hexconv_fwd_bf16(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), packed.data_ptr(), bias_ptr, y.data_ptr(),
                                                          B, mod.in_features, mod.out_features, _stream()), 'gin_hexconv_fwd_bf16')
-            ctx.save_for_backward(xb, packed)           # the bf16 copy is all wgrad needs: half the saved-activation bytes
+            # wgrad needs x in bf16 (one format per MMA): with fp16 forward operands that is a second 16-bit copy (`which` = 2)
+            xw = xb
+            if B > 0 and _lib.lib.gin_forward_operand_is_fp16() and (ctx.needs_input_grad[1] or torch.is_grad_enabled()):
+                xw = cast_bf16(xs, plan, 2, mod.subdivisions, use_cache=True)
+            ctx.save_for_backward(xw, packed)           # a 16-bit copy is all wgrad needs: half the saved-activation bytes
         else:
             xs, sb, sp, sc = pixel_strides(x)
             if B > 0:

@@ -102,11 +102,14 @@ int gin_hexconv_wgrad(const void* plan_host, const void* plan_dev, const float* 
                       const float* dy, float* dW, float* db, void* ws,
                       int B, int Cin, int Cout, int impl, void* stream);
 
-/* tcgen05 path.  The tensor-core kernels read a bf16 copy of the gathered activation: gin_cast_bf16 writes
- * [B*P + 2B][C] bf16 = the pixels followed by the per-sample pole means (so a pole cell is an ordinary row).
- * `which` = 0 for a conv INPUT (x, level of `subdivisions`), 1 for a conv OUTPUT gradient (dy, output level).
- * One cast of x serves forward and wgrad, one cast of dy serves dgrad and wgrad.  Operands are bf16, accumulation
- * is fp32 in TMEM, outputs are fp32.  Needs Cin % 64 == 0 and Cout % 64 == 0. */
+/* tcgen05 path.  The tensor-core kernels read a 16-bit copy of the gathered activation: gin_cast_bf16 writes
+ * [B*P + 2B][C] = the pixels followed by the per-sample pole means (so a pole cell is an ordinary row).
+ * `which` = 0: a conv INPUT x (level of `subdivisions`) in the FORWARD operand format (fp16 unless
+ *              gin_forward_operand_is_fp16() == 0) -- what gin_hexconv_fwd_bf16 reads;
+ *           1: a conv OUTPUT gradient dy (output level) in bf16 -- what dgrad and wgrad read;
+ *           2: a conv INPUT x in bf16 -- what wgrad reads (a kind::f16 MMA needs both operands in one format; identical to
+ *              which = 0 when the forward format is bf16).
+ * Accumulation is fp32 in TMEM, outputs are fp32.  Needs Cin % 64 == 0 and Cout % 64 == 0. */
 size_t gin_cast_bf16_bytes(int B, int level, int C);
 int gin_cast_bf16(const void* plan_host, const void* plan_dev, int which, const float* x, void* xb, int B, int C, void* stream);
 /* Same cast fused with the per-channel sums of x over all B*P pixels: with which = 1 this is the conv bias gradient
@@ -149,11 +152,12 @@ int gin_bn_stats(const float* y, int64_t ld, int64_t rows, int C, const float* g
 /* The same from per-CTA partial sums `parts` = nparts rows of [2][ld] (here pointing at the first of the C columns wanted). */
 int gin_bn_stats_from_parts(const float* parts, int nparts, int64_t ld, int64_t rows, int C, const float* gamma, const float* beta, float eps,
                             float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked, float* stat, void* stream);
-/* out = act(y1*scale1 + shift1 [+ y2*scale2 + shift2]) at level `level`: out_b (may be NULL) = bf16 [B*P + 2B][C] (pixels, then the
- * per-sample pole means) -- exactly what gin_cast_bf16 would produce from out; out_f (may be NULL) = fp32 [B*P][C]. */
+/* out = act(y1*scale1 + shift1 [+ y2*scale2 + shift2]) at level `level`: out_b (may be NULL) = 16-bit [B*P + 2B][C] (pixels, then the
+ * per-sample pole means) in the forward operand format -- exactly what gin_cast_bf16(which = 0) would produce from out;
+ * out_f (may be NULL) = fp32 [B*P][C]; out_w (may be NULL) = the same rows as out_b in bf16 (which = 2: wgrad operand, ReLU mask). */
 int gin_bn_act_fwd(const float* y1, int64_t ld1, const float* stat1, const float* y2 /* may be NULL */, int64_t ld2, const float* stat2,
-                   int relu, void* out_b, float* out_f, int B, int level, int C, void* stream);
-/* backward of out = act(bn(y) [+ ...]) with respect to y: g = dout * (mask_b > 0) (mask_b = the bf16 copy of out; NULL: no ReLU),
+                   int relu, void* out_b, float* out_f, void* out_w, int B, int level, int C, void* stream);
+/* backward of out = act(bn(y) [+ ...]) with respect to y: g = dout * (mask_b > 0) (mask_b = a 16-bit copy of out, either format; NULL: no ReLU),
  * bstat[4][C] = dbeta, dgamma, mean(g), mean(g*yhat);  dy = scale*(g - mean(g) - yhat*mean(g*yhat)) is written as the bf16
  * copy dy_b [B*P + 2B][.] with row stride ldo (pole-mean rows included) and / or as fp32 dy_f with row stride ldf. */
 int gin_bn_act_bwd(const float* dout, int64_t ldg, const void* mask_b, const float* y, int64_t ld, const float* stat, float* bstat,
@@ -164,9 +168,11 @@ size_t gin_bn_pair_ws_bytes(int C);
 int gin_bn_act_bwd_pair(const float* dout, int64_t ldg, const void* mask_b, const float* yA, int64_t ldA, const float* statA, float* bstatA,
                         void* dyA_b, int64_t ldoA, const float* yB, int64_t ldB, const float* statB, float* bstatB, void* dyB_b, int64_t ldoB,
                         void* ws, int B, int level, int C, void* stream);
-/* IcoUpsampleS2S.forward whose result exists only as the next convolution's operand copy out_b = bf16 [B*Pf + 2B][C]
- * (upsample plan).  in: the fp32 coarse map [B*Pc][C] (in_is_f32 = 1) or its bf16 operand copy [B*Pc + 2B][C] (0). */
-int gin_upsample_bf16(const void* plan_host, const void* plan_dev, const void* in, int in_is_f32, void* out_b, int B, int C, void* stream);
+/* IcoUpsampleS2S.forward whose result exists only as the next convolution's operand copy out_b = 16-bit [B*Pf + 2B][C] in the
+ * forward operand format (upsample plan), plus (out_w, may be NULL) its bf16 twin for wgrad.  in: the fp32 coarse map
+ * [B*Pc][C] (in_is_f32 = 1) or its forward-format operand copy [B*Pc + 2B][C] (0). */
+int gin_upsample_bf16(const void* plan_host, const void* plan_dev, const void* in, int in_is_f32, void* out_b, void* out_w, int B, int C,
+                      void* stream);
 
 /* ------------------------------------------------------------------ device: VAE ------ */
 /* VAE.reparameterize (models.py:89-92), row a6: eps ~ N(0,1) from Philox4x32-10

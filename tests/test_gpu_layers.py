@@ -329,7 +329,7 @@ def test_fused_bn_act_matches_torch(C, level, B, two):
     # ---- fused kernels
     stat1 = fused._bn_stats(ybuf, col0, ld, B * P, C, bns[0])
     stat2 = fused._bn_stats(y2, 0, C, B * P, C, bns[1]) if two else None
-    out_b, out_f = fused._bn_act(ybuf, col0, ld, stat1, y2, 0, C, stat2, B, level, C, want_b=True, want_f=True)
+    out_b, out_f, out_w = fused._bn_act(ybuf, col0, ld, stat1, y2, 0, C, stat2, B, level, C, want_b=True, want_f=True)
     torch.cuda.synchronize()
     ref_flat = out_r.detach().permute(0, 2, 3, 1).reshape(B * P, C)
     assert torch.allclose(out_f, ref_flat, rtol=1e-4, atol=1e-4)
@@ -338,6 +338,7 @@ def test_fused_bn_act_matches_torch(C, level, B, two):
     ring = [[k * n * 2 * n for k in range(5)], [k * n * 2 * n + (n - 1) * 2 * n + 2 * n - 1 for k in range(5)]]
     poles = torch.stack([ref_flat.view(B, P, C)[:, ring[p]].mean(1) for p in (0, 1)], 1).reshape(2 * B, C)     # [B][pole] rows
     assert torch.allclose(out_b16[B * P:].float(), poles, rtol=1e-2, atol=1e-2)
+    assert torch.allclose(out_w.float(), out_b16.float(), rtol=1e-2, atol=1e-2)          # the bf16 twin (wgrad operand, ReLU mask)
     for a, b in zip(refbn[:2 if two else 1], bns):
         assert torch.allclose(a.running_mean, b.running_mean, rtol=1e-4, atol=1e-5)
         assert torch.allclose(a.running_var, b.running_var, rtol=1e-4, atol=1e-5)
@@ -348,13 +349,13 @@ def test_fused_bn_act_matches_torch(C, level, B, two):
         dyB = torch.empty(B * P + 2 * B, C, dtype=torch.bfloat16, device=dev)
         bsA, bsB = torch.empty(4 * C, device=dev), torch.empty(4 * C, device=dev)
         ws = torch.empty(L.gin_bn_pair_ws_bytes(C), dtype=torch.uint8, device=dev)
-        _lib.check(L.gin_bn_act_bwd_pair(d.data_ptr(), C, out_b.data_ptr(), ybuf.data_ptr() + 4 * col0, ld, stat1.data_ptr(), bsA.data_ptr(),
+        _lib.check(L.gin_bn_act_bwd_pair(d.data_ptr(), C, out_w.data_ptr(), ybuf.data_ptr() + 4 * col0, ld, stat1.data_ptr(), bsA.data_ptr(),
                                          dyA.data_ptr(), C, y2.data_ptr(), C, stat2.data_ptr(), bsB.data_ptr(), dyB.data_ptr(), C, ws.data_ptr(),
                                          B, level, C, torch.cuda.current_stream().cuda_stream))
         pairs = [(bsA, dyA, y1r, refbn[0]), (bsB, dyB, y2r, refbn[1])]
     else:
         dyA = torch.empty(B * P + 2 * B, C, dtype=torch.bfloat16, device=dev)
-        bsA, dyf = fused._bn_bwd(d, out_b, ybuf, col0, ld, stat1, B, level, C, dy_b=dyA, dy_b_col=0, ldo=C, want_f=True)
+        bsA, dyf = fused._bn_bwd(d, out_w, ybuf, col0, ld, stat1, B, level, C, dy_b=dyA, dy_b_col=0, ldo=C, want_f=True)
         assert torch.allclose(dyf, y1r.grad, rtol=1e-3, atol=1e-5)
         pairs = [(bsA, dyA, y1r, refbn[0])]
     torch.cuda.synchronize()
