@@ -14,7 +14,7 @@ mod = IcoConvS2S(cin, cout, stride, True, level, 'average', impl='tc').cuda()
 mod.load_state_dict(ref.state_dict())
 n = 2 ** level
 g = torch.Generator().manual_seed(9)
-x = torch.randn(B, cin, 5 * n, 2 * n, generator=g).to(FWD).float()
+x = torch.randn(B, cin, 5 * n, 2 * n, generator=g).to(torch.float16).to(torch.bfloat16).float()      # exact in both formats (wgrad reads bf16)
 xr = x.clone().requires_grad_(True)
 yr = ref(xr); gy = torch.randn(yr.shape, generator=g).to(torch.bfloat16).float(); yr.backward(gy)
 xc = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
