@@ -82,11 +82,16 @@ bool patch_mode_enabled() { return tc_mode() >= 1; }
 // Cross-seam remainder of dgrad: the row-gather kernel over signature-sorted slot tiles (default), or GIN_SEAM=patch: the regular
 // form (GinPxSide, every tile runs all slots) through the patch kernel.  Measured equal within 5 % at I5 / B = 36 (both are bound
 // by the latency of ~20-40 tiny stages per CTA, not by work), so the one that moves less data stays the default.
-bool seam_v2_enabled() {
+// GIN_SEAM: "fold" (default, r02): boundary tiles inside the in-chart launch (GinPfSide: complete values, masked in-chart stores,
+// one launch); "patch": second launch of the patch kernel over GinPxSide (read-modify-write); "gather": second launch of the
+// first-generation row-gather kernel.
+int seam_mode() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("GIN_SEAM"); v = (e && strcmp(e, "gather") == 0) ? 0 : 1; }
-  return v == 1;
+  if (v < 0) { const char* e = getenv("GIN_SEAM"); v = (e && strcmp(e, "gather") == 0) ? 0 : (e && strcmp(e, "patch") == 0) ? 1 : 2; }
+  return v;
 }
+bool seam_v2_enabled() { return seam_mode() >= 1; }
+bool seam_fold_ok(const GinPfSide& pf) { return seam_mode() == 2 && pf.ntiles > 0 && pf.nslots <= gin::cv2::MAX_PLANES && pf.mask_off > 0; }
 
 // fp32 CUDA-core path
 int run_gather_gemm_simt(const int32_t* plan_dev, const GinSide& side, int group, GinSrcView X, const char* packed, int B, int K, int N,
@@ -116,12 +121,14 @@ int run_gemm_tc(const int32_t* plan_dev, const GinConvPlanHdr* h, const void* Xb
   // forward: activation copy x forward weight tiles (both the forward format); dgrad: dy copy x dgrad weight tiles (both bf16)
   gin::set_operand_formats(dgrad || !gin::fwd_fp16(), dgrad || !gin::fwd_fp16());
   if (h->stride == 1 && patch_mode_enabled() && gin::tcp_supported(ps, K, N)) {
+    const bool fold = dgrad && tc_mode() == 2 && gin::cv2_supported(ps, K, N) && seam_fold_ok(h->pf);
     if (tc_mode() == 2 && gin::cv2_supported(ps, K, N))
       rc = gin::launch_patch_conv2(plan_dev, ps, h->group, side.P_dst, 2 << h->level_in, Xb, wb, bias, Y, B, K, N, dgrad ? 1 : 0, st, dgrad ? nullptr : stats,
-                                   dgrad ? nullptr : stats_parts);
+                                   dgrad ? nullptr : stats_parts, fold ? &h->pf : nullptr);
     else rc = gin::launch_patch_gemm_tc(plan_dev, ps, h->group, side.P_dst, Xb, wb, bias, Y, B, K, N, dgrad ? 1 : 0, st);
     if (rc != GIN_OK) return fail(rc, "tcgen05 patch-GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (fold) return GIN_OK;                          // boundary pixels were part of the same launch
     if (dgrad && tc_mode() == 2 && seam_v2_enabled() && gin::cv2_seam_supported(h->px, K, N)) {   // cross-seam and pole entries, added on top
       rc = gin::launch_patch_conv2_seam(plan_dev, h->px, h->group, side.P_src, side.P_dst, Xb, wb, Y, B, K, N, st);
       if (rc != GIN_OK) return fail(rc, "tcgen05 seam pass (v2) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -136,10 +143,13 @@ int run_gemm_tc(const int32_t* plan_dev, const GinConvPlanHdr* h, const void* Xb
   if (h->stride == 2 && tc_mode() == 2 && gin::cv2_supported(h->p2, K, N)) {
     // stride 2 in patch mode on the coarse lattice: four parity planes (gin_plan.h: GinP2Side)
     const int Pf = h->fwd.P_src, Pc = h->fwd.P_dst;
+    rc = GIN_OK;
     if (!dgrad) rc = gin::launch_patch_conv2_s2_fwd(plan_dev, h->p2, h->group, Pf, Pc, 2 << h->level_out, Xb, wb, bias, Y, B, K, N, st, stats, stats_parts);
-    else rc = gin::launch_patch_conv2_s2_dgrad(plan_dev, h->p2, h->group, Pf, Pc, 2 << h->level_in, Xb, wb, Y, B, K, N, st);
+    const bool fold = dgrad && seam_fold_ok(h->pf);
+    if (dgrad) rc = gin::launch_patch_conv2_s2_dgrad(plan_dev, h->p2, h->group, Pf, Pc, 2 << h->level_in, Xb, wb, Y, B, K, N, st, fold ? &h->pf : nullptr);
     if (rc != GIN_OK) return fail(rc, "tcgen05 stride-2 patch launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (fold) return GIN_OK;
     if (dgrad && seam_v2_enabled() && gin::cv2_seam_supported(h->px, K, N)) {
       rc = gin::launch_patch_conv2_seam(plan_dev, h->px, h->group, Pc, Pf, Xb, wb, Y, B, K, N, st);
       if (rc != GIN_OK) return fail(rc, "tcgen05 seam pass (v2) launch failed: %s", cudaGetErrorString(cudaGetLastError()));

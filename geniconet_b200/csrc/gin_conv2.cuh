@@ -73,6 +73,11 @@ struct Params {
   int dst_row_stride, dst_px_stride, dst_plane_off[MAX_PLANES];
   int total_tiles, n_blocks;  // CTA c owns n-block c % n_blocks and tiles c / n_blocks + k * (gridDim.x / n_blocks)
   int a_stage_bytes, a_stages, b_stages, resident;
+  // Second tile class (SEAM kernels: dgrad in one launch, gin_plan.h GinPfSide): x_total boundary tiles in regular form --
+  // x_nslots segments of 128 gathered rows with one tap each, destination pixels from a table -- appended to the tile list after
+  // the total_tiles patch tiles.  mask_off >= 0: plan words [ntiles][nflush][4], bit r set = the patch tile does not store row r.
+  int x_total, x_ntiles, x_nslots, x_src_off, x_dst_off, mask_off;
+  int8_t x_tap[MAX_PLANES];
   int* stats_parts;           // host: receives the number of per-CTA statistics rows written (0: none)
   int dbg;                    // GIN_DBG bit mask (experiments only): 1 no epilogue stores, 2 no patch loads, 4 no MMAs
 };
@@ -102,7 +107,7 @@ constexpr int BAR_BYTES = NBARS * 8 + 16;
 #define PROF_ADD(acc)
 #endif
 
-template <int N_TILE, bool RESIDENT, bool STATS>
+template <int N_TILE, bool RESIDENT, bool STATS, bool SEAM>
 __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -132,6 +137,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
   constexpr uint32_t TM_COLS = (2 * N_TILE <= 32) ? 32 : 2 * N_TILE;
   const int nb = blockIdx.x % p.n_blocks, n0 = nb * N_TILE;
   const int t_first = blockIdx.x / p.n_blocks, t_step = gridDim.x / p.n_blocks;
+  const int TT = p.total_tiles + (SEAM ? p.x_total : 0);      // tiles of both classes; T >= p.total_tiles: a boundary tile
 
   if (warp == W_MMA) {
     if (lane == 0) {
@@ -163,26 +169,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
     const __nv_bfloat16* __restrict__ Xc = p.X + c8 * 8;
     int s = 0, ts = 0;
     uint32_t ph = 0, tph = 0;
-    for (int VT = t_first * NP; VT < p.total_tiles * NP; VT = (VT % NP == NP - 1) ? VT + 1 + (t_step - 1) * NP : VT + 1) {
-      int v[MAX_ITEMS];
-      { PROF_T0(); mbar_wait(&tab_full[ts], tph); PROF_ADD(pw[0]); }
+    for (int T = t_first; T < TT; T += t_step) {
+      const bool sx = SEAM && T >= p.total_tiles;
+      const int NPt = sx ? p.x_nslots : NP, Ut = sx ? BM : U;
+      for (int pl = 0; pl < NPt; ++pl) {
+        int v[MAX_ITEMS];
+        { PROF_T0(); mbar_wait(&tab_full[ts], tph); PROF_ADD(pw[0]); }
 #pragma unroll
-      for (int it = 0; it < MAX_ITEMS; ++it) v[it] = tab[ts * TAB_ROWS + it * 32 + warp * 4 + sub];
-      mbar_arrive(&tab_empty[ts]);                   // the row ids are in registers now
-      if (++ts == TAB_SLOTS) { ts = 0; tph ^= 1u; }
-      for (int kc = 0; kc < kchunks; ++kc) {
-        { PROF_T0(); mbar_wait(&a_empty[s], ph ^ 1u); PROF_ADD(pw[1]); }
-        const uint32_t st = smem_u32(a_smem + s * p.a_stage_bytes);
+        for (int it = 0; it < MAX_ITEMS; ++it) v[it] = tab[ts * TAB_ROWS + it * 32 + warp * 4 + sub];
+        mbar_arrive(&tab_empty[ts]);                   // the row ids are in registers now
+        if (++ts == TAB_SLOTS) { ts = 0; tph ^= 1u; }
+        for (int kc = 0; kc < kchunks; ++kc) {
+          { PROF_T0(); mbar_wait(&a_empty[s], ph ^ 1u); PROF_ADD(pw[1]); }
+          const uint32_t st = smem_u32(a_smem + s * p.a_stage_bytes);
 #pragma unroll
-        for (int it = 0; it < MAX_ITEMS; ++it) {
-          const int u = it * 32 + warp * 4 + sub;
-          if (u < U && !(p.dbg & 2)) {
-            const bool ok = v[it] >= 0;
-            cp_async16_cg(st + swz(u, c8), Xc + (size_t)(ok ? v[it] : 0) * p.K + kc * BK, ok);
+          for (int it = 0; it < MAX_ITEMS; ++it) {
+            const int u = it * 32 + warp * 4 + sub;
+            if (u < Ut && !(p.dbg & 2)) {
+              const bool ok = v[it] >= 0;
+              cp_async16_cg(st + swz(u, c8), Xc + (size_t)(ok ? v[it] : 0) * p.K + kc * BK, ok);
+            }
           }
+          cp_async_arrive(&a_full[s]);
+          if (++s == AS) { s = 0; ph ^= 1u; }
         }
-        cp_async_arrive(&a_full[s]);
-        if (++s == AS) { s = 0; ph ^= 1u; }
       }
     }
 #ifdef GIN_PROF
@@ -203,9 +213,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
     // blocking (its a_full + proxy fence, and the accumulator hand-back when it starts a new output); whatever is already
     // complete then costs nothing at the chunk boundary.
     bool a_ready = false, acc_ready = false;
-    for (int T = t_first; T < p.total_tiles; T += t_step) {
+    for (int T = t_first; T < TT; T += t_step) {
+      const bool sx = SEAM && T >= p.total_tiles;
+      const int NPt = sx ? p.x_nslots : NP;
+      const uint32_t gbytes = sx ? 1024u : (uint32_t)p.group_bytes;
       uint32_t fresh = 1;                            // the next MMA starts a new accumulation
-      for (int pl = 0; pl < NP; ++pl) {
+      for (int pl = 0; pl < NPt; ++pl) {
         const uint32_t ab = wc & 1;
         if (fresh && !acc_ready) {
           PROF_T0();
@@ -215,8 +228,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
         }
         acc_ready = false;
         const uint32_t d_tmem = tmem_base + ab * N_TILE;
-        const int nt = p.ntaps[pl];
-        const bool flush = p.flush_each || pl == NP - 1;
+        const int nt = sx ? 1 : p.ntaps[pl];
+        const bool flush = sx ? pl == NPt - 1 : (p.flush_each || pl == NP - 1);
         for (int kc = 0; kc < kchunks; ++kc) {
           if (!a_ready) {
             { PROF_T0(); mbar_wait(&a_full[s], ph); PROF_ADD(pw[1]); }
@@ -224,7 +237,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
           }
           a_ready = false;
           const uint32_t a_addr = smem_u32(a_smem + s * p.a_stage_bytes);
-          const bool last_chunk_of_cta = kc == kchunks - 1 && pl == NP - 1 && T + t_step >= p.total_tiles;
+          const bool last_chunk_of_cta = kc == kchunks - 1 && pl == NPt - 1 && T + t_step >= TT;
           for (int j = 0; j < nt; ++j) {
             if (j == nt - 1 && !last_chunk_of_cta) {  // open the next chunk while the earlier tap groups execute
               const int sn = (s + 1 == AS) ? 0 : s + 1;
@@ -241,7 +254,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
                 }
               }
             }
-            const int tap = p.tap_id[pl][j];
+            const int tap = sx ? p.x_tap[pl] : p.tap_id[pl][j];
+            const uint32_t trow = sx ? 0u : (uint32_t)p.tap_row[pl][j];
             uint32_t b_addr;
             if (RESIDENT) b_addr = smem_u32(b_smem + (size_t)(tap * kchunks + kc) * B_TILE);
             else {
@@ -249,7 +263,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
               tc_fence_after();
               b_addr = smem_u32(b_smem + (size_t)bs * B_TILE);
             }
-            const uint64_t da = desc_kmajor(a_addr + (uint32_t)p.tap_row[pl][j] * 128u, (uint32_t)p.group_bytes), db = desc_kmajor(b_addr, 1024);
+            const uint64_t da = desc_kmajor(a_addr + trow * 128u, gbytes), db = desc_kmajor(b_addr, 1024);
             {
               PROF_T0();
 #pragma unroll
@@ -290,16 +304,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
       } else {
         int bs = 0;
         uint32_t bph = 0;
-        for (int T = t_first; T < p.total_tiles; T += t_step)
-          for (int pl = 0; pl < NP; ++pl)
+        for (int T = t_first; T < TT; T += t_step) {
+          const bool sx = SEAM && T >= p.total_tiles;
+          const int NPt = sx ? p.x_nslots : NP;
+          for (int pl = 0; pl < NPt; ++pl)
             for (int kc = 0; kc < kchunks; ++kc)
-              for (int j = 0; j < p.ntaps[pl]; ++j) {
-                const int tap = p.tap_id[pl][j];
+              for (int j = 0; j < (sx ? 1 : p.ntaps[pl]); ++j) {
+                const int tap = sx ? p.x_tap[pl] : p.tap_id[pl][j];
                 mbar_wait(&b_empty[bs], bph ^ 1u);
                 mbar_arrive_expect_tx(&b_full[bs], B_TILE);
                 bulk_g2s(b_smem + (size_t)bs * B_TILE, p.Wt + (((size_t)tap * kchunks + kc) * p.N + n0) * BK, B_TILE, &b_full[bs]);
                 if (++bs == BS) { bs = 0; bph ^= 1u; }
               }
+        }
       }
     }
     __syncwarp();
@@ -308,30 +325,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
     const long long total_src = (long long)p.B * p.P_src;
     int ts = 0;
     uint32_t tph = 0;
-    const int vt_end = p.total_tiles * NP;
-    auto next_vt = [&](int vt) { return (vt % NP == NP - 1) ? vt + 1 + (t_step - 1) * NP : vt + 1; };
-    for (int VT0 = t_first * NP; VT0 < vt_end;) {
-      int code[TAB_BATCH][MAX_ITEMS], vts[TAB_BATCH];
-      int vt = VT0;
+    int Tn = t_first, pn = 0;                        // the next (tile, segment) in the producers' order
+    while (Tn < TT) {
+      int code[TAB_BATCH][MAX_ITEMS], tiles[TAB_BATCH];
 #pragma unroll
       for (int j = 0; j < TAB_BATCH; ++j) {
-        vts[j] = vt;
-        if (vt < vt_end) {
-          const int T = vt / NP, pl = vt - T * NP;
-          const int32_t* __restrict__ src_tab = p.plan + p.tab_off + (size_t)(T % p.ntiles) * p.tab_tstride + (size_t)pl * p.tab_pstride;
+        tiles[j] = -1;
+        if (Tn < TT) {
+          tiles[j] = Tn;
+          const bool sx = SEAM && Tn >= p.total_tiles;
+          const int32_t* __restrict__ src_tab =
+              sx ? p.plan + p.x_src_off + ((size_t)((Tn - p.total_tiles) % p.x_ntiles) * p.x_nslots + pn) * BM
+                 : p.plan + p.tab_off + (size_t)(Tn % p.ntiles) * p.tab_tstride + (size_t)pn * p.tab_pstride;
+          const int Ut = sx ? BM : U;
 #pragma unroll
           for (int it = 0; it < MAX_ITEMS; ++it) {
             const int u = it * 32 + lane;
-            code[j][it] = (u < U) ? __ldg(src_tab + u) : GIN_SRC_ZERO;
+            code[j][it] = (u < Ut) ? __ldg(src_tab + u) : GIN_SRC_ZERO;
           }
-          vt = next_vt(vt);
+          if (++pn == (sx ? p.x_nslots : NP)) { pn = 0; Tn += t_step; }
         }
       }
-      VT0 = vt;
 #pragma unroll
       for (int j = 0; j < TAB_BATCH; ++j) {
-        if (vts[j] < vt_end) {
-          const int G = (vts[j] / NP) / p.ntiles;
+        if (tiles[j] >= 0) {
+          const int G = (SEAM && tiles[j] >= p.total_tiles) ? (tiles[j] - p.total_tiles) / p.x_ntiles : tiles[j] / p.ntiles;
           const long long base = (long long)G * p.group * p.P_src;
           mbar_wait(&tab_empty[ts], tph ^ 1u);
 #pragma unroll
@@ -362,16 +380,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
     for (int si = 0; si < (STATS ? NS : 1); ++si)
 #pragma unroll
       for (int k = 0; k < 4; ++k) { ssum[si][k] = 0.f; ssq[si][k] = 0.f; }
-    for (int T = t_first; T < p.total_tiles; T += t_step)
-    for (int fl = 0; fl < nflush; ++fl, ++wc) {
-      const int G = T / p.ntiles, t = T - G * p.ntiles;
+    for (int T = t_first; T < TT; T += t_step) {
+    const bool sx = SEAM && T >= p.total_tiles;
+    const bool tabdst = sx || p.dst_tab_off >= 0;   // destination pixels from a table (boundary tiles / the stand-alone seam form)
+    for (int fl = 0; fl < (sx ? 1 : nflush); ++fl, ++wc) {
+      const int Tl = sx ? T - p.total_tiles : T, per = sx ? p.x_ntiles : p.ntiles;
+      const int G = Tl / per, t = Tl - G * per;
       long long gdl;
       bool extra_row = false;
-      if (p.dst_tab_off >= 0) {
-        const int dr = __ldg(p.plan + p.dst_tab_off + t * BM + row);
+      if (tabdst) {
+        const int dr = __ldg(p.plan + (sx ? p.x_dst_off : p.dst_tab_off) + t * BM + row);
         extra_row = dr == -3;                         // a further row of the pixel above (same 32-row group): folded in below
         gdl = dr >= 0 ? (long long)G * p.group * p.P_dst + dr : total_pix;
-      } else gdl = (long long)G * p.group * p.P_dst + tile_base[t * Q + oq] + row_off + p.dst_plane_off[fl];
+      } else {
+        gdl = (long long)G * p.group * p.P_dst + tile_base[t * Q + oq] + row_off + p.dst_plane_off[fl];
+        if (SEAM && p.mask_off >= 0) {                // boundary pixels are written by the boundary tiles
+          const uint32_t mw = (uint32_t)__ldg(p.plan + p.mask_off + (t * nflush + fl) * 4 + q);
+          if ((mw >> lane) & 1u) gdl = total_pix;
+        }
+      }
       const int gd = extra_row ? -3 : (gdl < total_pix ? (int)gdl : -1);       // B*P < 2^31 is checked by the launcher
       const uint32_t ab = wc & 1;
       { PROF_T0(); mbar_wait(&acc_full[ab], (wc >> 1) & 1u); PROF_ADD(pw[0]); }
@@ -401,7 +428,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
           const int gd2 = __shfl_sync(0xffffffffu, gd, r2);
           float4 o = *reinterpret_cast<const float4*>(my_stage + r2 * STAGE_PITCH + c4 * 4);
           o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-          if (p.dst_tab_off >= 0) {                       // seam form: up to two extra rows below belong to this pixel
+          if (tabdst) {                                   // table form: up to two extra rows below belong to this pixel
             const int x1 = __shfl_sync(0xffffffffu, gd, (r2 + 1) & 31), x2 = __shfl_sync(0xffffffffu, gd, (r2 + 2) & 31);
             if (r2 + 1 < 32 && x1 == -3) {
               const float4 u = *reinterpret_cast<const float4*>(my_stage + (r2 + 1) * STAGE_PITCH + c4 * 4);
@@ -425,6 +452,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
         }
         __syncwarp();
       }
+    }
     }
     if (STATS) {
       // column sums of this CTA's rows: lanes that share (lane & 7) hold the same columns; the four TMEM-quarter warps of a
@@ -493,26 +521,32 @@ int launch(Params p, cudaStream_t st) {
   static PerDeviceFlag configured_on;
   bool& configured = configured_on.here();
   if (!configured) {
-    if (cudaFuncSetAttribute(patch_conv_kernel<N_TILE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
-        cudaFuncSetAttribute(patch_conv_kernel<N_TILE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
-        cudaFuncSetAttribute(patch_conv_kernel<N_TILE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
-        cudaFuncSetAttribute(patch_conv_kernel<N_TILE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -3;
+    if (cudaFuncSetAttribute(patch_conv_kernel<N_TILE, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
+        cudaFuncSetAttribute(patch_conv_kernel<N_TILE, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
+        cudaFuncSetAttribute(patch_conv_kernel<N_TILE, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
+        cudaFuncSetAttribute(patch_conv_kernel<N_TILE, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
+        cudaFuncSetAttribute(patch_conv_kernel<N_TILE, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
+        cudaFuncSetAttribute(patch_conv_kernel<N_TILE, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -3;
     configured = true;
   }
   p.n_blocks = p.N / N_TILE;
-  const long long items = (long long)p.total_tiles * p.n_blocks;
+  const bool seam = p.x_total > 0;
+  const long long items = (long long)(p.total_tiles + p.x_total) * p.n_blocks;
   const int sms = num_sms();
   int grid = (int)(items < sms ? items : sms);
   grid -= grid % p.n_blocks;                         // every CTA keeps one n-block
   if (grid < p.n_blocks) grid = p.n_blocks;
-  const bool stats = p.stats != nullptr && !p.flush_each;
+  const bool stats = p.stats != nullptr && !p.flush_each && !seam;
   if (p.stats_parts) *p.stats_parts = stats ? grid / p.n_blocks : 0;
-  if (p.resident) {
-    if (stats) launch_pdl(patch_conv_kernel<N_TILE, true, true>, dim3(grid), dim3(NTHREADS), smem_total, st, p);
-    else launch_pdl(patch_conv_kernel<N_TILE, true, false>, dim3(grid), dim3(NTHREADS), smem_total, st, p);
+  if (seam) {                                        // dgrad in one launch: patch tiles + boundary tiles
+    if (p.resident) launch_pdl(patch_conv_kernel<N_TILE, true, false, true>, dim3(grid), dim3(NTHREADS), smem_total, st, p);
+    else launch_pdl(patch_conv_kernel<N_TILE, false, false, true>, dim3(grid), dim3(NTHREADS), smem_total, st, p);
+  } else if (p.resident) {
+    if (stats) launch_pdl(patch_conv_kernel<N_TILE, true, true, false>, dim3(grid), dim3(NTHREADS), smem_total, st, p);
+    else launch_pdl(patch_conv_kernel<N_TILE, true, false, false>, dim3(grid), dim3(NTHREADS), smem_total, st, p);
   } else {
-    if (stats) launch_pdl(patch_conv_kernel<N_TILE, false, true>, dim3(grid), dim3(NTHREADS), smem_total, st, p);
-    else launch_pdl(patch_conv_kernel<N_TILE, false, false>, dim3(grid), dim3(NTHREADS), smem_total, st, p);
+    if (stats) launch_pdl(patch_conv_kernel<N_TILE, false, true, false>, dim3(grid), dim3(NTHREADS), smem_total, st, p);
+    else launch_pdl(patch_conv_kernel<N_TILE, false, false, false>, dim3(grid), dim3(NTHREADS), smem_total, st, p);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
@@ -551,7 +585,7 @@ int cv2_launch_pair(cv2::Params& p, int nt, cudaStream_t st);
 inline bool cv2_pair_ok(const cv2::Params& p, int nt) {
   static int enabled = -1;
   if (enabled < 0) { const char* e = getenv("GIN_PAIR"); enabled = e ? atoi(e) : 1; }      // 0 off, 1 when it costs no extra round, 2 always
-  if (!enabled || p.flush_each || p.accumulate || p.dst_tab_off >= 0 || p.nplanes > 4) return false;
+  if (!enabled || p.flush_each || p.accumulate || p.dst_tab_off >= 0 || p.nplanes > 4 || p.x_total > 0) return false;
   const int ntp = nt < 128 ? nt : 128;
   if (7 * (p.K / 64) * ntp * 128 <= 114688) return false;                   // the weights fit: the resident single-tile kernel is better
   auto rounds = [&](long long items, int n_blocks) {
@@ -570,8 +604,9 @@ inline int cv2_dispatch(cv2::Params& p, int max_ntile, cudaStream_t st) {
   if ((long long)p.B * (p.P_src > p.P_dst ? p.P_src : p.P_dst) + 2LL * p.B >= 0x7fffffffLL) return -4;
   const int groups = (p.B + p.group - 1) / p.group;
   p.total_tiles = groups * p.ntiles;
+  p.x_total = p.x_ntiles > 0 ? groups * p.x_ntiles : 0;
   { const char* e = getenv("GIN_DBG"); p.dbg = e ? atoi(e) : 0; }
-  int nt = cv2_pick_ntile(p.total_tiles, p.N);
+  int nt = cv2_pick_ntile(p.total_tiles + p.x_total, p.N);
   while (nt > max_ntile) nt /= 2;
   if (cv2_pair_ok(p, nt)) {
     const int rc = cv2_launch_pair(p, nt < 128 ? nt : 128, st);
@@ -585,10 +620,19 @@ inline int cv2_dispatch(cv2::Params& p, int max_ntile, cudaStream_t st) {
 }
 
 // stride 1: forward (mirror 0) / in-chart dgrad (mirror 1: tap (di,dj) reads cell (-di,-dj)); W = 2n pixels per chart row
+// `pf` (dgrad only): fold the boundary tiles of the plan into the same launch
+inline void cv2_attach_boundary(cv2::Params& p, const GinPfSide* pf) {
+  p.mask_off = -1;
+  if (!pf || pf->ntiles <= 0 || pf->nslots > cv2::MAX_PLANES) return;
+  p.x_ntiles = pf->ntiles; p.x_nslots = pf->nslots; p.x_src_off = pf->src_off; p.x_dst_off = pf->dst_off; p.mask_off = pf->mask_off;
+  for (int s = 0; s < pf->nslots; ++s) p.x_tap[s] = pf->tap[s];
+}
+
 inline int launch_patch_conv2(const int32_t* plan_dev, const GinPSide& ps, int group, int P, int W, const void* Xb, const void* Wb,
                               const float* bias, float* Y, int B, int K, int N, int mirror, cudaStream_t st, float* stats = nullptr,
-                              int* stats_parts = nullptr) {
+                              int* stats_parts = nullptr, const GinPfSide* pf = nullptr) {
   cv2::Params p{};
+  cv2_attach_boundary(p, pf);
   p.stats = stats; p.stats_parts = stats_parts;
   p.plan = plan_dev; p.fmt = operand_format_bits(); p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P; p.P_dst = P;
   p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.Wt = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = bias; p.Y = Y;
@@ -614,6 +658,7 @@ inline int launch_patch_conv2_s2_fwd(const int32_t* plan_dev, const GinP2Side& p
                                      const void* Wb, const float* bias, float* Y, int B, int K, int N, cudaStream_t st, float* stats = nullptr,
                                      int* stats_parts = nullptr) {
   cv2::Params p{};
+  p.mask_off = -1;
   p.stats = stats; p.stats_parts = stats_parts;
   p.plan = plan_dev; p.fmt = operand_format_bits(); p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P_f; p.P_dst = P_c;
   p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.Wt = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = bias; p.Y = Y;
@@ -631,8 +676,9 @@ inline int launch_patch_conv2_s2_fwd(const int32_t* plan_dev, const GinP2Side& p
 
 // stride 2 dgrad, in-chart part: X is the coarse dy (K = Cout channels), Y the fine dx; Wf = 2n of the fine level
 inline int launch_patch_conv2_s2_dgrad(const int32_t* plan_dev, const GinP2Side& ps, int group, int P_f, int P_c, int Wf, const void* dYb,
-                                       const void* Wb, float* dX, int B, int K, int N, cudaStream_t st) {
+                                       const void* Wb, float* dX, int B, int K, int N, cudaStream_t st, const GinPfSide* pf = nullptr) {
   cv2::Params p{};
+  cv2_attach_boundary(p, pf);
   p.plan = plan_dev; p.fmt = operand_format_bits(); p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P_c; p.P_dst = P_f;
   p.X = reinterpret_cast<const __nv_bfloat16*>(dYb); p.Wt = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = nullptr; p.Y = dX;
   p.nplanes = 4; p.flush_each = 1; p.group_bytes = 1280; p.dst_tab_off = -1;
@@ -656,6 +702,7 @@ inline bool cv2_seam_supported(const GinPxSide& px, int K, int N) {
 inline int launch_patch_conv2_seam(const int32_t* plan_dev, const GinPxSide& px, int group, int P_src, int P_dst, const void* dYb, const void* Wb,
                                    float* dX, int B, int K, int N, cudaStream_t st) {
   cv2::Params p{};
+  p.mask_off = -1;
   p.plan = plan_dev; p.fmt = operand_format_bits(); p.U = GIN_TILE_M; p.Q = 1; p.ntiles = px.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P_src; p.P_dst = P_dst;
   p.X = reinterpret_cast<const __nv_bfloat16*>(dYb); p.Wt = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = nullptr; p.Y = dX;
   p.nplanes = px.nslots; p.flush_each = 0; p.group_bytes = 1024; p.accumulate = 1; p.dst_tab_off = px.dst_off;

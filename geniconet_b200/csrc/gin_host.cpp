@@ -216,6 +216,7 @@ bool build_conv(int level, int stride, int corner_mode, std::vector<int32_t>& bl
   // forward gather table: out pixel -> 7 sources
   std::vector<std::vector<Entry>> fwd(go.P), adj(gi.P), adjx(gi.P);   // adjx: entries that cross a chart seam / a pole
   std::vector<std::pair<int, int>> pole_readers[2];  // (out pixel, tap)
+  std::vector<char> is_boundary;                      // input-level pixels that own a cross-seam / pole entry of dgrad (filled with the seam plans)
   for (int k = 0; k < 5; ++k)
     for (int I = 0; I < go.n; ++I)
       for (int J = 0; J < go.W; ++J) {
@@ -343,7 +344,8 @@ bool build_conv(int level, int stride, int corner_mode, std::vector<int32_t>& bl
     // twice (the stitched corners) get one extra ROW per further entry, placed directly below the pixel's first row and inside
     // the same 32-row group (dst = -3): the epilogue warp that owns the group adds them to the row above before its single
     // read-modify-write, so the pass needs no atomics and its result does not depend on any execution order.
-    {
+    auto regular_form = [&](const std::vector<std::vector<Entry>>& only, int& out_ntiles, int& out_nslots, int8_t* out_tap,
+                            std::vector<int32_t>& xsrc, std::vector<int32_t>& xdst) -> bool {
       int slot_of_tap[7], nslots = 0;
       uint32_t taps_used = 0;
       for (const auto& row : only)
@@ -373,7 +375,8 @@ bool build_conv(int level, int stride, int corner_mode, std::vector<int32_t>& bl
             seq.emplace_back(sg, (int)i);
           }
         const int rows_total = (int)seq.size(), ntiles = (rows_total + GIN_TILE_M - 1) / GIN_TILE_M;
-        std::vector<int32_t> xsrc((size_t)ntiles * nslots * GIN_TILE_M, GIN_SRC_ZERO), xdst((size_t)ntiles * GIN_TILE_M, -1);
+        xsrc.assign((size_t)ntiles * nslots * GIN_TILE_M, GIN_SRC_ZERO);
+        xdst.assign((size_t)ntiles * GIN_TILE_M, -1);
         for (int r = 0; r < rows_total; ++r) {
           if (seq[r].first < 0) continue;
           const int sg = seq[r].first, t = r / GIN_TILE_M, rr = r % GIN_TILE_M;
@@ -384,16 +387,40 @@ bool build_conv(int level, int stride, int corner_mode, std::vector<int32_t>& bl
             xsrc[((size_t)t * nslots + slot_of_tap[e.tap]) * GIN_TILE_M + rr] = code;
           }
         }
-        GinPxSide& px = h.px;
-        px.ntiles = ntiles; px.nslots = nslots;
+        out_ntiles = ntiles; out_nslots = nslots;
         for (int t = 0; t < 7; ++t)
-          if (slot_of_tap[t] >= 0) px.tap[slot_of_tap[t]] = (int8_t)t;
-        px.src_off = (int)blob.size();
+          if (slot_of_tap[t] >= 0) out_tap[slot_of_tap[t]] = (int8_t)t;
+      }
+      return ok;
+    };
+    {
+      std::vector<int32_t> xsrc, xdst;
+      int nt = 0, ns = 0;
+      if (regular_form(only, nt, ns, h.px.tap, xsrc, xdst)) {
+        h.px.ntiles = nt; h.px.nslots = ns;
+        h.px.src_off = (int)blob.size();
         blob.insert(blob.end(), xsrc.begin(), xsrc.end());
-        px.dst_off = (int)blob.size();
+        h.px.dst_off = (int)blob.size();
         blob.insert(blob.end(), xdst.begin(), xdst.end());
       }
     }
+    // ---- one-launch dgrad (GinPfSide): the same boundary pixels carrying ALL their entries, and the store mask of the in-chart
+    // tiles (filled in below, once the in-chart tiles of this stride exist)
+    {
+      std::vector<std::vector<Entry>> full;
+      for (int v : pix) full.push_back(adj[v]);
+      std::vector<int32_t> xsrc, xdst;
+      int nt = 0, ns = 0;
+      if (regular_form(full, nt, ns, h.pf.tap, xsrc, xdst)) {
+        h.pf.ntiles = nt; h.pf.nslots = ns;
+        h.pf.src_off = (int)blob.size();
+        blob.insert(blob.end(), xsrc.begin(), xsrc.end());
+        h.pf.dst_off = (int)blob.size();
+        blob.insert(blob.end(), xdst.begin(), xdst.end());
+      }
+    }
+    is_boundary.assign((size_t)gi.P, 0);
+    for (int v : pix) is_boundary[v] = 1;
   }
   if (stride == 2 && go.s >= 2) {
     // ---- stride-2 patch tiles on the coarse lattice (see GinP2Side)
@@ -446,6 +473,35 @@ bool build_conv(int level, int stride, int corner_mode, std::vector<int32_t>& bl
     blob.insert(blob.end(), rows.begin(), rows.end());
     p2.frows_off = (int)blob.size();
     blob.insert(blob.end(), frows.begin(), frows.end());
+  }
+  if (h.pf.ntiles > 0) {
+    // ---- store mask of the in-chart dgrad tiles: the boundary pixels belong to the GinPfSide tiles
+    std::vector<uint32_t> mask;
+    if (stride == 1 && h.pdg.ntiles > 0) {
+      h.pf.nfl = 1;
+      mask.assign((size_t)h.pdg.ntiles * 4, 0u);
+      for (int t = 0; t < h.pdg.ntiles; ++t)
+        for (int r = 0; r < GIN_TILE_M; ++r) {
+          const int d = blob[(size_t)h.pdg.rows_off + (size_t)t * GIN_TILE_M + r];
+          if (d >= 0 && is_boundary[d % gi.P]) mask[(size_t)t * 4 + r / 32] |= 1u << (r % 32);
+        }
+    } else if (stride == 2 && h.p2.ntiles > 0) {
+      h.pf.nfl = 4;
+      const int Q = h.p2.Q;
+      mask.assign((size_t)h.p2.ntiles * 16, 0u);
+      for (int t = 0; t < h.p2.ntiles; ++t)
+        for (int pl = 0; pl < 4; ++pl)
+          for (int r = 0; r < GIN_TILE_M; ++r) {
+            const int g = r >> 3, r_in = g / Q, q = g % Q, px = r & 7;
+            const int fine = blob[(size_t)h.p2.frows_off + (size_t)t * Q + q] + r_in * 2 * gi.W + px * 2 + (pl >> 1) * gi.W + (pl & 1);
+            if (is_boundary[fine % gi.P]) mask[((size_t)t * 4 + pl) * 4 + r / 32] |= 1u << (r % 32);
+          }
+    }
+    if (mask.empty()) h.pf.ntiles = 0;            // no in-chart patch tiles at this size: the two-pass path stays
+    else {
+      h.pf.mask_off = (int)blob.size();
+      for (uint32_t w : mask) blob.push_back((int32_t)w);
+    }
   }
   h.magic = GIN_MAGIC; h.kind = GIN_PLAN_HEXCONV; h.level_in = level; h.level_out = go.s; h.stride = stride;
   h.corner_mode = corner_mode; h.group = group; h.total_words = (int)blob.size();

@@ -75,6 +75,24 @@ struct GinPxSide {
   int8_t tap[GIN_MAX_XSLOTS]; // weight index of each slot
 };
 
+// dgrad in ONE launch (r02): the patch kernel runs the in-chart tiles (GinPSide pdg / GinP2Side) and, appended to the same tile
+// list, the BOUNDARY tiles below.  A boundary pixel (any pixel with a cross-seam or pole entry) gets its COMPLETE gradient here --
+// in-chart and cross-seam entries alike, one slot per tap that occurs -- and the in-chart tiles skip its store (mask), so the two
+// tile classes write disjoint pixels: no read-modify-write, no ordering between tiles, no second launch.  Layout of src / dst as
+// in GinPxSide (extra rows with dst = -3 for a tap used more than once).
+//   mask[tile][fl][4]: 128 bits per output tile of the in-chart pass (fl = 0 for stride 1; the four parity classes of a
+//   stride-2 tile), bit r set = tile row r is a boundary pixel and is NOT stored by the in-chart pass.
+struct GinPfSide {
+  int32_t ntiles;             // boundary tiles per sample group (0 = not available: fall back to in-chart pass + GinPxSide pass)
+  int32_t nslots;             // <= GIN_MAX_XSLOTS
+  int32_t src_off;            // int32 src[ntiles][nslots][128]
+  int32_t dst_off;            // int32 dst[ntiles][128]
+  int32_t mask_off;           // uint32 mask[in-chart tiles per group][nfl][4]
+  int32_t nfl;                // 1 (stride 1) or 4 (stride 2)
+  int32_t pad_[2];
+  int8_t tap[GIN_MAX_XSLOTS];
+};
+
 struct GinConvPlanHdr {
   int32_t magic, kind, level_in, level_out, stride, corner_mode, group, total_words;
   GinSide fwd;                // y rows gathered from x   (also drives wgrad)
@@ -84,6 +102,7 @@ struct GinConvPlanHdr {
   GinSide dgx;                // ... plus the cross-seam / pole entries, ACCUMULATED on top by a gather-mode pass (both strides)
   GinP2Side p2;               // stride 2 only: forward / wgrad / in-chart dgrad in patch mode
   GinPxSide px;               // the same remainder as dgx, regular form (patch kernel, read-modify-write after the in-chart pass)
+  GinPfSide pf;               // boundary pixels with ALL their entries + the in-chart store mask: dgrad in one launch
 };
 
 struct GinUpPlanHdr {

@@ -391,3 +391,81 @@ def run_px_accumulate(blob, h, px, dy, Wd, dx):
                     k = 1 if int(dst[r - 1]) >= 0 else 2
                     assert r - k >= 0 and (r - k) // 32 == r // 32 and int(dst[r - k]) >= 0 and all(int(dst[r - j]) == -3 for j in range(0, k))
     return dx
+
+
+def parse_pf(blob):
+    """GinPfSide (words 64..75 of the conv plan header): one-launch dgrad."""
+    d = dict(zip(['ntiles', 'nslots', 'src_off', 'dst_off', 'mask_off', 'nfl'], [int(v) for v in blob[64:70]]))
+    d['tap'] = np.frombuffer(blob[72:76].tobytes(), dtype=np.int8)[:d['nslots']].astype(int)
+    return d
+
+
+def run_pf(blob, h, pf, dy, Wd, dx_inchart):
+    """One-launch dgrad as the patch kernel runs it: the in-chart tiles do NOT store the rows their mask flags; the boundary tiles
+    (GinPfSide) then store the complete gradient of exactly those pixels -- plain stores, each pixel written once overall."""
+    B = dy.shape[0]
+    group, stride = h['group'], h['stride']
+    P_src, P_dst = h['dg']['P_src'], h['dg']['P_dst']
+    ring = blob[h['dgx']['ring_off']:h['dgx']['ring_off'] + 10]
+    dx = dx_inchart.copy()
+    dxf = dx.reshape(B * P_dst, -1)
+    masked = set()
+    groups = (B + group - 1) // group
+    if stride == 1:
+        ps = h['pdg']
+        assert pf['nfl'] == 1
+        for G in range(groups):
+            for t in range(ps['ntiles']):
+                rows = blob[ps['rows_off'] + t * TILE: ps['rows_off'] + (t + 1) * TILE]
+                words = blob[pf['mask_off'] + t * 4: pf['mask_off'] + t * 4 + 4].astype(np.int64) & 0xffffffff
+                for r in range(TILE):
+                    if (int(words[r // 32]) >> (r % 32)) & 1:
+                        gd = G * group * P_dst + int(rows[r])
+                        if gd < B * P_dst:
+                            masked.add(gd)
+    else:
+        p2 = parse_p2(blob)
+        assert pf['nfl'] == 4
+        Q, Wf = p2['Q'], 2 << h['level_in']
+        for G in range(groups):
+            for t in range(p2['ntiles']):
+                fr = blob[p2['frows_off'] + t * Q: p2['frows_off'] + (t + 1) * Q]
+                for pl in range(4):
+                    words = blob[pf['mask_off'] + (t * 4 + pl) * 4: pf['mask_off'] + (t * 4 + pl) * 4 + 4].astype(np.int64) & 0xffffffff
+                    for r in range(TILE):
+                        if (int(words[r // 32]) >> (r % 32)) & 1:
+                            g, px = divmod(r, 8)
+                            r_in, q = divmod(g, Q)
+                            gd = G * group * P_dst + int(fr[q]) + r_in * 2 * Wf + 2 * px + (pl >> 1) * Wf + (pl & 1)
+                            if gd < B * P_dst:
+                                masked.add(gd)
+    for gd in masked:
+        dxf[gd] = np.nan                                   # not stored by the in-chart pass
+    written = set()
+    for G in range(groups):
+        for t in range(pf['ntiles']):
+            acc = np.zeros((TILE, Wd.shape[2]), dtype=dy.dtype)
+            for s in range(pf['nslots']):
+                off = pf['src_off'] + (t * pf['nslots'] + s) * TILE
+                acc += gather_rows(dy, blob[off:off + TILE], G * group, ring, P_src) @ Wd[pf['tap'][s]]
+            dst = blob[pf['dst_off'] + t * TILE: pf['dst_off'] + (t + 1) * TILE]
+            for r, d in enumerate(dst):
+                d = int(d)
+                if d < 0:
+                    assert d in (-1, -3)
+                    continue
+                tot = acc[r].copy()
+                for k in (1, 2):
+                    if (r + k) // 32 == r // 32 and r + k < TILE and all(int(dst[r + j]) == -3 for j in range(1, k + 1)):
+                        tot = tot + acc[r + k]
+                gd = G * group * P_dst + d
+                if gd < B * P_dst:
+                    assert gd in masked and gd not in written      # exactly the pixels the in-chart pass left out, once each
+                    written.add(gd)
+                    dxf[gd] = tot
+            for r, d in enumerate(dst):
+                if int(d) == -3:
+                    k = 1 if int(dst[r - 1]) >= 0 else 2
+                    assert r - k >= 0 and (r - k) // 32 == r // 32 and int(dst[r - k]) >= 0
+    assert written == masked
+    return dx

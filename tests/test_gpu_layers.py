@@ -367,7 +367,7 @@ def test_fused_bn_act_matches_torch(C, level, B, two):
         assert (dyb[B * P:].float() - gp).abs().max().item() <= 1e-2 * scale
 
 
-@pytest.mark.parametrize('env', [{'GIN_SEAM': 'gather'}, {'GIN_TC_MODE': 'patch1'}, {'GIN_TC_MODE': 'gather'}])
+@pytest.mark.parametrize('env', [{'GIN_SEAM': 'gather'}, {'GIN_SEAM': 'patch'}, {'GIN_TC_MODE': 'patch1'}, {'GIN_TC_MODE': 'gather'}, {'GIN_FWD_FP16': '0'}])
 def test_alternative_kernel_paths_match_oracle(env):
     """The A/B kernel selections (read once per process from the environment): signature-sorted gather seam pass (the default is the regular-form pass through the patch kernel),
     first-generation patch kernels, first-generation gather kernels -- each in a fresh process, conv fwd / dgrad / wgrad of a

@@ -81,6 +81,12 @@ def test_patch_plan_reproduces_oracle(case):
     assert px['ntiles'] > 0 and px['nslots'] <= 16
     dxe2 = pe.run_px_accumulate(blob, h, px, gyn, Wd, dxe.copy())            # + remainder, regular form (patch kernel)
     assert np.abs(dxe2 - dxn).max() < 1e-12
+    pf = pe.parse_pf(blob)                                                    # one-launch dgrad: masked in-chart tiles + boundary tiles
+    assert pf['ntiles'] > 0 and pf['nslots'] <= 16 and pf['nfl'] == (1 if stride == 1 else 4)
+    dxe3 = pe.run_pf(blob, h, pf, gyn, Wd, dxe)
+    assert not np.isnan(dxe3).any() and np.abs(dxe3 - dxn).max() < 1e-12
+    print('level %d stride %d: boundary tiles %d x %d slots per group of %d (in-chart tiles %d)' % (
+        lvl, stride, pf['ntiles'], pf['nslots'], h['group'], h['pdg']['ntiles'] if stride == 1 else pe.parse_p2(blob)['ntiles']))
     dxe = pe.run_side_accumulate(blob, h['dgx'], h['group'], gyn, Wd, dxe)   # + cross-seam / pole remainder (gather kernel)
     assert np.abs(dxe - dxn).max() < 1e-12
     assert np.abs(dWe - dWn).max() < 1e-10
