@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get('GIN_LIB') or os.path.join(_HERE, 'libgeniconet_b200.s
 
 PLAN_HEXCONV, PLAN_UPSAMPLE, PLAN_LOSS = 1, 2, 3
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+ERR_UNSUPPORTED = -4
 CORNER = {'zeros': 0, 'average': 1}
 
 
@@ -53,6 +54,7 @@ _SIGS = {
     'gin_hexconv_packed_bytes': (_sz, [_i, _i]),
     'gin_hexconv_pack_weights': (_i, [_vp, _vp, _i, _i, _vp]),
     'gin_hexconv_pack_weights_bf16': (_i, [_vp, _i, _vp, _i, _vp, _i, _vp]),
+    'gin_hexconv_pack_weights_bf16_multi': (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'gin_hexconv_fwd': (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'gin_hexconv_dgrad': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'gin_hexconv_wgrad_ws_bytes': (_sz, [_i, _i]),
@@ -64,6 +66,7 @@ _SIGS = {
     'gin_hexconv_fwd_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'gin_hexconv_stats_ws_bytes': (_sz, [_i]),
     'gin_hexconv_fwd_bf16_stats': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    'gin_hexconv_fwd_bf16_stats2': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
     'gin_bn_stats_from_parts': (_i, [_vp, _i, _i64, _i64, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     'gin_hexconv_dgrad_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'gin_hexconv_wgrad_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -204,6 +204,32 @@ int gin_hexconv_pack_weights_bf16(const float* w0, int Cout0, const float* w1, i
   return check_launch("pack_weights_bf16");
 }
 
+int gin_hexconv_pack_weights_bf16_multi(int n, const float* const* w0, const int* Cout0, const float* const* w1, const int* Cout1,
+                                        void* const* packed, const int* Cin, void* stream) {
+  if (n <= 0 || n > gin::PACK_MAX_JOBS || !w0 || !Cout0 || !w1 || !Cout1 || !packed || !Cin)
+    return fail(GIN_ERR_ARG, "gin_hexconv_pack_weights_bf16_multi: bad argument (1..%d jobs)", gin::PACK_MAX_JOBS);
+  gin::PackJobs J{};
+  J.n = n; J.fwd_f16 = (int)gin::fwd_fp16();
+  int blocks = 0;
+  for (int j = 0; j < n; ++j) {
+    const int Cout = Cout0[j] + Cout1[j];
+    if (!w0[j] || Cout0[j] <= 0 || Cout1[j] < 0 || (Cout1[j] > 0 && !w1[j]) || !packed[j] || Cin[j] <= 0 || (Cin[j] & 63) || (Cout & 63))
+      return fail(GIN_ERR_ARG, "gin_hexconv_pack_weights_bf16_multi: job %d: bad argument (channel counts must be multiples of 64)", j);
+    char* pk = reinterpret_cast<char*>(packed[j]);
+    J.w0[j] = w0[j]; J.w1[j] = w1[j]; J.cin[j] = Cin[j]; J.cout0[j] = Cout0[j]; J.cout[j] = Cout;
+    J.bf[j] = reinterpret_cast<unsigned short*>(pk + packed_off_bf(Cin[j], Cout));
+    J.bd[j] = reinterpret_cast<unsigned short*>(pk + packed_off_bd(Cin[j], Cout));
+    J.first[j] = blocks;
+    const long long nel = 7LL * Cin[j] * Cout;
+    int nb = (int)((nel + 256 * 8 - 1) / (256 * 8));           // 8 elements per thread
+    if (nb < 1) nb = 1;
+    blocks += nb;
+  }
+  J.first[n] = blocks;
+  gin::launch_pdl(gin::pack_weights_multi_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, J);
+  return check_launch("pack_weights_multi");
+}
+
 static int conv_hdr(const void* plan_host, const void* plan_dev, const GinConvPlanHdr** out) {
   if (!plan_dev) return fail(GIN_ERR_ARG, "null plan");
   const int32_t* w = plan_header(plan_host);
@@ -402,6 +428,24 @@ int gin_hexconv_fwd_bf16_stats(const void* plan_host, const void* plan_dev, cons
   if (rc) return rc;
   return run_gemm_tc(plan_words(plan_dev), h, xb, reinterpret_cast<const char*>(packed), B, false, bias, y, (cudaStream_t)stream, Cin, Cout, stats_ws,
                      nparts);
+}
+
+int gin_hexconv_fwd_bf16_stats2(const void* plan_host, const void* plan_dev, const void* xb, const void* packed, const float* bias0,
+                                const float* bias1, int split, float* y, int B, int Cin, int Cout, float* stats_ws, int* nparts, void* stream) {
+  if (!bias0 || !bias1 || split <= 0 || split >= Cout || (split & 63)) return fail(GIN_ERR_ARG, "gin_hexconv_fwd_bf16_stats2: bad bias split");
+  {
+    const GinConvPlanHdr* h;
+    int rc0 = conv_hdr(plan_host, plan_dev, &h);
+    if (rc0) return rc0;
+    const bool v2 = tc_mode() == 2 && gin::tc_supported(Cin, Cout) &&
+                    (h->stride == 1 ? (patch_mode_enabled() && gin::tcp_supported(h->pfwd, Cin, Cout) && gin::cv2_supported(h->pfwd, Cin, Cout))
+                                    : gin::cv2_supported(h->p2, Cin, Cout));
+    if (!v2) return fail(GIN_ERR_UNSUPPORTED, "gin_hexconv_fwd_bf16_stats2: this plan / size does not run the second-generation patch kernel");
+  }
+  gin::bias2_ref().p = bias1; gin::bias2_ref().split = split;
+  const int rc = gin_hexconv_fwd_bf16_stats(plan_host, plan_dev, xb, packed, bias0, y, B, Cin, Cout, stats_ws, nparts, stream);
+  gin::bias2_ref().p = nullptr; gin::bias2_ref().split = 0;
+  return rc;
 }
 
 int gin_hexconv_dgrad_bf16(const void* plan_host, const void* plan_dev, const void* dyb, const void* packed, float* dx, int B, int Cin, int Cout,

@@ -59,6 +59,8 @@ struct Params {
   const __nv_bfloat16* X;     // [B*P_src + 2B][K] bf16 (pixels, then pole-mean rows)
   const __nv_bfloat16* Wt;    // pre-swizzled bf16 tiles [7][K/64][N][64]
   const float* bias;
+  const float* bias1;         // optional: columns >= bias_split take bias1[col - bias_split] (two sibling convolutions as one GEMM)
+  int bias_split;
   float* Y;                   // [B*P_dst][N] fp32
   float* stats;               // optional [gridDim.x / n_blocks][2][N]: per-CTA column sums of y and y^2 (BatchNorm statistics)
   int nplanes, flush_each;    // nplanes <= MAX_PLANES
@@ -76,7 +78,7 @@ struct Params {
   // Second tile class (SEAM kernels: dgrad in one launch, gin_plan.h GinPfSide): x_total boundary tiles in regular form --
   // x_nslots segments of 128 gathered rows with one tap each, destination pixels from a table -- appended to the tile list after
   // the total_tiles patch tiles.  mask_off >= 0: plan words [ntiles][nflush][4], bit r set = the patch tile does not store row r.
-  int x_total, x_ntiles, x_nslots, x_src_off, x_dst_off, mask_off;
+  int x_total, x_ntiles, x_nslots, x_src_off, x_dst_off, mask_off, x_all;   // x_all: no patch tiles at all (every pixel is a boundary-form row)
   int8_t x_tap[MAX_PLANES];
   int* stats_parts;           // host: receives the number of per-CTA statistics rows written (0: none)
   int dbg;                    // GIN_DBG bit mask (experiments only): 1 no epilogue stores, 2 no patch loads, 4 no MMAs
@@ -421,7 +423,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
         }
         __syncwarp();
         float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + slab + c4));
+        if (p.bias) {
+          const int col = n0 + slab + c4;
+          bb = __ldg(reinterpret_cast<const float4*>((p.bias1 && col >= p.bias_split) ? p.bias1 + (col - p.bias_split) : p.bias + col));
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r2 = 4 * i + rsub;
@@ -603,7 +608,7 @@ inline bool cv2_pair_ok(const cv2::Params& p, int nt) {
 inline int cv2_dispatch(cv2::Params& p, int max_ntile, cudaStream_t st) {
   if ((long long)p.B * (p.P_src > p.P_dst ? p.P_src : p.P_dst) + 2LL * p.B >= 0x7fffffffLL) return -4;
   const int groups = (p.B + p.group - 1) / p.group;
-  p.total_tiles = groups * p.ntiles;
+  p.total_tiles = (p.x_ntiles > 0 && p.x_all) ? 0 : groups * p.ntiles;
   p.x_total = p.x_ntiles > 0 ? groups * p.x_ntiles : 0;
   { const char* e = getenv("GIN_DBG"); p.dbg = e ? atoi(e) : 0; }
   int nt = cv2_pick_ntile(p.total_tiles + p.x_total, p.N);
@@ -620,12 +625,17 @@ inline int cv2_dispatch(cv2::Params& p, int max_ntile, cudaStream_t st) {
 }
 
 // stride 1: forward (mirror 0) / in-chart dgrad (mirror 1: tap (di,dj) reads cell (-di,-dj)); W = 2n pixels per chart row
+// second bias of a concatenated forward (set by the C-ABI entry point around the launch; null otherwise)
+struct Bias2 { const float* p = nullptr; int split = 0; };
+inline Bias2& bias2_ref() { static thread_local Bias2 b; return b; }
+
 // `pf` (dgrad only): fold the boundary tiles of the plan into the same launch
 inline void cv2_attach_boundary(cv2::Params& p, const GinPfSide* pf) {
   p.mask_off = -1;
   if (!pf || pf->ntiles <= 0 || pf->nslots > cv2::MAX_PLANES) return;
   p.x_ntiles = pf->ntiles; p.x_nslots = pf->nslots; p.x_src_off = pf->src_off; p.x_dst_off = pf->dst_off; p.mask_off = pf->mask_off;
   for (int s = 0; s < pf->nslots; ++s) p.x_tap[s] = pf->tap[s];
+  p.x_all = pf->all;
 }
 
 inline int launch_patch_conv2(const int32_t* plan_dev, const GinPSide& ps, int group, int P, int W, const void* Xb, const void* Wb,
@@ -636,6 +646,7 @@ inline int launch_patch_conv2(const int32_t* plan_dev, const GinPSide& ps, int g
   p.stats = stats; p.stats_parts = stats_parts;
   p.plan = plan_dev; p.fmt = operand_format_bits(); p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P; p.P_dst = P;
   p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.Wt = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = bias; p.Y = Y;
+  if (bias) { p.bias1 = bias2_ref().p; p.bias_split = bias2_ref().split; }
   p.nplanes = 1; p.flush_each = 0; p.ntaps[0] = 7; p.group_bytes = 1280; p.dst_tab_off = -1;
   for (int t = 0; t < 7; ++t) {
     const int di = mirror ? -cv2::kDi[t] : cv2::kDi[t], dj = mirror ? -cv2::kDj[t] : cv2::kDj[t];
@@ -662,6 +673,7 @@ inline int launch_patch_conv2_s2_fwd(const int32_t* plan_dev, const GinP2Side& p
   p.stats = stats; p.stats_parts = stats_parts;
   p.plan = plan_dev; p.fmt = operand_format_bits(); p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P_f; p.P_dst = P_c;
   p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.Wt = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = bias; p.Y = Y;
+  if (bias) { p.bias1 = bias2_ref().p; p.bias_split = bias2_ref().split; }
   p.nplanes = 4; p.flush_each = 0; p.group_bytes = 1280; p.dst_tab_off = -1;
   for (int t = 0; t < 7; ++t) {
     const int pl = kS2Plane[t], j = p.ntaps[pl]++;

@@ -252,7 +252,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_pair_kernel(const Para
           }
           __syncwarp();
           float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + slab + c4));
+        if (p.bias) {
+          const int col = n0 + slab + c4;
+          bb = __ldg(reinterpret_cast<const float4*>((p.bias1 && col >= p.bias_split) ? p.bias1 + (col - p.bias_split) : p.bias + col));
+        }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r2 = 4 * i + rsub;

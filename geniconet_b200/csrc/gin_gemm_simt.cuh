@@ -328,6 +328,46 @@ __global__ void pack_weights_bf16_kernel(const float* __restrict__ w0, int Cout0
   }
 }
 
+// The same for up to PACK_MAX_JOBS weights in ONE launch (a fused chain packs ~12 weights per step; launched one by one they
+// cost ~8 us each of pure launch latency).  Job j owns blocks [first[j], first[j+1]); descriptors travel as kernel parameters.
+constexpr int PACK_MAX_JOBS = 24;
+struct PackJobs {
+  const float* w0[PACK_MAX_JOBS];
+  const float* w1[PACK_MAX_JOBS];
+  unsigned short* bf[PACK_MAX_JOBS];
+  unsigned short* bd[PACK_MAX_JOBS];
+  int cin[PACK_MAX_JOBS], cout0[PACK_MAX_JOBS], cout[PACK_MAX_JOBS];
+  int first[PACK_MAX_JOBS + 1];
+  int n, fwd_f16;
+};
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackJobs J) {
+  GIN_PDL_SYNC();
+  int j = 0;
+  while (j + 1 < J.n && (int)blockIdx.x >= J.first[j + 1]) ++j;
+  const int Cin = J.cin[j], Cout = J.cout[j], Cout0 = J.cout0[j];
+  const float* __restrict__ w0 = J.w0[j];
+  const float* __restrict__ w1 = J.w1[j];
+  unsigned short* __restrict__ bf = J.bf[j];
+  unsigned short* __restrict__ bd = J.bd[j];
+  const long long n = (long long)Cin * Cout * 7;
+  const int nb = J.first[j + 1] - J.first[j];
+  for (long long i = (long long)(blockIdx.x - J.first[j]) * 256 + threadIdx.x; i < n; i += (long long)nb * 256) {
+    const int t = (int)(i % 7);
+    const long long r = i / 7;
+    const int ci = (int)(r % Cin), co = (int)(r / Cin);
+    const float v = co < Cout0 ? w0[i] : w1[i - (long long)Cout0 * Cin * 7];
+    const unsigned short h = cvt_op(v, 0), hf = cvt_op(v, J.fwd_f16);
+    {
+      const int kc = ci >> 6, c = (ci >> 3) & 7, e = ci & 7;
+      bf[((((size_t)t * (Cin >> 6) + kc) * Cout + co) << 6) + (((c ^ (co & 7)) << 3) | e)] = hf;
+    }
+    {
+      const int kc = co >> 6, c = (co >> 3) & 7, e = co & 7;
+      bd[((((size_t)t * (Cout >> 6) + kc) * Cin + ci) << 6) + (((c ^ (ci & 7)) << 3) | e)] = h;
+    }
+  }
+}
+
 // dWp[7][Cin][Cout] -> dW[Cout][Cin][7]
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dWp, float* __restrict__ dW, int Cin, int Cout) {
   const long long n = (long long)Cin * Cout * 7;

@@ -406,6 +406,13 @@ bool build_conv(int level, int stride, int corner_mode, std::vector<int32_t>& bl
     }
     // ---- one-launch dgrad (GinPfSide): the same boundary pixels carrying ALL their entries, and the store mask of the in-chart
     // tiles (filled in below, once the in-chart tiles of this stride exist)
+    // At levels <= 3 (stride 1) more than a third of all pixels are boundary pixels: there the boundary form takes EVERY pixel and
+    // the in-chart tiles are dropped altogether (pf.all = 1) -- 5 tile-units per 640 pixels instead of 5 + 3.
+    const bool take_all = stride == 1 && level <= 3;
+    if (take_all) {
+      pix.clear();
+      for (int v = 0; v < gi.P; ++v) pix.push_back(v);
+    }
     {
       std::vector<std::vector<Entry>> full;
       for (int v : pix) full.push_back(adj[v]);
@@ -417,6 +424,7 @@ bool build_conv(int level, int stride, int corner_mode, std::vector<int32_t>& bl
         blob.insert(blob.end(), xsrc.begin(), xsrc.end());
         h.pf.dst_off = (int)blob.size();
         blob.insert(blob.end(), xdst.begin(), xdst.end());
+        h.pf.all = take_all ? 1 : 0;
       }
     }
     is_boundary.assign((size_t)gi.P, 0);

@@ -89,7 +89,8 @@ struct GinPfSide {
   int32_t dst_off;            // int32 dst[ntiles][128]
   int32_t mask_off;           // uint32 mask[in-chart tiles per group][nfl][4]
   int32_t nfl;                // 1 (stride 1) or 4 (stride 2)
-  int32_t pad_[2];
+  int32_t all;                // 1: the boundary tiles cover EVERY pixel (small levels); the in-chart tiles are not run at all
+  int32_t pad_;
   int8_t tap[GIN_MAX_XSLOTS];
 };
 

@@ -93,12 +93,42 @@ def _pack_bf16(w0, w1, cin):
     return packed
 
 
-def _conv_fwd(plan, xb, packed, bias, B, cin, cout, p_out):
-    """Returns (y fp32 [B*p_out][cout], per-CTA BatchNorm partial sums [nparts][2][cout] or None)."""
+def _pack_many(jobs):
+    """jobs: list of (w0, w1 or None, cin) -> list of packed blobs (16-bit tile images only), ONE launch for all of them."""
+    import ctypes
+    n = len(jobs)
+    if n == 0:
+        return []
+    if n > 24:
+        return _pack_many(jobs[:24]) + _pack_many(jobs[24:])
+    dev = jobs[0][0].device
+    outs = [_empty(L.gin_hexconv_packed_bytes(cin, w0.shape[0] + (w1.shape[0] if w1 is not None else 0)), torch.uint8, dev) for w0, w1, cin in jobs]
+    P, I = ctypes.c_void_p * n, ctypes.c_int * n
+    w0s = P(*[w0.data_ptr() for w0, _, _ in jobs])
+    w1s = P(*[(w1.data_ptr() if w1 is not None else None) for _, w1, _ in jobs])
+    c0 = I(*[w0.shape[0] for w0, _, _ in jobs])
+    c1 = I(*[(w1.shape[0] if w1 is not None else 0) for _, w1, _ in jobs])
+    pk = P(*[o.data_ptr() for o in outs])
+    ci = I(*[cin for _, _, cin in jobs])
+    _lib.check(L.gin_hexconv_pack_weights_bf16_multi(n, w0s, c0, w1s, c1, pk, ci, _stream()), 'gin_hexconv_pack_weights_bf16_multi')
+    return outs
+
+
+def _conv_fwd(plan, xb, packed, bias, B, cin, cout, p_out, bias1=None):
+    """Returns (y fp32 [B*p_out][cout], per-CTA BatchNorm partial sums [nparts][2][cout] or None).  With `bias1` the output
+    channels are two sibling convolutions side by side: `bias` belongs to the first half, `bias1` to the second."""
     import ctypes
     y = _empty((B * p_out, cout), torch.float32, xb.device)
     parts = _empty(L.gin_hexconv_stats_ws_bytes(cout) // 4, torch.float32, xb.device)
     n = ctypes.c_int(0)
+    if bias1 is not None:
+        rc = L.gin_hexconv_fwd_bf16_stats2(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), packed.data_ptr(), bias.data_ptr(), bias1.data_ptr(), cout // 2,
+                                           y.data_ptr(), B, cin, cout, parts.data_ptr(), ctypes.addressof(n), _stream())
+        if rc == 0:
+            return y, ((parts, n.value) if n.value > 0 else None)
+        if rc != _lib.ERR_UNSUPPORTED:
+            _lib.check(rc, 'gin_hexconv_fwd_bf16_stats2')
+        bias = torch.cat((bias, bias1), 0)               # a kernel generation without the second bias pointer
     _lib.check(L.gin_hexconv_fwd_bf16_stats(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), packed.data_ptr(), bias.data_ptr(), y.data_ptr(), B, cin, cout,
                                             parts.data_ptr(), ctypes.addressof(n), _stream()), 'gin_hexconv_fwd_bf16_stats')
     return y, ((parts, n.value) if n.value > 0 else None)
@@ -240,6 +270,12 @@ class _Chain(torch.autograd.Function):
             act_f = _acl(x).permute(0, 2, 3, 1).reshape(-1, C)
         last = len(mods) - 1
         out_f = None
+        # every weight of the chain's tensor-core convolutions is packed by ONE launch
+        jobs = []
+        for blk in mods[i:]:
+            jobs.append((blk.conv00.weight.detach().contiguous(), blk.conv10.weight.detach().contiguous(), blk.conv00.in_features))
+            jobs.append((blk.conv01.weight.detach().contiguous(), None, blk.conv01.in_features))
+        packs = _pack_many(jobs)
         for j in range(i, len(mods)):
             blk = mods[j]
             cm = blk.conv00.corner_mode
@@ -261,13 +297,11 @@ class _Chain(torch.autograd.Function):
                 st['up_plan'] = up_plan
             plan_b = get_plan(_lib.PLAN_HEXCONV, lvl, 1, cm, dev)
             rows = B * _P(lvl)
-            bcat = torch.cat((blk.conv00.bias.detach(), blk.conv10.bias.detach()), 0)
-            pk_cat = _pack_bf16(blk.conv00.weight.detach().contiguous(), blk.conv10.weight.detach().contiguous(), cin)
-            ycat, pcat = _conv_fwd(plan_a, a_b, pk_cat, bcat, B, cin, 2 * cout, _P(lvl))    # [rows][conv00 | conv10]
+            pk_cat, pk01 = packs[2 * (j - i)], packs[2 * (j - i) + 1]
+            ycat, pcat = _conv_fwd(plan_a, a_b, pk_cat, blk.conv00.bias.detach(), B, cin, 2 * cout, _P(lvl), bias1=blk.conv10.bias.detach())   # [rows][conv00 | conv10]
             stat00 = _bn_stats(ycat, 0, 2 * cout, rows, cout, blk.icobn00, pcat)
             stat10 = _bn_stats(ycat, cout, 2 * cout, rows, cout, blk.icobn10, pcat)
             h_b, _, h_w = _bn_act(ycat, 0, 2 * cout, stat00, None, 0, 0, None, B, lvl, cout)
-            pk01 = _pack_bf16(blk.conv01.weight.detach().contiguous(), None, cout)
             y01, p01 = _conv_fwd(plan_b, h_b, pk01, blk.conv01.bias.detach(), B, cout, cout, _P(lvl))
             stat01 = _bn_stats(y01, 0, cout, rows, cout, blk.icobn01, p01)
             is_last = j == last
@@ -298,6 +332,8 @@ class _Chain(torch.autograd.Function):
         dx = None
         side = _wgrad_stream(d.device)
         plist = chain_params(ctx.mods)          # the Parameter objects, in the order of the gradients this function returns
+        zmax = max([st['cout'] for st in saved if st['kind'] in ('down', 'up')] + [1])
+        zeros = torch.zeros(zmax, dtype=torch.float32, device=d.device)     # the (exactly zero) gradients of conv biases that feed a BatchNorm
         for st in reversed(saved):
             n_before = len(grads)
             if st['kind'] in ('down', 'up'):
@@ -324,7 +360,7 @@ class _Chain(torch.autograd.Function):
                     d_prev = torch.empty((B * _P(st['in_level']), cin), dtype=torch.float32, device=dev)
                     _lib.check(L.gin_upsample_bwd(upp.host_ptr, upp.dev_ptr, d_in.data_ptr(), d_prev.data_ptr(), B, cin, _stream()), 'gin_upsample_bwd')
                     d_in = d_prev
-                zero_b = torch.zeros(cout, dtype=torch.float32, device=dev)
+                zero_b = zeros[:cout]
                 # parameter order of chain_params: conv00 (w, b, gamma, beta), conv01 (...), conv10 (...); appended reversed
                 grads += [bs10[:cout], bs10[cout:2 * cout], zero_b, dWcat[cout:],
                           bs01[:cout], bs01[cout:2 * cout], zero_b, dW01,

@@ -87,6 +87,9 @@ int gin_hexconv_pack_weights(const float* weight, void* packed, int Cin, int Cou
  * fused chains run the two sibling convolutions of a residual block (models.py:25-33, 45-55) as one GEMM.  Channel counts
  * must be multiples of 64; `packed` has gin_hexconv_packed_bytes(Cin, Cout0 + Cout1) bytes (the fp32 parts stay unwritten). */
 int gin_hexconv_pack_weights_bf16(const float* w0, int Cout0, const float* w1, int Cout1, void* packed, int Cin, void* stream);
+/* The same for n <= 24 weights in ONE launch (host arrays of n entries each; w1[j] may be NULL with Cout1[j] = 0). */
+int gin_hexconv_pack_weights_bf16_multi(int n, const float* const* w0, const int* Cout0, const float* const* w1, const int* Cout1,
+                                        void* const* packed, const int* Cin, void* stream);
 
 /* IcoConvS2S.forward (models.py:14,25-33,45-55,104,165,269,279): rows a1+a2+a3.
  * y[b,p,:] = bias + sum_t W_t^T x~[b, p+t, :] with the padding fused into the gather. */
@@ -127,6 +130,11 @@ int gin_hexconv_fwd_bf16(const void* plan_host, const void* plan_dev, const void
 size_t gin_hexconv_stats_ws_bytes(int Cout);
 int gin_hexconv_fwd_bf16_stats(const void* plan_host, const void* plan_dev, const void* xb, const void* packed, const float* bias,
                                float* y, int B, int Cin, int Cout, float* stats_ws, int* nparts, void* stream);
+/* The same for two sibling convolutions run as ONE GEMM with concatenated output channels: columns [0, split) take bias0,
+ * columns [split, Cout) take bias1 (no concatenated bias tensor has to be built).  Needs a plan whose forward runs in patch mode. */
+int gin_hexconv_fwd_bf16_stats2(const void* plan_host, const void* plan_dev, const void* xb, const void* packed, const float* bias0,
+                                const float* bias1, int split, float* y, int B, int Cin, int Cout, float* stats_ws, int* nparts,
+                                void* stream);
 int gin_hexconv_dgrad_bf16(const void* plan_host, const void* plan_dev, const void* dyb, const void* packed, float* dx,
                            int B, int Cin, int Cout, void* stream);
 /* dy (fp32) is only read for db and may be NULL when db is NULL */

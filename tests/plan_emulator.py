@@ -395,7 +395,7 @@ def run_px_accumulate(blob, h, px, dy, Wd, dx):
 
 def parse_pf(blob):
     """GinPfSide (words 64..75 of the conv plan header): one-launch dgrad."""
-    d = dict(zip(['ntiles', 'nslots', 'src_off', 'dst_off', 'mask_off', 'nfl'], [int(v) for v in blob[64:70]]))
+    d = dict(zip(['ntiles', 'nslots', 'src_off', 'dst_off', 'mask_off', 'nfl', 'all'], [int(v) for v in blob[64:71]]))
     d['tap'] = np.frombuffer(blob[72:76].tobytes(), dtype=np.int8)[:d['nslots']].astype(int)
     return d
 
@@ -408,6 +408,8 @@ def run_pf(blob, h, pf, dy, Wd, dx_inchart):
     P_src, P_dst = h['dg']['P_src'], h['dg']['P_dst']
     ring = blob[h['dgx']['ring_off']:h['dgx']['ring_off'] + 10]
     dx = dx_inchart.copy()
+    if pf['all']:                                          # small levels: the in-chart tiles are not run at all
+        dx[:] = np.nan
     dxf = dx.reshape(B * P_dst, -1)
     masked = set()
     groups = (B + group - 1) // group
@@ -468,4 +470,6 @@ def run_pf(blob, h, pf, dy, Wd, dx_inchart):
                     k = 1 if int(dst[r - 1]) >= 0 else 2
                     assert r - k >= 0 and (r - k) // 32 == r // 32 and int(dst[r - k]) >= 0
     assert written == masked
+    if pf['all']:
+        assert len(written) == B * P_dst
     return dx
