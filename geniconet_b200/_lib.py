@@ -66,16 +66,16 @@ _SIGS = {
     'gin_hexconv_fwd_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'gin_hexconv_stats_ws_bytes': (_sz, [_i]),
     'gin_hexconv_fwd_bf16_stats': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
-    'gin_hexconv_fwd_bf16_stats2': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    'gin_hexconv_fwd_bf16_stats2': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     'gin_bn_stats_from_parts': (_i, [_vp, _i, _i64, _i64, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     'gin_hexconv_dgrad_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'gin_hexconv_wgrad_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'gin_bn_ws_bytes': (_sz, [_i]),
     'gin_bn_stats': (_i, [_vp, _i64, _i64, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
-    'gin_bn_act_fwd': (_i, [_vp, _i64, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    'gin_bn_act_bwd': (_i, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _vp]),
+    'gin_bn_act_fwd': (_i, [_vp, _i64, _vp, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    'gin_bn_act_bwd': (_i, [_vp, _i64, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _vp]),
     'gin_bn_pair_ws_bytes': (_sz, [_i]),
-    'gin_bn_act_bwd_pair': (_i, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i, _i, _i, _vp]),
+    'gin_bn_act_bwd_pair': (_i, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i, _vp, _i, _i, _i, _vp]),
     'gin_upsample_bf16': (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
     'gin_upsample_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     'gin_upsample_bwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),

@@ -431,8 +431,9 @@ int gin_hexconv_fwd_bf16_stats(const void* plan_host, const void* plan_dev, cons
 }
 
 int gin_hexconv_fwd_bf16_stats2(const void* plan_host, const void* plan_dev, const void* xb, const void* packed, const float* bias0,
-                                const float* bias1, int split, float* y, int B, int Cin, int Cout, float* stats_ws, int* nparts, void* stream) {
-  if (!bias0 || !bias1 || split <= 0 || split >= Cout || (split & 63)) return fail(GIN_ERR_ARG, "gin_hexconv_fwd_bf16_stats2: bad bias split");
+                                const float* bias1, int split, void* y, int y_fp16, int B, int Cin, int Cout, float* stats_ws, int* nparts,
+                                void* stream) {
+  if (!bias0 || (bias1 && (split <= 0 || split >= Cout || (split & 63)))) return fail(GIN_ERR_ARG, "gin_hexconv_fwd_bf16_stats2: bad bias split");
   {
     const GinConvPlanHdr* h;
     int rc0 = conv_hdr(plan_host, plan_dev, &h);
@@ -442,9 +443,9 @@ int gin_hexconv_fwd_bf16_stats2(const void* plan_host, const void* plan_dev, con
                                     : gin::cv2_supported(h->p2, Cin, Cout));
     if (!v2) return fail(GIN_ERR_UNSUPPORTED, "gin_hexconv_fwd_bf16_stats2: this plan / size does not run the second-generation patch kernel");
   }
-  gin::bias2_ref().p = bias1; gin::bias2_ref().split = split;
-  const int rc = gin_hexconv_fwd_bf16_stats(plan_host, plan_dev, xb, packed, bias0, y, B, Cin, Cout, stats_ws, nparts, stream);
-  gin::bias2_ref().p = nullptr; gin::bias2_ref().split = 0;
+  gin::bias2_ref().p = bias1; gin::bias2_ref().split = bias1 ? split : 0; gin::bias2_ref().y_f16 = y_fp16 ? 1 : 0;
+  const int rc = gin_hexconv_fwd_bf16_stats(plan_host, plan_dev, xb, packed, bias0, reinterpret_cast<float*>(y), B, Cin, Cout, stats_ws, nparts, stream);
+  gin::bias2_ref() = gin::Bias2{};
   return rc;
 }
 
@@ -616,7 +617,7 @@ int gin_bn_stats(const float* y, int64_t ld, int64_t rows, int C, const float* g
   cudaStream_t st = (cudaStream_t)stream;
   if (!y || !stat || !ws || rows <= 0 || !bn_shape_ok(C) || ld < C || (ld & 3)) return fail(GIN_ERR_ARG, "gin_bn_stats: bad argument (C/8 must divide 256)");
   const int ctas = gin::bn::grid_for_rows(rows * (C >> 3));
-  gin::launch_pdl(gin::bn::stats_kernel, dim3(ctas), dim3(256), 0, st, gin::bn::Src{y, (long long)ld}, rows, C, reinterpret_cast<float*>(ws));
+  gin::launch_pdl(gin::bn::stats_kernel, dim3(ctas), dim3(256), 0, st, gin::bn::Src{y, (long long)ld, 0}, rows, C, reinterpret_cast<float*>(ws));
   int rc = check_launch("bn_stats");
   if (rc) return rc;
   gin::launch_pdl(gin::bn::stats_final_kernel, dim3(C / 8), dim3(256), 0, st, reinterpret_cast<const float*>(ws), ctas, rows, C, gamma, beta, eps, momentum, running_mean,
@@ -635,28 +636,28 @@ int gin_bn_stats_from_parts(const float* parts, int nparts, int64_t ld, int64_t 
   return check_launch("bn_stats_final");
 }
 
-int gin_bn_act_fwd(const float* y1, int64_t ld1, const float* stat1, const float* y2, int64_t ld2, const float* stat2, int relu, void* out_b,
+int gin_bn_act_fwd(const void* y1, int64_t ld1, const float* stat1, const void* y2, int64_t ld2, const float* stat2, int y_fp16, int relu, void* out_b,
                    float* out_f, void* out_w, int B, int level, int C, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (!y1 || !stat1 || (y2 && !stat2) || (!out_b && !out_f && !out_w) || B <= 0 || level < 0 || level > 9 || !bn_shape_ok(C))
     return fail(GIN_ERR_ARG, "gin_bn_act_fwd: bad argument");
   const int n = 1 << level, P = 10 << (2 * level);
   const int ctas = gin::bn::grid_for_rows(((long long)B * P + 2LL * B) * (C >> 3));
-  const gin::bn::Src s1{y1, (long long)ld1}, s2{y2, (long long)ld2};
+  const gin::bn::Src s1{reinterpret_cast<const float*>(y1), (long long)ld1, y_fp16 ? 1 : 0}, s2{reinterpret_cast<const float*>(y2), (long long)ld2, y_fp16 ? 1 : 0};
   const int f16 = (int)gin::fwd_fp16();          // out_b is the next convolution's FORWARD operand copy
   if (y2) gin::launch_pdl(gin::bn::act_fwd_kernel<true>, dim3(ctas), dim3(256), 0, st, s1, stat1, s2, stat2, relu, reinterpret_cast<__nv_bfloat16*>(out_b), out_f, n, B, P, C, f16, reinterpret_cast<__nv_bfloat16*>(out_w));
   else gin::launch_pdl(gin::bn::act_fwd_kernel<false>, dim3(ctas), dim3(256), 0, st, s1, stat1, s2, stat2, relu, reinterpret_cast<__nv_bfloat16*>(out_b), out_f, n, B, P, C, f16, reinterpret_cast<__nv_bfloat16*>(out_w));
   return check_launch("bn_act_fwd");
 }
 
-int gin_bn_act_bwd(const float* dout, int64_t ldg, const void* mask_b, const float* y, int64_t ld, const float* stat, float* bstat, void* dy_b,
+int gin_bn_act_bwd(const float* dout, int64_t ldg, const void* mask_b, const void* y, int64_t ld, int y_fp16, const float* stat, float* bstat, void* dy_b,
                    int64_t ldo, float* dy_f, int64_t ldf, void* ws, int B, int level, int C, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (!dout || !y || !stat || !bstat || !ws || (!dy_b && !dy_f) || B <= 0 || level < 0 || level > 9 || !bn_shape_ok(C))
     return fail(GIN_ERR_ARG, "gin_bn_act_bwd: bad argument");
   const int n = 1 << level, P = 10 << (2 * level);
   const long long rows = (long long)B * P;
-  const gin::bn::Src sy{y, (long long)ld};
+  const gin::bn::Src sy{reinterpret_cast<const float*>(y), (long long)ld, y_fp16 ? 1 : 0};
   const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(mask_b);
   const int ctas = gin::bn::grid_for_rows(rows * (C >> 3));
   gin::launch_pdl(gin::bn::bwd_reduce_kernel, dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sy, stat, rows, C, reinterpret_cast<float*>(ws));
@@ -670,15 +671,15 @@ int gin_bn_act_bwd(const float* dout, int64_t ldg, const void* mask_b, const flo
 
 size_t gin_bn_pair_ws_bytes(int C) { return C <= 0 ? 0 : (size_t)gin::bn::MAX_CTAS * 4 * C * 4; }
 
-int gin_bn_act_bwd_pair(const float* dout, int64_t ldg, const void* mask_b, const float* yA, int64_t ldA, const float* statA, float* bstatA,
-                        void* dyA_b, int64_t ldoA, const float* yB, int64_t ldB, const float* statB, float* bstatB, void* dyB_b, int64_t ldoB,
-                        void* ws, int B, int level, int C, void* stream) {
+int gin_bn_act_bwd_pair(const float* dout, int64_t ldg, const void* mask_b, const void* yA, int64_t ldA, const float* statA, float* bstatA,
+                        void* dyA_b, int64_t ldoA, const void* yB, int64_t ldB, const float* statB, float* bstatB, void* dyB_b, int64_t ldoB,
+                        int y_fp16, void* ws, int B, int level, int C, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (!dout || !yA || !yB || !statA || !statB || !bstatA || !bstatB || !dyA_b || !dyB_b || !ws || B <= 0 || level < 0 || level > 9 || !bn_shape_ok(C))
     return fail(GIN_ERR_ARG, "gin_bn_act_bwd_pair: bad argument");
   const int n = 1 << level, P = 10 << (2 * level);
   const long long rows = (long long)B * P;
-  const gin::bn::Src sA{yA, (long long)ldA}, sB{yB, (long long)ldB};
+  const gin::bn::Src sA{reinterpret_cast<const float*>(yA), (long long)ldA, y_fp16 ? 1 : 0}, sB{reinterpret_cast<const float*>(yB), (long long)ldB, y_fp16 ? 1 : 0};
   const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(mask_b);
   const int ctas = gin::bn::grid_for_rows(rows * (C >> 3));
   gin::launch_pdl(gin::bn::bwd_reduce2_kernel, dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sA, statA, sB, statB, rows, C, reinterpret_cast<float*>(ws));

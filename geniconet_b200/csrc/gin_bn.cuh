@@ -27,9 +27,10 @@ namespace bn {
 
 constexpr int MAX_CTAS = 148 * 4;          // upper bound (sizes the partial-sum buffers); the grid actually used: bn_ctas()
 
-struct Src {               // a [rows][C] fp32 view inside a wider row-major matrix
-  const float* p;
-  long long ld;            // row stride in floats
+struct Src {               // a [rows][C] view inside a wider row-major matrix: fp32, or fp16 (f16 != 0: conv outputs of the fused chains)
+  const float* p;          // for f16 sources the pointer is reinterpreted
+  long long ld;            // row stride in ELEMENTS
+  int f16;
 };
 
 // pixel e (0..4) of the ring of `pole` on a level with n = 2^level: chart e, first pixel of row 0 / last pixel of row n-1
@@ -71,6 +72,14 @@ GIN_DEVINL void ld8_mask(const __nv_bfloat16* p, bool m[8]) {
 GIN_DEVINL void ld8_op(const __nv_bfloat16* p, float v[8], int f16) {
   if (!f16) { ld8_bf16(p, v); return; }
   const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+// 8 consecutive channels of row r of a source
+GIN_DEVINL void ld8_src(const Src& s, long long r, int c, float v[8]) {
+  if (!s.f16) { ld8(s.p + r * s.ld + c, v); return; }
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(s.p) + r * s.ld + c));
   const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
   for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
@@ -133,7 +142,7 @@ __global__ void __launch_bounds__(256) stats_kernel(Src y, long long rows, int C
     const long long r = i / C8;
     const int c = (int)(i - r * C8) * 8;
     float v[8];
-    ld8(y.p + r * y.ld + c, v);
+    ld8_src(y, r, c, v);
 #pragma unroll
     for (int k = 0; k < 8; ++k) { s0[k] += v[k]; s1[k] = fmaf(v[k], v[k], s1[k]); }
   }
@@ -176,11 +185,11 @@ template <bool TWO>
 GIN_DEVINL void apply_row(const Src& y1, const Src& y2, long long r, int c, const float sc1[8], const float sh1[8], const float sc2[8],
                           const float sh2[8], int relu, float o[8]) {
   float v[8];
-  ld8(y1.p + r * y1.ld + c, v);
+  ld8_src(y1, r, c, v);
 #pragma unroll
   for (int k = 0; k < 8; ++k) o[k] = fmaf(v[k], sc1[k], sh1[k]);
   if (TWO) {
-    ld8(y2.p + r * y2.ld + c, v);
+    ld8_src(y2, r, c, v);
 #pragma unroll
     for (int k = 0; k < 8; ++k) o[k] += fmaf(v[k], sc2[k], sh2[k]);
   }
@@ -236,7 +245,7 @@ GIN_DEVINL void grad_row(const float* __restrict__ dout, long long ldg, const __
     for (int k = 0; k < 8; ++k) g[k] = m[k] ? g[k] : 0.f;
   }
   float v[8];
-  ld8(y.p + r * y.ld + c, v);
+  ld8_src(y, r, c, v);
 #pragma unroll
   for (int k = 0; k < 8; ++k) yh[k] = (v[k] - mean[k]) * invstd[k];
 }
@@ -403,7 +412,7 @@ bwd_reduce2_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfl
     const long long r = i / C8;
     float g[8], yh[8], v[8];
     grad_row(dout, ldg, mask, yA, r, c, C, meanA, invA, g, yh);
-    ld8(yB.p + r * yB.ld + c, v);
+    ld8_src(yB, r, c, v);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       s0[k] += g[k];
@@ -473,7 +482,7 @@ bwd_apply2_kernel(const float* __restrict__ dout, long long ldg, const __nv_bflo
       const long long r = i / C8;
       float g[8], yh[8], v[8];
       grad_row(dout, ldg, mask, yA, r, c, C, meanA, invA, g, yh);
-      ld8(yB.p + r * yB.ld + c, v);
+      ld8_src(yB, r, c, v);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         oA[k] = scA[k] * (g[k] - c1A[k] - yh[k] * c2A[k]);
@@ -488,7 +497,7 @@ bwd_apply2_kernel(const float* __restrict__ dout, long long ldg, const __nv_bflo
         const long long r = (long long)sample * P + ring_pixel(nlat, pole, e);
         float g[8], yh[8], v[8];
         grad_row(dout, ldg, mask, yA, r, c, C, meanA, invA, g, yh);
-        ld8(yB.p + r * yB.ld + c, v);
+        ld8_src(yB, r, c, v);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           oA[k] = fmaf(0.2f * scA[k], g[k] - c1A[k] - yh[k] * c2A[k], oA[k]);

@@ -27,6 +27,8 @@
 //   8 epilogue warps (tcgen05.ld -> smem transpose -> +bias -> coalesced fp32 stores).
 // Two TMEM accumulators of N_TILE columns: the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "gin_gemm_tc.cuh"
 
 namespace gin {
@@ -61,7 +63,8 @@ struct Params {
   const float* bias;
   const float* bias1;         // optional: columns >= bias_split take bias1[col - bias_split] (two sibling convolutions as one GEMM)
   int bias_split;
-  float* Y;                   // [B*P_dst][N] fp32
+  float* Y;                   // [B*P_dst][N] fp32, or fp16 when y_f16 (forward outputs that only a BatchNorm reads: half the bytes)
+  int y_f16;
   float* stats;               // optional [gridDim.x / n_blocks][2][N]: per-CTA column sums of y and y^2 (BatchNorm statistics)
   int nplanes, flush_each;    // nplanes <= MAX_PLANES
   int group_bytes;            // distance between the 8-row groups of a tile inside the image: 1280 (patch) or 1024 (gathered rows)
@@ -448,7 +451,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
             const float4 old = *reinterpret_cast<const float4*>(p.Y + (size_t)gd2 * p.N + n0 + slab + c4);
             o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
           }
-          if (gd2 >= 0 && !(p.dbg & 1)) *reinterpret_cast<float4*>(p.Y + (size_t)gd2 * p.N + n0 + slab + c4) = o;
+          if (gd2 >= 0 && !(p.dbg & 1)) {
+            if (p.y_f16) *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.Y) + (size_t)gd2 * p.N + n0 + slab + c4) = make_uint2(pack2_f16(o.x, o.y), pack2_f16(o.z, o.w));
+            else *reinterpret_cast<float4*>(p.Y + (size_t)gd2 * p.N + n0 + slab + c4) = o;
+          }
           if (STATS && gd2 >= 0) {
             ssum[si][0] += o.x; ssum[si][1] += o.y; ssum[si][2] += o.z; ssum[si][3] += o.w;
             ssq[si][0] = fmaf(o.x, o.x, ssq[si][0]); ssq[si][1] = fmaf(o.y, o.y, ssq[si][1]);
@@ -626,7 +632,7 @@ inline int cv2_dispatch(cv2::Params& p, int max_ntile, cudaStream_t st) {
 
 // stride 1: forward (mirror 0) / in-chart dgrad (mirror 1: tap (di,dj) reads cell (-di,-dj)); W = 2n pixels per chart row
 // second bias of a concatenated forward (set by the C-ABI entry point around the launch; null otherwise)
-struct Bias2 { const float* p = nullptr; int split = 0; };
+struct Bias2 { const float* p = nullptr; int split = 0; int y_f16 = 0; };
 inline Bias2& bias2_ref() { static thread_local Bias2 b; return b; }
 
 // `pf` (dgrad only): fold the boundary tiles of the plan into the same launch
@@ -646,7 +652,7 @@ inline int launch_patch_conv2(const int32_t* plan_dev, const GinPSide& ps, int g
   p.stats = stats; p.stats_parts = stats_parts;
   p.plan = plan_dev; p.fmt = operand_format_bits(); p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P; p.P_dst = P;
   p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.Wt = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = bias; p.Y = Y;
-  if (bias) { p.bias1 = bias2_ref().p; p.bias_split = bias2_ref().split; }
+  if (bias) { p.bias1 = bias2_ref().p; p.bias_split = bias2_ref().split; p.y_f16 = bias2_ref().y_f16; }
   p.nplanes = 1; p.flush_each = 0; p.ntaps[0] = 7; p.group_bytes = 1280; p.dst_tab_off = -1;
   for (int t = 0; t < 7; ++t) {
     const int di = mirror ? -cv2::kDi[t] : cv2::kDi[t], dj = mirror ? -cv2::kDj[t] : cv2::kDj[t];
@@ -673,7 +679,7 @@ inline int launch_patch_conv2_s2_fwd(const int32_t* plan_dev, const GinP2Side& p
   p.stats = stats; p.stats_parts = stats_parts;
   p.plan = plan_dev; p.fmt = operand_format_bits(); p.U = ps.U; p.Q = ps.Q; p.ntiles = ps.ntiles; p.group = group; p.B = B; p.K = K; p.N = N; p.P_src = P_f; p.P_dst = P_c;
   p.X = reinterpret_cast<const __nv_bfloat16*>(Xb); p.Wt = reinterpret_cast<const __nv_bfloat16*>(Wb); p.bias = bias; p.Y = Y;
-  if (bias) { p.bias1 = bias2_ref().p; p.bias_split = bias2_ref().split; }
+  if (bias) { p.bias1 = bias2_ref().p; p.bias_split = bias2_ref().split; p.y_f16 = bias2_ref().y_f16; }
   p.nplanes = 4; p.flush_each = 0; p.group_bytes = 1280; p.dst_tab_off = -1;
   for (int t = 0; t < 7; ++t) {
     const int pl = kS2Plane[t], j = p.ntaps[pl]++;

@@ -263,7 +263,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_pair_kernel(const Para
             float4 o = *reinterpret_cast<const float4*>(my_stage + r2 * STAGE_PITCH + c4 * 4);
             o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
             if (gd2 >= 0) {
-              *reinterpret_cast<float4*>(p.Y + (size_t)gd2 * p.N + n0 + slab + c4) = o;
+              if (p.y_f16) *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.Y) + (size_t)gd2 * p.N + n0 + slab + c4) = make_uint2(pack2_f16(o.x, o.y), pack2_f16(o.z, o.w));
+              else *reinterpret_cast<float4*>(p.Y + (size_t)gd2 * p.N + n0 + slab + c4) = o;
               if (STATS) {
                 ssum[si][0] += o.x; ssum[si][1] += o.y; ssum[si][2] += o.z; ssum[si][3] += o.w;
                 ssq[si][0] = fmaf(o.x, o.x, ssq[si][0]); ssq[si][1] = fmaf(o.y, o.y, ssq[si][1]);

@@ -118,17 +118,22 @@ def _conv_fwd(plan, xb, packed, bias, B, cin, cout, p_out, bias1=None):
     """Returns (y fp32 [B*p_out][cout], per-CTA BatchNorm partial sums [nparts][2][cout] or None).  With `bias1` the output
     channels are two sibling convolutions side by side: `bias` belongs to the first half, `bias1` to the second."""
     import ctypes
-    y = _empty((B * p_out, cout), torch.float32, xb.device)
     parts = _empty(L.gin_hexconv_stats_ws_bytes(cout) // 4, torch.float32, xb.device)
     n = ctypes.c_int(0)
+    # The output is only ever read by the BatchNorm kernels: written as fp16 (GIN_Y_FP16=0: fp32) it costs half the bytes of its
+    # one write and three reads; the statistics come from the fp32 accumulators either way.
+    y = _empty((B * p_out, cout), torch.float16 if _Y16 else torch.float32, xb.device)
+    rc = L.gin_hexconv_fwd_bf16_stats2(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), packed.data_ptr(), bias.data_ptr(),
+                                       bias1.data_ptr() if bias1 is not None else None, cout // 2 if bias1 is not None else 0,
+                                       y.data_ptr(), 1 if _Y16 else 0, B, cin, cout, parts.data_ptr(), ctypes.addressof(n), _stream())
+    if rc == 0:
+        return y, ((parts, n.value) if n.value > 0 else None)
+    if rc != _lib.ERR_UNSUPPORTED:
+        _lib.check(rc, 'gin_hexconv_fwd_bf16_stats2')
+    # a kernel generation without the second bias pointer / the fp16 epilogue
+    y = _empty((B * p_out, cout), torch.float32, xb.device)
     if bias1 is not None:
-        rc = L.gin_hexconv_fwd_bf16_stats2(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), packed.data_ptr(), bias.data_ptr(), bias1.data_ptr(), cout // 2,
-                                           y.data_ptr(), B, cin, cout, parts.data_ptr(), ctypes.addressof(n), _stream())
-        if rc == 0:
-            return y, ((parts, n.value) if n.value > 0 else None)
-        if rc != _lib.ERR_UNSUPPORTED:
-            _lib.check(rc, 'gin_hexconv_fwd_bf16_stats2')
-        bias = torch.cat((bias, bias1), 0)               # a kernel generation without the second bias pointer
+        bias = torch.cat((bias, bias1), 0)
     _lib.check(L.gin_hexconv_fwd_bf16_stats(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), packed.data_ptr(), bias.data_ptr(), y.data_ptr(), B, cin, cout,
                                             parts.data_ptr(), ctypes.addressof(n), _stream()), 'gin_hexconv_fwd_bf16_stats')
     return y, ((parts, n.value) if n.value > 0 else None)
@@ -162,6 +167,8 @@ def _conv_wgrad(plan, xb, dyb, B, cin, cout, side=None):
     return dW
 
 
+import os as _os
+_Y16 = _os.environ.get('GIN_Y_FP16', '1') != '0'
 _side_streams = {}
 _grad_sink = None
 
@@ -194,6 +201,7 @@ def _bn_stats(y, col0, ld, rows, C, bn, parts=None):
                                              float(bn.momentum), bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
                                              bn.num_batches_tracked.data_ptr(), stat.data_ptr(), _stream()), 'gin_bn_stats_from_parts')
         return stat
+    assert y.dtype == torch.float32, 'gin_bn_stats reads fp32 maps (fp16 conv outputs always come with epilogue statistics)'
     ws = _empty(L.gin_bn_ws_bytes(C), torch.uint8, y.device)
     _lib.check(L.gin_bn_stats(y.data_ptr() + 4 * col0, ld, rows, C, bn.weight.data_ptr(), bn.bias.data_ptr(), float(bn.eps), float(bn.momentum),
                               bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), stat.data_ptr(), ws.data_ptr(),
@@ -211,8 +219,10 @@ def _bn_act(y1, col1, ld1, stat1, y2, col2, ld2, stat2, B, level, C, want_b=True
     out_b = _empty(((B * _P(level) + 2 * B), C), torch.bfloat16, dev) if want_b else None
     out_f = _empty((B * _P(level), C), torch.float32, dev) if want_f else None
     out_w = _empty(((B * _P(level) + 2 * B), C), torch.bfloat16, dev) if (want_w and (_DUAL or not want_b)) else None
-    _lib.check(L.gin_bn_act_fwd(y1.data_ptr() + 4 * col1, ld1, stat1.data_ptr(),
-                                (y2.data_ptr() + 4 * col2) if y2 is not None else None, ld2, stat2.data_ptr() if stat2 is not None else None, 1,
+    assert y2 is None or y2.dtype == y1.dtype
+    _lib.check(L.gin_bn_act_fwd(y1.data_ptr() + y1.element_size() * col1, ld1, stat1.data_ptr(),
+                                (y2.data_ptr() + y2.element_size() * col2) if y2 is not None else None, ld2, stat2.data_ptr() if stat2 is not None else None,
+                                1 if y1.dtype == torch.float16 else 0, 1,
                                 out_b.data_ptr() if want_b else None, out_f.data_ptr() if want_f else None,
                                 out_w.data_ptr() if out_w is not None else None, B, level, C, _stream()), 'gin_bn_act_fwd')
     if want_w and out_w is None:
@@ -226,8 +236,8 @@ def _bn_bwd(dout, mask_b, y, col0, ld, stat, B, level, C, dy_b=None, dy_b_col=0,
     bstat = _empty(4 * C, torch.float32, dev)
     ws = _empty(L.gin_bn_ws_bytes(C), torch.uint8, dev)
     dy_f = _empty((B * _P(level), C), torch.float32, dev) if want_f else None
-    _lib.check(L.gin_bn_act_bwd(dout.data_ptr(), C, mask_b.data_ptr() if mask_b is not None else None, y.data_ptr() + 4 * col0, ld,
-                                stat.data_ptr(), bstat.data_ptr(), (dy_b.data_ptr() + 2 * dy_b_col) if dy_b is not None else None, ldo,
+    _lib.check(L.gin_bn_act_bwd(dout.data_ptr(), C, mask_b.data_ptr() if mask_b is not None else None, y.data_ptr() + y.element_size() * col0, ld,
+                                1 if y.dtype == torch.float16 else 0, stat.data_ptr(), bstat.data_ptr(), (dy_b.data_ptr() + 2 * dy_b_col) if dy_b is not None else None, ldo,
                                 dy_f.data_ptr() if want_f else None, C, ws.data_ptr(), B, level, C, _stream()), 'gin_bn_act_bwd')
     return bstat, dy_f
 
@@ -345,10 +355,11 @@ class _Chain(torch.autograd.Function):
                 bs01 = torch.empty(4 * cout, dtype=torch.float32, device=dev)
                 bs10 = torch.empty(4 * cout, dtype=torch.float32, device=dev)
                 ws = torch.empty(L.gin_bn_pair_ws_bytes(cout), dtype=torch.uint8, device=dev)
+                assert st['y01'].dtype == st['ycat'].dtype
                 _lib.check(L.gin_bn_act_bwd_pair(d.data_ptr(), cout, st['out_b'].data_ptr(), st['y01'].data_ptr(), cout, st['stat01'].data_ptr(),
-                                                 bs01.data_ptr(), dy01_b.data_ptr(), cout, st['ycat'].data_ptr() + 4 * cout, 2 * cout,
-                                                 st['stat10'].data_ptr(), bs10.data_ptr(), dycat_b.data_ptr() + 2 * cout, 2 * cout, ws.data_ptr(),
-                                                 B, lvl, cout, _stream()), 'gin_bn_act_bwd_pair')
+                                                 bs01.data_ptr(), dy01_b.data_ptr(), cout, st['ycat'].data_ptr() + st['ycat'].element_size() * cout, 2 * cout,
+                                                 st['stat10'].data_ptr(), bs10.data_ptr(), dycat_b.data_ptr() + 2 * cout, 2 * cout,
+                                                 1 if st['ycat'].dtype == torch.float16 else 0, ws.data_ptr(), B, lvl, cout, _stream()), 'gin_bn_act_bwd_pair')
                 dW01 = _conv_wgrad(st['plan_b'], st['h_b'], dy01_b, B, cout, cout, side)
                 d_h = _conv_dgrad(st['plan_b'], dy01_b, st['pk01'], B, cout, cout, _P(lvl))
                 bs00, _ = _bn_bwd(d_h, st['h_b'], st['ycat'], 0, 2 * cout, st['stat00'], B, lvl, cout, dycat_b, 0, 2 * cout)

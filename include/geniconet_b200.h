@@ -130,11 +130,14 @@ int gin_hexconv_fwd_bf16(const void* plan_host, const void* plan_dev, const void
 size_t gin_hexconv_stats_ws_bytes(int Cout);
 int gin_hexconv_fwd_bf16_stats(const void* plan_host, const void* plan_dev, const void* xb, const void* packed, const float* bias,
                                float* y, int B, int Cin, int Cout, float* stats_ws, int* nparts, void* stream);
-/* The same for two sibling convolutions run as ONE GEMM with concatenated output channels: columns [0, split) take bias0,
- * columns [split, Cout) take bias1 (no concatenated bias tensor has to be built).  Needs a plan whose forward runs in patch mode. */
+/* The forward of the fused chains.  bias1 != NULL: two sibling convolutions run as ONE GEMM with concatenated output channels --
+ * columns [0, split) take bias0, columns [split, Cout) take bias1 (no concatenated bias tensor has to be built).  y_fp16 != 0:
+ * y is written as fp16 [B*P][Cout] (it is only read by the BatchNorm kernels below: half the bytes of its one write and three
+ * reads; the statistics still come from the fp32 accumulators).  GIN_ERR_UNSUPPORTED when the plan / size does not run the
+ * second-generation patch kernel (then use gin_hexconv_fwd_bf16_stats with an fp32 y). */
 int gin_hexconv_fwd_bf16_stats2(const void* plan_host, const void* plan_dev, const void* xb, const void* packed, const float* bias0,
-                                const float* bias1, int split, float* y, int B, int Cin, int Cout, float* stats_ws, int* nparts,
-                                void* stream);
+                                const float* bias1, int split, void* y, int y_fp16, int B, int Cin, int Cout, float* stats_ws,
+                                int* nparts, void* stream);
 int gin_hexconv_dgrad_bf16(const void* plan_host, const void* plan_dev, const void* dyb, const void* packed, float* dx,
                            int B, int Cin, int Cout, void* stream);
 /* dy (fp32) is only read for db and may be NULL when db is NULL */
@@ -163,19 +166,20 @@ int gin_bn_stats_from_parts(const float* parts, int nparts, int64_t ld, int64_t 
 /* out = act(y1*scale1 + shift1 [+ y2*scale2 + shift2]) at level `level`: out_b (may be NULL) = 16-bit [B*P + 2B][C] (pixels, then the
  * per-sample pole means) in the forward operand format -- exactly what gin_cast_bf16(which = 0) would produce from out;
  * out_f (may be NULL) = fp32 [B*P][C]; out_w (may be NULL) = the same rows as out_b in bf16 (which = 2: wgrad operand, ReLU mask). */
-int gin_bn_act_fwd(const float* y1, int64_t ld1, const float* stat1, const float* y2 /* may be NULL */, int64_t ld2, const float* stat2,
-                   int relu, void* out_b, float* out_f, void* out_w, int B, int level, int C, void* stream);
+/* y_fp16 != 0: y1 / y2 (and y / yA / yB below) are fp16 maps (gin_hexconv_fwd_bf16_stats2), `ld` counts elements either way. */
+int gin_bn_act_fwd(const void* y1, int64_t ld1, const float* stat1, const void* y2 /* may be NULL */, int64_t ld2, const float* stat2,
+                   int y_fp16, int relu, void* out_b, float* out_f, void* out_w, int B, int level, int C, void* stream);
 /* backward of out = act(bn(y) [+ ...]) with respect to y: g = dout * (mask_b > 0) (mask_b = a 16-bit copy of out, either format; NULL: no ReLU),
  * bstat[4][C] = dbeta, dgamma, mean(g), mean(g*yhat);  dy = scale*(g - mean(g) - yhat*mean(g*yhat)) is written as the bf16
  * copy dy_b [B*P + 2B][.] with row stride ldo (pole-mean rows included) and / or as fp32 dy_f with row stride ldf. */
-int gin_bn_act_bwd(const float* dout, int64_t ldg, const void* mask_b, const float* y, int64_t ld, const float* stat, float* bstat,
+int gin_bn_act_bwd(const float* dout, int64_t ldg, const void* mask_b, const void* y, int64_t ld, int y_fp16, const float* stat, float* bstat,
                    void* dy_b, int64_t ldo, float* dy_f, int64_t ldf, void* ws, int B, int level, int C, void* stream);
 /* Backward of out = relu(bnA(yA) + bnB(yB)) (the residual output of models.py:38-39, 60-61) with respect to yA and yB in one pass pair:
  * both BatchNorms see the same g = dout * (mask_b > 0), which is read once.  ws: gin_bn_pair_ws_bytes(C). */
 size_t gin_bn_pair_ws_bytes(int C);
-int gin_bn_act_bwd_pair(const float* dout, int64_t ldg, const void* mask_b, const float* yA, int64_t ldA, const float* statA, float* bstatA,
-                        void* dyA_b, int64_t ldoA, const float* yB, int64_t ldB, const float* statB, float* bstatB, void* dyB_b, int64_t ldoB,
-                        void* ws, int B, int level, int C, void* stream);
+int gin_bn_act_bwd_pair(const float* dout, int64_t ldg, const void* mask_b, const void* yA, int64_t ldA, const float* statA, float* bstatA,
+                        void* dyA_b, int64_t ldoA, const void* yB, int64_t ldB, const float* statB, float* bstatB, void* dyB_b, int64_t ldoB,
+                        int y_fp16, void* ws, int B, int level, int C, void* stream);
 /* IcoUpsampleS2S.forward whose result exists only as the next convolution's operand copy out_b = 16-bit [B*Pf + 2B][C] in the
  * forward operand format (upsample plan), plus (out_w, may be NULL) its bf16 twin for wgrad.  in: the fp32 coarse map
  * [B*Pc][C] (in_is_f32 = 1) or its forward-format operand copy [B*Pc + 2B][C] (0). */

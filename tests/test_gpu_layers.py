@@ -349,7 +349,7 @@ def test_fused_bn_act_matches_torch(C, level, B, two):
         bsA, bsB = torch.empty(4 * C, device=dev), torch.empty(4 * C, device=dev)
         ws = torch.empty(L.gin_bn_pair_ws_bytes(C), dtype=torch.uint8, device=dev)
         _lib.check(L.gin_bn_act_bwd_pair(d.data_ptr(), C, out_w.data_ptr(), ybuf.data_ptr() + 4 * col0, ld, stat1.data_ptr(), bsA.data_ptr(),
-                                         dyA.data_ptr(), C, y2.data_ptr(), C, stat2.data_ptr(), bsB.data_ptr(), dyB.data_ptr(), C, ws.data_ptr(),
+                                         dyA.data_ptr(), C, y2.data_ptr(), C, stat2.data_ptr(), bsB.data_ptr(), dyB.data_ptr(), C, 0, ws.data_ptr(),
                                          B, level, C, torch.cuda.current_stream().cuda_stream))
         pairs = [(bsA, dyA, y1r, refbn[0]), (bsB, dyB, y2r, refbn[1])]
     else:
