@@ -78,6 +78,7 @@ struct Params {
   int dst_row_stride, dst_px_stride, dst_plane_off[MAX_PLANES];
   int total_tiles, n_blocks;  // CTA c owns n-block c % n_blocks and tiles c / n_blocks + k * (gridDim.x / n_blocks)
   int a_stage_bytes, a_stages, b_stages, resident;
+  int cl;                     // CTAs per cluster (1, 2 or 4): > 1 only with streamed weights
   // Second tile class (SEAM kernels: dgrad in one launch, gin_plan.h GinPfSide): x_total boundary tiles in regular form --
   // x_nslots segments of 128 gathered rows with one tap each, destination pixels from a table -- appended to the tile list after
   // the total_tiles patch tiles.  mask_off >= 0: plan words [ntiles][nflush][4], bit r set = the patch tile does not store row r.
@@ -97,6 +98,26 @@ GIN_DEVINL uint64_t desc_kmajor(uint32_t smem_addr, uint32_t sbo_bytes) {
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;                         // SWIZZLE_128B, base offset 0 (address-based pattern)
   return d;
+}
+
+// ---- thread-block clusters: the CTAs of a cluster (p.cl = 2 or 4) work on consecutive tiles of the same class in lock step and
+// SHARE the weight stream: every CTA fetches 1/cl of each weight tile and multicasts it into the shared memory of all of them,
+// so a weight tile crosses the L2 -> SM fabric once per cluster instead of once per CTA (that stream, ~10 TB/s aggregate, is what
+// bounded the streamed-weight layers: profiles/r01_bottleneck_matrix_v2_kernel.log, profiles/r02_ncu_conv_kernels.txt).
+GIN_DEVINL uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+GIN_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// bulk copy whose bytes (and mbarrier completion) land at the same shared-memory offsets in every CTA of `mask`
+GIN_DEVINL void bulk_g2s_mc(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+// tcgen05.commit arriving on the barrier at this offset in every CTA of `mask`
+GIN_DEVINL void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
 }
 
 // barrier block: a_full[4] a_empty[4] b_full[8] b_empty[8] acc_full[2] acc_empty[2] tab_full[8] tab_empty[8] | tmem slot
@@ -140,14 +161,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
   const int U = p.U, Q = p.Q, NP = p.nplanes;
   const int AS = p.a_stages, BS = p.b_stages;
   constexpr uint32_t TM_COLS = (2 * N_TILE <= 32) ? 32 : 2 * N_TILE;
-  const int nb = blockIdx.x % p.n_blocks, n0 = nb * N_TILE;
-  const int t_first = blockIdx.x / p.n_blocks, t_step = gridDim.x / p.n_blocks;
-  const int TT = p.total_tiles + (SEAM ? p.x_total : 0);      // tiles of both classes; T >= p.total_tiles: a boundary tile
+  // Tiles are handed out in GROUPS of CL consecutive tiles of one class (CL = cluster size; 1: a group is a tile): cluster c keeps
+  // n-block c % n_blocks and the groups c / n_blocks + k * (clusters / n_blocks); its CTA of rank r takes tile r of each group (a
+  // "ghost" -- all rows zero, nothing stored -- where a class does not fill its last group).  Groups >= groups0 are boundary tiles.
+  const int CL = RESIDENT ? 1 : p.cl;
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
+  const int cid = blockIdx.x / CL;
+  const int nb = cid % p.n_blocks, n0 = nb * N_TILE;
+  const int q_first = cid / p.n_blocks, q_step = (gridDim.x / CL) / p.n_blocks;
+  const int groups0 = (p.total_tiles + CL - 1) / CL;
+  const int NG = groups0 + (SEAM ? (p.x_total + CL - 1) / CL : 0);
 
   if (warp == W_MMA) {
     if (lane == 0) {
       for (int s = 0; s < MAX_A_STAGES; ++s) { mbar_init(&a_full[s], PROD_THREADS); mbar_init(&a_empty[s], 1); }
-      for (int s = 0; s < MAX_B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+      for (int s = 0; s < MAX_B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], CL); }   // a slot is free once EVERY CTA of the cluster has used it
       for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_WARPS * 32); }
       for (int s = 0; s < TAB_SLOTS; ++s) { mbar_init(&tab_full[s], 1); mbar_init(&tab_empty[s], PROD_THREADS); }
       fence_barrier_init();
@@ -161,6 +190,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (CL > 1) cluster_sync_all();                    // every CTA's barriers exist before a peer multicasts into them
   const uint32_t tmem_base = *tmem_slot;
   GIN_PDL_SYNC();                                    // everything above touched only shared memory, TMEM and the constant plan
 #ifdef GIN_PROF
@@ -174,8 +204,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
     const __nv_bfloat16* __restrict__ Xc = p.X + c8 * 8;
     int s = 0, ts = 0;
     uint32_t ph = 0, tph = 0;
-    for (int T = t_first; T < TT; T += t_step) {
-      const bool sx = SEAM && T >= p.total_tiles;
+    for (int g = q_first; g < NG; g += q_step) {
+      const bool sx = SEAM && g >= groups0;
       const int NPt = sx ? p.x_nslots : NP, Ut = sx ? BM : U;
       for (int pl = 0; pl < NPt; ++pl) {
         int v[MAX_ITEMS];
@@ -218,8 +248,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
     // blocking (its a_full + proxy fence, and the accumulator hand-back when it starts a new output); whatever is already
     // complete then costs nothing at the chunk boundary.
     bool a_ready = false, acc_ready = false;
-    for (int T = t_first; T < TT; T += t_step) {
-      const bool sx = SEAM && T >= p.total_tiles;
+    for (int g = q_first; g < NG; g += q_step) {
+      const bool sx = SEAM && g >= groups0;
       const int NPt = sx ? p.x_nslots : NP;
       const uint32_t gbytes = sx ? 1024u : (uint32_t)p.group_bytes;
       uint32_t fresh = 1;                            // the next MMA starts a new accumulation
@@ -242,7 +272,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
           }
           a_ready = false;
           const uint32_t a_addr = smem_u32(a_smem + s * p.a_stage_bytes);
-          const bool last_chunk_of_cta = kc == kchunks - 1 && pl == NPt - 1 && T + t_step >= TT;
+          const bool last_chunk_of_cta = kc == kchunks - 1 && pl == NPt - 1 && g + q_step >= NG;
           for (int j = 0; j < nt; ++j) {
             if (j == nt - 1 && !last_chunk_of_cta) {  // open the next chunk while the earlier tap groups execute
               const int sn = (s + 1 == AS) ? 0 : s + 1;
@@ -279,7 +309,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
               PROF_ADD(pw[4]);
             }
             if (!RESIDENT) {
-              if (leader) umma_commit(&b_empty[bs]);
+              if (leader) { if (CL > 1) umma_commit_mc(&b_empty[bs], cmask); else umma_commit(&b_empty[bs]); }
               if (++bs == BS) { bs = 0; bph ^= 1u; }
             }
           }
@@ -309,16 +339,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
       } else {
         int bs = 0;
         uint32_t bph = 0;
-        for (int T = t_first; T < TT; T += t_step) {
-          const bool sx = SEAM && T >= p.total_tiles;
+        const uint32_t part = (uint32_t)B_TILE / (uint32_t)CL;      // this CTA's share of every weight tile
+        for (int g = q_first; g < NG; g += q_step) {
+          const bool sx = SEAM && g >= groups0;
           const int NPt = sx ? p.x_nslots : NP;
           for (int pl = 0; pl < NPt; ++pl)
             for (int kc = 0; kc < kchunks; ++kc)
               for (int j = 0; j < (sx ? 1 : p.ntaps[pl]); ++j) {
                 const int tap = sx ? p.x_tap[pl] : p.tap_id[pl][j];
-                mbar_wait(&b_empty[bs], bph ^ 1u);
-                mbar_arrive_expect_tx(&b_full[bs], B_TILE);
-                bulk_g2s(b_smem + (size_t)bs * B_TILE, p.Wt + (((size_t)tap * kchunks + kc) * p.N + n0) * BK, B_TILE, &b_full[bs]);
+                mbar_wait(&b_empty[bs], bph ^ 1u);            // completed by the MMA commits of all CL CTAs
+                mbar_arrive_expect_tx(&b_full[bs], B_TILE);   // the whole tile: this CTA's share + the shares multicast by its peers
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Wt + (((size_t)tap * kchunks + kc) * p.N + n0) * BK);
+                if (CL > 1) bulk_g2s_mc(b_smem + (size_t)bs * B_TILE + crank * part, src + crank * part, part, &b_full[bs], cmask);
+                else bulk_g2s(b_smem + (size_t)bs * B_TILE, src, B_TILE, &b_full[bs]);
                 if (++bs == BS) { bs = 0; bph ^= 1u; }
               }
         }
@@ -330,31 +363,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
     const long long total_src = (long long)p.B * p.P_src;
     int ts = 0;
     uint32_t tph = 0;
-    int Tn = t_first, pn = 0;                        // the next (tile, segment) in the producers' order
-    while (Tn < TT) {
-      int code[TAB_BATCH][MAX_ITEMS], tiles[TAB_BATCH];
+    int gn = q_first, pn = 0;                        // the next (group, segment) in the producers' order
+    while (gn < NG) {
+      int code[TAB_BATCH][MAX_ITEMS], grp[TAB_BATCH], sgrp[TAB_BATCH];      // sgrp: sample group of the tile, -1 for a ghost
 #pragma unroll
       for (int j = 0; j < TAB_BATCH; ++j) {
-        tiles[j] = -1;
-        if (Tn < TT) {
-          tiles[j] = Tn;
-          const bool sx = SEAM && Tn >= p.total_tiles;
+        grp[j] = -1;
+        if (gn < NG) {
+          grp[j] = gn;
+          const bool sx = SEAM && gn >= groups0;
+          const int loc = (sx ? gn - groups0 : gn) * CL + crank, per = sx ? p.x_ntiles : p.ntiles;
+          const bool ghost = loc >= (sx ? p.x_total : p.total_tiles);
+          sgrp[j] = ghost ? -1 : loc / per;
           const int32_t* __restrict__ src_tab =
-              sx ? p.plan + p.x_src_off + ((size_t)((Tn - p.total_tiles) % p.x_ntiles) * p.x_nslots + pn) * BM
-                 : p.plan + p.tab_off + (size_t)(Tn % p.ntiles) * p.tab_tstride + (size_t)pn * p.tab_pstride;
-          const int Ut = sx ? BM : U;
+              sx ? p.plan + p.x_src_off + ((size_t)(loc % per) * p.x_nslots + pn) * BM
+                 : p.plan + p.tab_off + (size_t)(loc % per) * p.tab_tstride + (size_t)pn * p.tab_pstride;
+          const int Ut = (sx ? BM : U);
 #pragma unroll
           for (int it = 0; it < MAX_ITEMS; ++it) {
             const int u = it * 32 + lane;
-            code[j][it] = (u < Ut) ? __ldg(src_tab + u) : GIN_SRC_ZERO;
+            code[j][it] = (u < Ut && !ghost) ? __ldg(src_tab + u) : GIN_SRC_ZERO;
           }
-          if (++pn == (sx ? p.x_nslots : NP)) { pn = 0; Tn += t_step; }
+          if (++pn == (sx ? p.x_nslots : NP)) { pn = 0; gn += q_step; }
         }
       }
 #pragma unroll
       for (int j = 0; j < TAB_BATCH; ++j) {
-        if (tiles[j] >= 0) {
-          const int G = (SEAM && tiles[j] >= p.total_tiles) ? (tiles[j] - p.total_tiles) / p.x_ntiles : tiles[j] / p.ntiles;
+        if (grp[j] >= 0) {
+          const int G = sgrp[j] < 0 ? 0 : sgrp[j];
           const long long base = (long long)G * p.group * p.P_src;
           mbar_wait(&tab_empty[ts], tph ^ 1u);
 #pragma unroll
@@ -385,15 +421,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
     for (int si = 0; si < (STATS ? NS : 1); ++si)
 #pragma unroll
       for (int k = 0; k < 4; ++k) { ssum[si][k] = 0.f; ssq[si][k] = 0.f; }
-    for (int T = t_first; T < TT; T += t_step) {
-    const bool sx = SEAM && T >= p.total_tiles;
+    for (int g0 = q_first; g0 < NG; g0 += q_step) {
+    const bool sx = SEAM && g0 >= groups0;
     const bool tabdst = sx || p.dst_tab_off >= 0;   // destination pixels from a table (boundary tiles / the stand-alone seam form)
+    const int Tl = (sx ? g0 - groups0 : g0) * CL + crank, per = sx ? p.x_ntiles : p.ntiles;
+    const bool ghost = Tl >= (sx ? p.x_total : p.total_tiles);
     for (int fl = 0; fl < (sx ? 1 : nflush); ++fl, ++wc) {
-      const int Tl = sx ? T - p.total_tiles : T, per = sx ? p.x_ntiles : p.ntiles;
       const int G = Tl / per, t = Tl - G * per;
       long long gdl;
       bool extra_row = false;
-      if (tabdst) {
+      if (ghost) gdl = total_pix;                    // a ghost tile stores nothing
+      else if (tabdst) {
         const int dr = __ldg(p.plan + (sx ? p.x_dst_off : p.dst_tab_off) + t * BM + row);
         extra_row = dr == -3;                         // a further row of the pixel above (same 32-row group): folded in below
         gdl = dr >= 0 ? (long long)G * p.group * p.P_dst + dr : total_pix;
@@ -486,7 +524,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
           }
         }
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-      float* out = p.stats + (size_t)(blockIdx.x / p.n_blocks) * 2 * p.N + n0;
+      float* out = p.stats + (size_t)((cid / p.n_blocks) * CL + crank) * 2 * p.N + n0;
       for (int i = (warp - W_EPI0) * 32 + lane; i < 2 * N_TILE; i += EPI_WARPS * 32)
         out[(i / N_TILE) * p.N + (i % N_TILE)] = (sred[i] + sred[2 * N_TILE + i]) + (sred[4 * N_TILE + i] + sred[6 * N_TILE + i]);
     }
@@ -496,6 +534,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) patch_conv_kernel(const Params p)
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();                    // no CTA leaves while a peer may still multicast into it / arrive on its barriers
   if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TM_COLS);
@@ -525,6 +564,8 @@ inline bool plan_smem(int n_tile, int K, int U, int ntiles, int Q, Params& p, in
   return true;
 }
 
+constexpr int B_TILE_OF(int n_tile) { return n_tile * 128; }
+
 template <int N_TILE>
 int launch(Params p, cudaStream_t st) {
   int smem_total = 0;
@@ -542,23 +583,49 @@ int launch(Params p, cudaStream_t st) {
   }
   p.n_blocks = p.N / N_TILE;
   const bool seam = p.x_total > 0;
-  const long long items = (long long)(p.total_tiles + p.x_total) * p.n_blocks;
-  const int sms = num_sms();
-  int grid = (int)(items < sms ? items : sms);
-  grid -= grid % p.n_blocks;                         // every CTA keeps one n-block
-  if (grid < p.n_blocks) grid = p.n_blocks;
   const bool stats = p.stats != nullptr && !p.flush_each && !seam;
-  if (p.stats_parts) *p.stats_parts = stats ? grid / p.n_blocks : 0;
-  if (seam) {                                        // dgrad in one launch: patch tiles + boundary tiles
-    if (p.resident) launch_pdl(patch_conv_kernel<N_TILE, true, false, true>, dim3(grid), dim3(NTHREADS), smem_total, st, p);
-    else launch_pdl(patch_conv_kernel<N_TILE, false, false, true>, dim3(grid), dim3(NTHREADS), smem_total, st, p);
-  } else if (p.resident) {
-    if (stats) launch_pdl(patch_conv_kernel<N_TILE, true, true, false>, dim3(grid), dim3(NTHREADS), smem_total, st, p);
-    else launch_pdl(patch_conv_kernel<N_TILE, true, false, false>, dim3(grid), dim3(NTHREADS), smem_total, st, p);
-  } else {
-    if (stats) launch_pdl(patch_conv_kernel<N_TILE, false, true, false>, dim3(grid), dim3(NTHREADS), smem_total, st, p);
-    else launch_pdl(patch_conv_kernel<N_TILE, false, false, false>, dim3(grid), dim3(NTHREADS), smem_total, st, p);
+  const int sms = num_sms();
+  void (*kern)(const Params);
+  if (seam) kern = p.resident ? patch_conv_kernel<N_TILE, true, false, true> : patch_conv_kernel<N_TILE, false, false, true>;
+  else if (p.resident) kern = stats ? patch_conv_kernel<N_TILE, true, true, false> : patch_conv_kernel<N_TILE, true, false, false>;
+  else kern = stats ? patch_conv_kernel<N_TILE, false, true, false> : patch_conv_kernel<N_TILE, false, false, false>;
+  // Streamed weights: clusters of CL CTAs share the weight stream (GIN_CLUSTER = 1 switches it off, 4 asks for clusters of four).
+  int CL = 1;
+  if (!p.resident) {
+    static int want = -1;
+    if (want < 0) { const char* e = getenv("GIN_CLUSTER"); want = e ? atoi(e) : 2; if (want != 1 && want != 2 && want != 4) want = 2; }
+    CL = want;
+    while (CL > 1 && (B_TILE_OF(N_TILE) / CL) % 16) CL /= 2;
   }
+  int grid = 0;
+  while (true) {
+    const long long groups = ((long long)p.total_tiles + CL - 1) / CL + ((long long)p.x_total + CL - 1) / CL;
+    const long long want_clusters = groups * p.n_blocks;
+    int cap = sms / CL;                                // clusters that can be resident at once
+    if (CL > 1) {
+      static PerDeviceFlag probed_on[3];
+      static int cap_cl[kMaxDevices][3];
+      const int slot = CL == 2 ? 1 : 2, d = current_device();
+      if (!probed_on[slot].here()) {
+        // the limit is set by shared memory (1 CTA per SM) and by how the SMs pair up inside their GPCs: ask the driver
+        cap_cl[d][slot] = max_active_clusters(patch_conv_kernel<N_TILE, false, false, false>, CL, NTHREADS, SMEM_LIMIT);
+        probed_on[slot].here() = true;
+      }
+      cap = cap_cl[d][slot] < cap ? cap_cl[d][slot] : cap;
+    }
+    long long clusters = want_clusters < cap ? want_clusters : cap;
+    clusters -= clusters % p.n_blocks;                 // every cluster keeps one n-block
+    if (clusters < p.n_blocks) {
+      if (CL > 1) { CL /= 2; continue; }               // not even one cluster per n-block fits: smaller clusters
+      clusters = p.n_blocks;
+    }
+    grid = (int)clusters * CL;
+    break;
+  }
+  p.cl = CL;
+  if (p.stats_parts) *p.stats_parts = stats ? grid / p.n_blocks : 0;
+  if (CL > 1) launch_cluster(kern, CL, dim3(grid), dim3(NTHREADS), smem_total, st, p);
+  else launch_pdl(kern, dim3(grid), dim3(NTHREADS), smem_total, st, p);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
