@@ -593,7 +593,9 @@ int launch(Params p, cudaStream_t st) {
   int CL = 1;
   if (!p.resident) {
     static int want = -1;
-    if (want < 0) { const char* e = getenv("GIN_CLUSTER"); want = e ? atoi(e) : 2; if (want != 1 && want != 2 && want != 4) want = 2; }
+    // Measured (profiles/r02_cluster_multicast_experiment.md): no gain -- the weight ring is bound by the LATENCY of a tile's round trip
+    // (96 KB in flight / ~1.5 us), not by L2 bandwidth, and multicast does not shorten that -- so clusters stay opt-in.
+    if (want < 0) { const char* e = getenv("GIN_CLUSTER"); want = e ? atoi(e) : 1; if (want != 1 && want != 2 && want != 4) want = 1; }
     CL = want;
     while (CL > 1 && (B_TILE_OF(N_TILE) / CL) % 16) CL /= 2;
   }
@@ -685,6 +687,7 @@ inline int cv2_dispatch(cv2::Params& p, int max_ntile, cudaStream_t st) {
   p.x_total = p.x_ntiles > 0 ? groups * p.x_ntiles : 0;
   { const char* e = getenv("GIN_DBG"); p.dbg = e ? atoi(e) : 0; }
   int nt = cv2_pick_ntile(p.total_tiles + p.x_total, p.N);
+  { static int cap = -1; if (cap < 0) { const char* e = getenv("GIN_NTILE_MAX"); cap = e ? atoi(e) : 256; } if (cap < max_ntile && cap >= 64) max_ntile = cap; }
   while (nt > max_ntile) nt /= 2;
   if (cv2_pair_ok(p, nt)) {
     const int rc = cv2_launch_pair(p, nt < 128 ? nt : 128, st);
