@@ -352,6 +352,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    per_rank_ms = []          # ms per step of every rank, one list per timed() call (the reported time is the maximum)
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -362,6 +364,9 @@ def run_ours(args):
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
         if world > 1:
+            every = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(every, ms)
+            per_rank_ms.append([v.item() / steps for v in every])
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
@@ -463,6 +468,7 @@ def run_ours(args):
                 'e2e': {'value': meshes / (ms_e2e * 1e-3), 'unit': 'meshes/s', 'ms_per_step': ms_e2e,
                         'h2d_bytes_per_step': x_host.numel() * 4 + t_host.numel() * 4, 'd2h_bytes_per_step': 4},
                 'gpu_launches': int(launches), 'clocks': clk, 'loss': final_loss,
+                'ms_per_step_per_rank': per_rank_ms[0] if per_rank_ms else None,
                 'tflops_algorithmic': FLOP_PER_MESH.get((args.model, args.level), 0) * meshes / (ms_step * 1e-3) / 1e12,
                 'roofline': roof, 'cpu_baseline': cpu}
         if table is not None:

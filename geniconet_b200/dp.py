@@ -12,6 +12,8 @@ backward has run -- they hand every residual block's gradients to `early_grads()
 enqueued, so a bucket can start its all-reduce (NCCL enqueues on its own stream, also under CUDA-graph capture) while the
 remaining blocks are still being differentiated.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -47,6 +49,7 @@ class GradBuckets:
         self._pending = [0] * len(self.buckets)
         self._handles = []
         self._early = set()          # id(param) of gradients that arrived through early_grads() this step
+        self._early_grad = {}        # id(param) -> that gradient, until its bucket is complete
         self._bucket_of = {}
         for bi, (_, ps, _) in enumerate(self.buckets):
             for p in ps:
@@ -72,7 +75,8 @@ class GradBuckets:
             self._pending[bi] = len(ps)
         self._handles = []
         self._early = set()
-        if self.world > 1:
+        self._early_grad = {}
+        if self.world > 1 and os.environ.get('GIN_DP_EARLY', '1') != '0':
             from . import fused
             fused.set_grad_sink(self.early_grads)
 
@@ -90,30 +94,31 @@ class GradBuckets:
         starts its all-reduce immediately.  Parameters of other models (not in any bucket) are ignored."""
         if self.world <= 1:
             return
-        by_bucket = {}
+        touched = set()
         for p, g in pairs:
             bi = self._bucket_of.get(p)
             if bi is None or id(p) in self._early or g is None:
                 continue
             self._early.add(id(p))
-            by_bucket.setdefault(bi, []).append((p, g))
-        for bi, items in by_bucket.items():
-            flat, ps, views = self.buckets[bi]
-            slot = {id(p): v for p, v in zip(ps, views)}
-            torch._foreach_copy_([slot[id(p)] for p, _ in items], [g.view_as(p) for p, g in items])
-            self._pending[bi] -= len(items)
+            self._early_grad[id(p)] = g.view_as(p)      # copied into the bucket in ONE launch when the bucket is complete
+            self._pending[bi] -= 1
+            touched.add(bi)
+        for bi in touched:
             if self._pending[bi] == 0:
                 self._launch(bi)
 
     def _launch(self, bi):
         flat, ps, views = self.buckets[bi]
         have = [(v, p.grad) for v, p in zip(views, ps) if p.grad is not None and id(p) not in self._early]
-        if len(have) + sum(1 for p in ps if id(p) in self._early) < len(ps):
+        have += [(v, self._early_grad.pop(id(p))) for v, p in zip(views, ps) if id(p) in self._early_grad]
+        if len(have) < len(ps):
             # parameters that got no gradient this step contribute zeros (their slots may hold last step's averages)
             missing = [v for v, p in zip(views, ps) if p.grad is None and id(p) not in self._early]
             torch._foreach_zero_(missing)
         if have:
             torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        if os.environ.get('GIN_DP_NOCOMM') == '1':           # diagnosis only: bucket copies without the exchange
+            return
         if dist.get_backend(self.group) == 'nccl':
             h = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
             self._handles.append((h, None))

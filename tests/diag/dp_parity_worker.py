@@ -45,13 +45,17 @@ def restore_bn():
                 v.copy_(bn_state[k])
 
 
-# (1) local gradient, eager, no buckets, no sink
+# (1) local gradient, eager, no buckets, no sink.  Not on the legacy default stream: the AccumulateGrad nodes created here stay
+# bound to the stream of this first backward, and a capture may not synchronise with the legacy stream.
 fused.set_grad_sink(None)
 reparam.manual_seed(9)
 for p in model.parameters():
     p.grad = None
-loss = crit(model(x), t)
-loss.backward()
+work = torch.cuda.Stream()
+work.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(work):
+    loss = crit(model(x), t)
+    loss.backward()
 torch.cuda.synchronize()
 named = list(model.named_parameters())
 local_g = [p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p) for _, p in named]
