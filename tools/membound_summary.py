@@ -15,7 +15,7 @@ import re
 import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
-steps = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+steps = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0
 hi = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
 hdr = rows[hi]
 kn, mn, mu, mv, idc = hdr.index('Kernel Name'), hdr.index('Metric Name'), hdr.index('Metric Unit'), hdr.index('Metric Value'), hdr.index('ID')
@@ -37,6 +37,8 @@ for d in per.values():
     a[1] += d.get('gpu__time_duration.sum', 0.0)
     a[2] += d.get('dram__bytes_read.sum', 0.0)
     a[3] += d.get('dram__bytes_write.sum', 0.0)
+if steps <= 0:          # one p2p_final_kernel per loss forward = per training step
+    steps = float(max(1, sum(a[0] for k, a in agg.items() if 'p2p_final_kernel' in k)))
 peak = 6546.2
 try:
     peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')))['hbm_gbs']
