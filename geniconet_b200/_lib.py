@@ -56,6 +56,8 @@ _SIGS = {
     'gin_hexconv_pack_weights_bf16': (_i, [_vp, _i, _vp, _i, _vp, _i, _vp]),
     'gin_hexconv_pack_weights_bf16_multi': (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'gin_hexconv_fwd': (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'gin_hexconv_narrow_stats_ws_bytes': (_sz, [_i]),
+    'gin_hexconv_fwd_narrow_stats': (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     'gin_hexconv_dgrad': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'gin_hexconv_wgrad_ws_bytes': (_sz, [_i, _i]),
     'gin_hexconv_wgrad': (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -261,6 +261,24 @@ int gin_hexconv_fwd(const void* plan_host, const void* plan_dev, const float* x,
                               bias, y, st, Cin, Cout);
 }
 
+size_t gin_hexconv_narrow_stats_ws_bytes(int Cout) { return Cout <= 0 ? 0 : (size_t)148 * 4 * 2 * Cout * 4; }
+
+int gin_hexconv_fwd_narrow_stats(const void* plan_host, const void* plan_dev, const float* x, int64_t sb, int64_t sp, int64_t sc, const void* packed,
+                                 const float* bias, void* y, int y_fp16, int B, int Cin, int Cout, float* stats_ws, int* nparts, void* stream) {
+  if (!x || !packed || !y || !stats_ws || !nparts || B <= 0 || Cin <= 0 || Cout <= 0) return fail(GIN_ERR_ARG, "gin_hexconv_fwd_narrow_stats: bad argument");
+  const GinConvPlanHdr* h;
+  int rc = conv_hdr(plan_host, plan_dev, &h);
+  if (rc) return rc;
+  if (!gin::narrow_supported(Cin, Cout, h->fwd)) return fail(GIN_ERR_UNSUPPORTED, "gin_hexconv_fwd_narrow_stats: only the xyz input layer (Cin = 3, Cout = 64 | 128)");
+  GinSrcView X{x, (long long)sb, (long long)sp, (long long)sc, h->fwd.P_src};
+  const float* wf = reinterpret_cast<const float*>(reinterpret_cast<const char*>(packed) + packed_off_wf(Cin, Cout));
+  rc = gin::launch_narrow_fwd(plan_words(plan_dev), h->fwd, h->group, X, wf, bias, reinterpret_cast<float*>(y), B, Cin, Cout, (cudaStream_t)stream, stats_ws, nparts,
+                              y_fp16 ? 1 : 0);
+  if (rc != GIN_OK) return fail(rc, "narrow forward launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return GIN_OK;
+}
+
 int gin_hexconv_dgrad(const void* plan_host, const void* plan_dev, const float* dy, const void* packed, float* dx, int B, int Cin, int Cout, int impl,
                       void* stream) {
   cudaStream_t st = (cudaStream_t)stream;

@@ -55,10 +55,12 @@ GIN_DEVINL void stage_tile(const int32_t* __restrict__ plan, const GinSide& side
 
 // ------------------------------------------------------------------------------------------------ forward
 // CPL = output channels per lane (Cout = 32 * CPL).  W is wf[7][CIN][Cout] fp32.
+// stats != null: this CTA's column sums of y and y^2 (BatchNorm statistics of the layer's output) go to stats[blockIdx][2][COUT];
+// y_f16: Y is written as fp16 (the fused chain's stem output is only read by BatchNorm kernels).
 template <int CIN, int CPL>
 __global__ void __launch_bounds__(THREADS, 4)
 fwd_kernel(const int32_t* __restrict__ plan, GinSide side, GinSrcView X, const float* __restrict__ W, const float* __restrict__ bias,
-           float* __restrict__ Y, int group, int B, int total_tiles) {
+           float* __restrict__ Y, int group, int B, int total_tiles, float* __restrict__ stats, int y_f16) {
   extern __shared__ __align__(16) float smem_f[];
   constexpr int COUT = 32 * CPL;
   float* ws = smem_f;                                  // [7][CIN][COUT]
@@ -67,9 +69,9 @@ fwd_kernel(const int32_t* __restrict__ plan, GinSide side, GinSrcView X, const f
   __shared__ int8_t tap_s[GIN_MAX_SLOTS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 7 * CIN * COUT; i += THREADS) ws[i] = __ldg(W + i);
-  float bz[CPL];
+  float bz[CPL], ssum[CPL], ssq[CPL];
 #pragma unroll
-  for (int k = 0; k < CPL; ++k) bz[k] = bias ? __ldg(bias + lane * CPL + k) : 0.f;
+  for (int k = 0; k < CPL; ++k) { bz[k] = bias ? __ldg(bias + lane * CPL + k) : 0.f; ssum[k] = 0.f; ssq[k] = 0.f; }
 
   for (int T = blockIdx.x; T < total_tiles; T += gridDim.x) {
     const int G = T / side.ntiles, t = T % side.ntiles;
@@ -111,15 +113,44 @@ fwd_kernel(const int32_t* __restrict__ plan, GinSide side, GinSrcView X, const f
       for (int r = 0; r < 8; ++r) {
         const long long d = dst_s[r0 + r];
         if (d >= 0) {
-          float* yp = Y + (size_t)d * COUT + lane * CPL;
-          if (CPL == 2) *reinterpret_cast<float2*>(yp) = make_float2(acc[r][0], acc[r][1]);
-          else if (CPL == 4) *reinterpret_cast<float4*>(yp) = make_float4(acc[r][0], acc[r][1 % CPL], acc[r][2 % CPL], acc[r][3 % CPL]);
-          else {
 #pragma unroll
-            for (int k = 0; k < CPL; ++k) yp[k] = acc[r][k];
+          for (int k = 0; k < CPL; ++k) { ssum[k] += acc[r][k]; ssq[k] = fmaf(acc[r][k], acc[r][k], ssq[k]); }
+          if (y_f16) {
+            unsigned short* yh = reinterpret_cast<unsigned short*>(Y) + (size_t)d * COUT + lane * CPL;
+            if (CPL == 2) *reinterpret_cast<uint32_t*>(yh) = pack2_f16(acc[r][0], acc[r][1]);
+            else if (CPL == 4) *reinterpret_cast<uint2*>(yh) = make_uint2(pack2_f16(acc[r][0], acc[r][1 % CPL]), pack2_f16(acc[r][2 % CPL], acc[r][3 % CPL]));
+            else {
+#pragma unroll
+              for (int k = 0; k < CPL; ++k) yh[k] = cvt_op(acc[r][k], 1);
+            }
+          } else {
+            float* yp = Y + (size_t)d * COUT + lane * CPL;
+            if (CPL == 2) *reinterpret_cast<float2*>(yp) = make_float2(acc[r][0], acc[r][1]);
+            else if (CPL == 4) *reinterpret_cast<float4*>(yp) = make_float4(acc[r][0], acc[r][1 % CPL], acc[r][2 % CPL], acc[r][3 % CPL]);
+            else {
+#pragma unroll
+              for (int k = 0; k < CPL; ++k) yp[k] = acc[r][k];
+            }
           }
         }
       }
+    }
+  }
+  if (stats) {
+    // lane l of every warp owns the same CPL channels: the eight warps meet in shared memory and are added in a fixed order
+    __syncthreads();
+    float* red = xs;                                   // [WARPS][2][COUT], the staging area is free now
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      red[(warp * 2) * COUT + lane * CPL + k] = ssum[k];
+      red[(warp * 2 + 1) * COUT + lane * CPL + k] = ssq[k];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * COUT; i += THREADS) {
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) a += red[w * 2 * COUT + i];
+      stats[(size_t)blockIdx.x * 2 * COUT + i] = a;
     }
   }
 }
@@ -272,19 +303,21 @@ inline int narrow_config(K kern, size_t smem) {
   return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess ? 0 : -3;
 }
 
+// stats (optional): [grid][2][Cout] per-CTA column sums of y and y^2, *nparts receives the grid size; y_f16: Y is fp16
 inline int launch_narrow_fwd(const int32_t* plan_dev, const GinSide& side, int group, GinSrcView X, const float* W, const float* bias, float* Y,
-                             int B, int Cin, int Cout, cudaStream_t st) {
+                             int B, int Cin, int Cout, cudaStream_t st, float* stats = nullptr, int* nparts = nullptr, int y_f16 = 0) {
   const int groups = (B + group - 1) / group, total = groups * side.ntiles;
   const size_t smem = narrow::fwd_smem(Cin, Cout, side.max_slots);
   const int grid = total < 148 * 4 ? total : 148 * 4;      // several CTAs per SM hide the table -> value load chain of a tile
+  if (nparts) *nparts = stats ? grid : 0;
   if (Cout == 64) {
     auto k = narrow::fwd_kernel<3, 2>;
     if (narrow_config(k, smem)) return -3;
-    k<<<grid, narrow::THREADS, smem, st>>>(plan_dev, side, X, W, bias, Y, group, B, total);
+    k<<<grid, narrow::THREADS, smem, st>>>(plan_dev, side, X, W, bias, Y, group, B, total, stats, y_f16);
   } else {
     auto k = narrow::fwd_kernel<3, 4>;
     if (narrow_config(k, smem)) return -3;
-    k<<<grid, narrow::THREADS, smem, st>>>(plan_dev, side, X, W, bias, Y, group, B, total);
+    k<<<grid, narrow::THREADS, smem, st>>>(plan_dev, side, X, W, bias, Y, group, B, total, stats, y_f16);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

@@ -258,10 +258,21 @@ class _Chain(torch.autograd.Function):
             plan = get_plan(_lib.PLAN_HEXCONV, level, 1, conv.corner_mode, dev)
             packed = _pack(conv.weight.detach().contiguous(), 3, C)
             xs, sb, sp, sc = pixel_strides(x)
-            y = _empty((B * _P(level), C), torch.float32, dev)
-            _lib.check(L.gin_hexconv_fwd(plan.host_ptr, plan.dev_ptr, xs.data_ptr(), sb, sp, sc, packed.data_ptr(), conv.bias.data_ptr(),
-                                         y.data_ptr(), B, 3, C, _lib.IMPL_AUTO, _stream()), 'gin_hexconv_fwd')
-            stat = _bn_stats(y, 0, C, B * _P(level), C, bn)
+            import ctypes
+            y = _empty((B * _P(level), C), torch.float16 if _Y16 else torch.float32, dev)
+            sparts = _empty(L.gin_hexconv_narrow_stats_ws_bytes(C) // 4, torch.float32, dev)
+            npart = ctypes.c_int(0)
+            rc = L.gin_hexconv_fwd_narrow_stats(plan.host_ptr, plan.dev_ptr, xs.data_ptr(), sb, sp, sc, packed.data_ptr(), conv.bias.data_ptr(),
+                                                y.data_ptr(), 1 if _Y16 else 0, B, 3, C, sparts.data_ptr(), ctypes.addressof(npart), _stream())
+            if rc == 0 and npart.value > 0:          # output statistics came out of the conv epilogue
+                stat = _bn_stats(y, 0, C, B * _P(level), C, bn, (sparts, npart.value))
+            else:
+                if rc != 0 and rc != _lib.ERR_UNSUPPORTED:
+                    _lib.check(rc, 'gin_hexconv_fwd_narrow_stats')
+                y = _empty((B * _P(level), C), torch.float32, dev)
+                _lib.check(L.gin_hexconv_fwd(plan.host_ptr, plan.dev_ptr, xs.data_ptr(), sb, sp, sc, packed.data_ptr(), conv.bias.data_ptr(),
+                                             y.data_ptr(), B, 3, C, _lib.IMPL_AUTO, _stream()), 'gin_hexconv_fwd')
+                stat = _bn_stats(y, 0, C, B * _P(level), C, bn)
             act_b, _, act_w = _bn_act(y, 0, C, stat, None, 0, 0, None, B, level, C)
             saved.append(dict(kind='stem', plan=plan, xs=xs, strides=(sb, sp, sc), y=y, stat=stat, out_b=act_w, C=C, level=level, packed=packed))
             i = 3

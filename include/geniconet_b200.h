@@ -96,6 +96,13 @@ int gin_hexconv_pack_weights_bf16_multi(int n, const float* const* w0, const int
 int gin_hexconv_fwd(const void* plan_host, const void* plan_dev, const float* x, int64_t sb, int64_t sp, int64_t sc,
                     const void* packed, const float* bias /* may be NULL */, float* y,
                     int B, int Cin, int Cout, int impl, void* stream);
+/* The xyz input layer (Cin = 3, models.py:104) inside a fused chain: the same forward, with the BatchNorm column sums of its output
+ * taken in the epilogue (stats_ws: gin_hexconv_narrow_stats_ws_bytes(Cout); *nparts rows of [2][Cout] for gin_bn_stats_from_parts) and
+ * y optionally written as fp16 (it is only read by BatchNorm kernels).  GIN_ERR_UNSUPPORTED for any other layer. */
+size_t gin_hexconv_narrow_stats_ws_bytes(int Cout);
+int gin_hexconv_fwd_narrow_stats(const void* plan_host, const void* plan_dev, const float* x, int64_t sb, int64_t sp, int64_t sc,
+                                 const void* packed, const float* bias, void* y, int y_fp16, int B, int Cin, int Cout, float* stats_ws,
+                                 int* nparts, void* stream);
 /* autograd backward of the above (run.py:249), row a5: dgrad = adjoint of pad o conv. */
 int gin_hexconv_dgrad(const void* plan_host, const void* plan_dev, const float* dy, const void* packed, float* dx,
                       int B, int Cin, int Cout, int impl, void* stream);
