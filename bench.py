@@ -301,6 +301,15 @@ def conv_roofline(table, peaks, args, B):
 
 
 def run_ours(args):
+    world_env = int(os.environ.get('WORLD_SIZE', 1))
+    if world_env > 1:
+        # Data parallel: the persistent conv kernels leave GIN_DP_SPARE_SMS SMs to the NCCL kernels, which are held to that many
+        # CTAs -- otherwise the all-reduce cannot overlap backward at all (profiles/r02_dp_overhead_breakdown.md).  Both must be
+        # in the environment before the library / NCCL initialise.
+        spare = int(os.environ.get('GIN_DP_SPARE_SMS', '8'))
+        if spare > 0:
+            os.environ.setdefault('GIN_SMS', str(148 - spare))
+            os.environ.setdefault('NCCL_MAX_CTAS', str(spare))
     import torch
     import torch.distributed as dist
     from geniconet_b200 import _lib, models as gm, losses, data

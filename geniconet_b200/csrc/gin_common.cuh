@@ -33,6 +33,9 @@ inline int num_sms() {
   if (!n[d]) {
     int v = kMaxSMs;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || v <= 0) v = kMaxSMs;
+    // GIN_SMS: leave some SMs to a concurrent kernel (data-parallel training: the NCCL all-reduce).  The persistent kernels own an SM
+    // per CTA and hand tiles out statically, so a kernel that takes SMs from them would push CTAs into a second wave.
+    if (const char* e = getenv("GIN_SMS")) { const int cap = atoi(e); if (cap >= 8 && cap < v) v = cap; }
     n[d] = v < kMaxSMs ? v : kMaxSMs;
   }
   return n[d];
