@@ -490,3 +490,39 @@ def test_upsample_sharing_survives_in_place_ops():
     (3 * up0(xr).sum()).backward()
     assert torch.allclose(xg.grad, xr.grad)
     clear_caches()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('y16', [0, 1])
+def test_stem_forward_with_epilogue_statistics(y16):
+    """gin_hexconv_fwd_narrow_stats (the xyz layer inside a fused chain): output against the oracle conv, BatchNorm column sums
+    from the epilogue against sums over the fp32 oracle output, fp16 or fp32 output."""
+    import ctypes
+    from geniconet_b200 import _lib
+    from geniconet_b200.ico_conv import get_plan
+    L = _lib.lib
+    level, B, C = 4, 3, 64
+    n, P = 2 ** level, 10 * 4 ** level
+    torch.manual_seed(4)
+    ref = icocnn_ref.IcoConvS2S(3, C, 1, True, level, 'average')
+    x = torch.randn(B, 3, 5 * n, 2 * n)
+    with torch.no_grad():
+        yr = ref(x).permute(0, 2, 3, 1).reshape(B * P, C)
+    plan = get_plan(_lib.PLAN_HEXCONV, level, 1, 'average', 'cuda')
+    st = torch.cuda.current_stream().cuda_stream
+    w = ref.weight.detach().cuda().contiguous()
+    packed = torch.empty(L.gin_hexconv_packed_bytes(3, C), dtype=torch.uint8, device='cuda')
+    _lib.check(L.gin_hexconv_pack_weights(w.data_ptr(), packed.data_ptr(), 3, C, st))
+    xc = x.cuda()
+    y = torch.empty(B * P, C, dtype=torch.float16 if y16 else torch.float32, device='cuda')
+    parts = torch.empty(L.gin_hexconv_narrow_stats_ws_bytes(C) // 4, dtype=torch.float32, device='cuda')
+    npart = ctypes.c_int(0)
+    _lib.check(L.gin_hexconv_fwd_narrow_stats(plan.host_ptr, plan.dev_ptr, xc.data_ptr(), xc.stride(0), xc.stride(3), xc.stride(1), packed.data_ptr(),
+                                              ref.bias.detach().cuda().data_ptr(), y.data_ptr(), y16, B, 3, C, parts.data_ptr(), ctypes.addressof(npart), st))
+    torch.cuda.synchronize()
+    assert npart.value > 0
+    tol = 2e-3 if y16 else 1e-5
+    assert torch.allclose(y.float().cpu(), yr, rtol=tol, atol=tol)
+    sums = parts[:npart.value * 2 * C].view(npart.value, 2, C).double().sum(0).cpu()
+    assert torch.allclose(sums[0], yr.double().sum(0), rtol=1e-4, atol=1e-3)
+    assert torch.allclose(sums[1], (yr.double() ** 2).sum(0), rtol=1e-4, atol=1e-3)
