@@ -337,7 +337,8 @@ def run_ours(args):
         broadcast_parameters(model)
     f = (params['ico']['factor_pos'], params['ico']['factor_nor'], params['ico']['factor_lap'])
     crit = losses.P2PKLD_Loss(args.level, *f, 1.0) if args.model == 'ico2ico_vae' else losses.P2P_Loss(args.level, *f)
-    buckets = GradBuckets(model.parameters(), world)
+    from geniconet_b200 import fused as _fused
+    buckets = GradBuckets(model.parameters(), world, adjacent=_fused.weight_pairs(model))
     use_graph = not args.no_graph
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=use_graph)
 

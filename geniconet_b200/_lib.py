@@ -70,6 +70,7 @@ _SIGS = {
     'gin_hexconv_fwd_bf16_stats': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     'gin_hexconv_fwd_bf16_stats2': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     'gin_bn_stats_from_parts': (_i, [_vp, _i, _i64, _i64, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    'gin_bn_stats_from_parts2': (_i, [_vp, _i, _i64, _i64, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     'gin_hexconv_dgrad_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'gin_hexconv_wgrad_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'gin_bn_ws_bytes': (_sz, [_i]),

@@ -221,7 +221,7 @@ int gin_hexconv_pack_weights_bf16_multi(int n, const float* const* w0, const int
     J.bd[j] = reinterpret_cast<unsigned short*>(pk + packed_off_bd(Cin[j], Cout));
     J.first[j] = blocks;
     const long long nel = 7LL * Cin[j] * Cout;
-    int nb = (int)((nel + 256 * 8 - 1) / (256 * 8));           // 8 elements per thread
+    int nb = (int)((nel / 4 + 256 * 2 - 1) / (256 * 2));       // nel / 4 sixteen-byte chunks (both images), two per thread
     if (nb < 1) nb = 1;
     blocks += nb;
   }
@@ -652,6 +652,17 @@ int gin_bn_stats_from_parts(const float* parts, int nparts, int64_t ld, int64_t 
   gin::launch_pdl(gin::bn::stats_final_kernel, dim3(C / 8), dim3(256), 0, (cudaStream_t)stream, parts, nparts, rows, C, gamma, beta, eps, momentum, running_mean, running_var,
                                                                        reinterpret_cast<long long*>(num_batches_tracked), stat, ld);
   return check_launch("bn_stats_final");
+}
+
+int gin_bn_stats_from_parts2(const float* parts, int nparts, int64_t ld, int64_t rows, int C, int colA, const float* gammaA, const float* betaA,
+                             float epsA, float momentumA, float* rmeanA, float* rvarA, int64_t* nbtA, float* statA, int colB, const float* gammaB,
+                             const float* betaB, float epsB, float momentumB, float* rmeanB, float* rvarB, int64_t* nbtB, float* statB, void* stream) {
+  if (!parts || nparts <= 0 || nparts > gin::bn::MAX_CTAS || !statA || !statB || rows <= 0 || !bn_shape_ok(C) || colA < 0 || colB < 0 || ld < C + (colA > colB ? colA : colB))
+    return fail(GIN_ERR_ARG, "gin_bn_stats_from_parts2: bad argument");
+  gin::bn::StatsTarget a{parts + colA, gammaA, betaA, rmeanA, rvarA, reinterpret_cast<long long*>(nbtA), statA, epsA, momentumA};
+  gin::bn::StatsTarget b{parts + colB, gammaB, betaB, rmeanB, rvarB, reinterpret_cast<long long*>(nbtB), statB, epsB, momentumB};
+  gin::launch_pdl(gin::bn::stats_final2_kernel, dim3(2 * (C / 8)), dim3(256), 0, (cudaStream_t)stream, a, b, nparts, (long long)rows, C, (long long)ld);
+  return check_launch("bn_stats_final2");
 }
 
 int gin_bn_act_fwd(const void* y1, int64_t ld1, const float* stat1, const void* y2, int64_t ld2, const float* stat2, int y_fp16, int relu, void* out_b,

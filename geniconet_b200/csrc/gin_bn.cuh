@@ -178,6 +178,48 @@ stats_final_kernel(const float* __restrict__ partial, int nblocks, long long row
   }
 }
 
+// Two BatchNorms whose statistics come from column slices of the SAME partial-sum rows (the two sibling convolutions of a residual
+// block run as one GEMM): one launch, blockIdx.x < C/8 -> the first, else the second.
+struct StatsTarget {
+  const float* partial;      // first column of this BatchNorm inside the partial-sum rows
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  long long* num_batches_tracked;
+  float* stat;
+  float eps, momentum;
+};
+__global__ void __launch_bounds__(256)
+stats_final2_kernel(StatsTarget a, StatsTarget b, int nblocks, long long rows, int C, long long ld) {
+  GIN_PDL_SYNC();
+  __shared__ double sums[16];
+  const int nb = C / 8;
+  const bool second = (int)blockIdx.x >= nb;
+  const StatsTarget& t = second ? b : a;
+  const int blk = second ? blockIdx.x - nb : blockIdx.x;
+  // final_sum indexes channels by blockIdx.x: shift the base pointer instead
+  const double s = final_sum(t.partial - (second ? (size_t)nb * 8 : 0), nblocks, C + (second ? nb * 8 : 0), ld);
+  if (threadIdx.x < 16) sums[threadIdx.x] = s;
+  __syncthreads();
+  const int c = blk * 8 + threadIdx.x;
+  if (t.num_batches_tracked && blk == 0 && threadIdx.x == 0) *t.num_batches_tracked += 1;
+  if (threadIdx.x < 8 && c < C) {
+    const double mean = sums[threadIdx.x] / (double)rows;
+    double var = sums[8 + threadIdx.x] / (double)rows - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)t.eps));
+    const float g = t.gamma ? t.gamma[c] : 1.f, be = t.beta ? t.beta[c] : 0.f;
+    const float scale = g * invstd;
+    t.stat[c] = (float)mean; t.stat[C + c] = invstd; t.stat[2 * C + c] = scale; t.stat[3 * C + c] = be - (float)mean * scale;
+    if (t.running_mean) {
+      const double unbiased = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
+      t.running_mean[c] = (1.f - t.momentum) * t.running_mean[c] + t.momentum * (float)mean;
+      t.running_var[c] = (1.f - t.momentum) * t.running_var[c] + t.momentum * (float)unbiased;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ forward apply
 // out[row, :] = act(y1*scale1 + shift1 [+ y2*scale2 + shift2]) -> bf16 rows [0, rows) of out_b, per-sample pole means
 // (mean over the pole's five ring pixels of the fp32 values) in rows [rows, rows + 2B), optional fp32 copy out_f.

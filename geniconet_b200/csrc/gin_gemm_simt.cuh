@@ -347,24 +347,33 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackJobs 
   const int Cin = J.cin[j], Cout = J.cout[j], Cout0 = J.cout0[j];
   const float* __restrict__ w0 = J.w0[j];
   const float* __restrict__ w1 = J.w1[j];
-  unsigned short* __restrict__ bf = J.bf[j];
-  unsigned short* __restrict__ bd = J.bd[j];
-  const long long n = (long long)Cin * Cout * 7;
+  // One thread = one 16-byte chunk (8 consecutive K elements) of a tile image, threads in the order of the image: the stores are
+  // whole 128-byte rows; the reads are strided gathers from the fp32 weight, which is a few MB and L2-resident.
+  //   forward image  [t][Cin/64][Cout][8 chunks]: K = ci, row n = co;   dgrad image [t][Cout/64][Cin][8 chunks]: K = co, row n = ci
+  const long long half = 7LL * Cin * Cout / 8, n = 2 * half;
   const int nb = J.first[j + 1] - J.first[j];
   for (long long i = (long long)(blockIdx.x - J.first[j]) * 256 + threadIdx.x; i < n; i += (long long)nb * 256) {
-    const int t = (int)(i % 7);
-    const long long r = i / 7;
-    const int ci = (int)(r % Cin), co = (int)(r / Cin);
-    const float v = co < Cout0 ? w0[i] : w1[i - (long long)Cout0 * Cin * 7];
-    const unsigned short h = cvt_op(v, 0), hf = cvt_op(v, J.fwd_f16);
-    {
-      const int kc = ci >> 6, c = (ci >> 3) & 7, e = ci & 7;
-      bf[((((size_t)t * (Cin >> 6) + kc) * Cout + co) << 6) + (((c ^ (co & 7)) << 3) | e)] = hf;
+    const bool dg = i >= half;
+    long long pos = dg ? i - half : i;
+    const int cpos = (int)(pos & 7);
+    pos >>= 3;
+    const int N = dg ? Cin : Cout, K = dg ? Cout : Cin;
+    const int row = (int)(pos % N);
+    pos /= N;
+    const int kc = (int)(pos % (K >> 6)), t = (int)(pos / (K >> 6));
+    const int k0 = kc * 64 + ((cpos ^ (row & 7)) << 3);       // first of the 8 K elements this physical chunk holds
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int co = dg ? k0 + e : row, ci = dg ? row : k0 + e;
+      const long long src = ((long long)co * Cin + ci) * 7 + t;
+      v[e] = co < Cout0 ? __ldg(w0 + src) : __ldg(w1 + (src - (long long)Cout0 * Cin * 7));
     }
-    {
-      const int kc = co >> 6, c = (co >> 3) & 7, e = co & 7;
-      bd[((((size_t)t * (Cout >> 6) + kc) * Cin + ci) << 6) + (((c ^ (ci & 7)) << 3) | e)] = h;
-    }
+    const int f16 = dg ? 0 : J.fwd_f16;
+    uint4 o;
+    o.x = pack2_op(v[0], v[1], f16); o.y = pack2_op(v[2], v[3], f16); o.z = pack2_op(v[4], v[5], f16); o.w = pack2_op(v[6], v[7], f16);
+    unsigned short* img = dg ? J.bd[j] : J.bf[j];
+    *reinterpret_cast<uint4*>(img + (dg ? i - half : i) * 8) = o;
   }
 }
 

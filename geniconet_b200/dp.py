@@ -28,24 +28,46 @@ class GradBuckets:
     p.grad at the reduced views.  With world_size 1 nothing is copied or exchanged at all.
     """
 
-    def __init__(self, params, world_size, bucket_bytes=None, process_group=None):
+    def __init__(self, params, world_size, bucket_bytes=None, process_group=None, adjacent=()):
         import os
         if bucket_bytes is None:
             bucket_bytes = int(float(os.environ.get('GIN_DP_BUCKET_MB', '8')) * (1 << 20))
         self.world = int(world_size)
         self.group = process_group
-        # reverse registration order ~ the order gradients become ready in backward
-        self.params = [p for p in params if p.requires_grad][::-1]
+        # reverse registration order ~ the order gradients become ready in backward.  `adjacent`: tuples of parameters whose
+        # gradients one kernel produces as ONE tensor (fused.weight_pairs): they are laid out side by side, in the given order, and
+        # never split across buckets, so that kernel can write into the bucket directly (grad_dest).
+        order = [p for p in params if p.requires_grad][::-1]
+        group_of = {}
+        for grp in adjacent:
+            if all(q.requires_grad for q in grp):
+                for q in grp:
+                    group_of[id(q)] = tuple(grp)
+        self.params, seen, units = [], set(), []
+        for p in order:
+            if id(p) in seen:
+                continue
+            unit = list(group_of.get(id(p), (p,)))
+            for q in unit:
+                seen.add(id(q))
+            units.append(unit)
+            self.params += unit
         self.buckets = []          # (flat tensor, [params], [views])
         cur, cur_n = [], 0
-        for p in self.params:
-            cur.append(p)
-            cur_n += p.numel() * 4
+        for unit in units:
+            cur += unit
+            cur_n += sum(q.numel() for q in unit) * 4
             if cur_n >= bucket_bytes:
                 self._seal(cur)
                 cur, cur_n = [], 0
         if cur:
             self._seal(cur)
+        self._slot = {}            # id(param) -> (bucket index, element offset)
+        for bi, (flat, ps, views) in enumerate(self.buckets):
+            off = 0
+            for q in ps:
+                self._slot[id(q)] = (bi, off)
+                off += q.numel()
         self._pending = [0] * len(self.buckets)
         self._handles = []
         self._early = set()          # id(param) of gradients that arrived through early_grads() this step
@@ -79,6 +101,7 @@ class GradBuckets:
         if self.world > 1 and os.environ.get('GIN_DP_EARLY', '1') != '0':
             from . import fused
             fused.set_grad_sink(self.early_grads)
+            fused.set_grad_dest(self.grad_dest)
 
     def _on_grad(self, p):
         if id(p) in self._early:                         # already counted (and copied) when the fused chain produced it
@@ -87,6 +110,18 @@ class GradBuckets:
         self._pending[bi] -= 1
         if self._pending[bi] == 0:
             self._launch(bi)
+
+    def grad_dest(self, params):
+        """The bucket storage of `params` laid end to end, if that is how the bucket holds them (adjacent, in this order)."""
+        if self.world <= 1 or not params or any(id(q) not in self._slot for q in params):
+            return None
+        bi, off0 = self._slot[id(params[0])]
+        off = off0
+        for q in params:
+            if self._slot[id(q)] != (bi, off):
+                return None
+            off += q.numel()
+        return self.buckets[bi][0][off0:off]
 
     def early_grads(self, pairs):
         """(parameter, gradient) pairs whose gradient kernels are enqueued on the current stream although autograd has not
@@ -100,7 +135,9 @@ class GradBuckets:
             if bi is None or id(p) in self._early or g is None:
                 continue
             self._early.add(id(p))
-            self._early_grad[id(p)] = g.view_as(p)      # copied into the bucket in ONE launch when the bucket is complete
+            slot_bi, slot_off = self._slot[id(p)]
+            if g.data_ptr() != self.buckets[slot_bi][0].data_ptr() + 4 * slot_off:      # else: the kernel wrote it in place
+                self._early_grad[id(p)] = g.view_as(p)  # copied into the bucket in ONE launch when the bucket is complete
             self._pending[bi] -= 1
             touched.add(bi)
         for bi in touched:
@@ -111,7 +148,7 @@ class GradBuckets:
         flat, ps, views = self.buckets[bi]
         have = [(v, p.grad) for v, p in zip(views, ps) if p.grad is not None and id(p) not in self._early]
         have += [(v, self._early_grad.pop(id(p))) for v, p in zip(views, ps) if id(p) in self._early_grad]
-        if len(have) < len(ps):
+        if len([p for p in ps if p.grad is not None or id(p) in self._early]) < len(ps):
             # parameters that got no gradient this step contribute zeros (their slots may hold last step's averages)
             missing = [v for v, p in zip(views, ps) if p.grad is None and id(p) not in self._early]
             torch._foreach_zero_(missing)
@@ -144,6 +181,7 @@ class GradBuckets:
                 p.grad = v
         from . import fused
         fused.set_grad_sink(None)
+        fused.set_grad_dest(None)
 
     def total_bytes(self):
         return sum(f.numel() * 4 for f, _, _ in self.buckets)

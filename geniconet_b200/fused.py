@@ -146,11 +146,12 @@ def _conv_dgrad(plan, dyb, packed, B, cin, cout, p_in):
     return dx
 
 
-def _conv_wgrad(plan, xb, dyb, B, cin, cout, side=None):
-    """dW [cout][cin][7].  With `side` (a CUDA stream) the wgrad is issued there: nothing on the rest of the backward pass depends
-    on it, so the tensor-bound wgrad overlaps the memory-bound BatchNorm backward kernels of the main stream."""
+def _conv_wgrad(plan, xb, dyb, B, cin, cout, side=None, out=None):
+    """dW [cout][cin][7] (written into `out` when given: a data-parallel bucket slot).  With `side` (a CUDA stream) the wgrad is
+    issued there: nothing on the rest of the backward pass depends on it, so the tensor-bound wgrad overlaps the memory-bound
+    BatchNorm backward kernels of the main stream."""
     if side is None:
-        dW = _empty((cout, cin, 7), torch.float32, xb.device)
+        dW = out if out is not None else _empty((cout, cin, 7), torch.float32, xb.device)
         ws = _empty(L.gin_hexconv_wgrad_ws_bytes(cin, cout), torch.uint8, xb.device)
         _lib.check(L.gin_hexconv_wgrad_bf16(plan.host_ptr, plan.dev_ptr, xb.data_ptr(), dyb.data_ptr(), None, dW.data_ptr(), None, ws.data_ptr(),
                                             B, cin, cout, _stream()), 'gin_hexconv_wgrad_bf16')
@@ -171,6 +172,7 @@ import os as _os
 _Y16 = _os.environ.get('GIN_Y_FP16', '1') != '0'
 _side_streams = {}
 _grad_sink = None
+_grad_dest = None
 
 
 def set_grad_sink(fn):
@@ -179,6 +181,26 @@ def set_grad_sink(fn):
     removes it.  The chain still returns the same gradients to autograd afterwards."""
     global _grad_sink
     _grad_sink = fn
+
+
+def set_grad_dest(fn):
+    """fn(tuple of parameters) -> a contiguous fp32 tensor that IS the gradient storage of those parameters laid end to end (a
+    slot of a data-parallel bucket), or None.  The chain's wgrad kernels then write straight into it (no bucket copy)."""
+    global _grad_dest
+    _grad_dest = fn
+
+
+def weight_pairs(model):
+    """The (conv00.weight, conv10.weight) pairs of every residual block: their gradients come out of ONE wgrad GEMM as one
+    [2*Cout, Cin, 7] tensor, so a data-parallel bucket that keeps each pair adjacent can receive it in place."""
+    return [(m.conv00.weight, m.conv10.weight) for m in model.modules() if _is_block(m)]
+
+
+def _dest(params, shape):
+    if _grad_dest is None:
+        return None
+    t = _grad_dest(params)
+    return t.view(shape) if t is not None and t.numel() == int(torch.Size(shape).numel()) else None
 
 
 def _wgrad_stream(dev):
@@ -301,7 +323,7 @@ class _Chain(torch.autograd.Function):
             blk = mods[j]
             cm = blk.conv00.corner_mode
             cin, cout = blk.conv00.in_features, blk.conv00.out_features
-            st = dict(kind='down' if blk._down else 'up', cin=cin, cout=cout, in_level=level)
+            st = dict(kind='down' if blk._down else 'up', cin=cin, cout=cout, in_level=level, blk=blk)
             if blk._down:
                 lvl = level - 1
                 plan_a = get_plan(_lib.PLAN_HEXCONV, level, 2, cm, dev)
@@ -320,8 +342,18 @@ class _Chain(torch.autograd.Function):
             rows = B * _P(lvl)
             pk_cat, pk01 = packs[2 * (j - i)], packs[2 * (j - i) + 1]
             ycat, pcat = _conv_fwd(plan_a, a_b, pk_cat, blk.conv00.bias.detach(), B, cin, 2 * cout, _P(lvl), bias1=blk.conv10.bias.detach())   # [rows][conv00 | conv10]
-            stat00 = _bn_stats(ycat, 0, 2 * cout, rows, cout, blk.icobn00, pcat)
-            stat10 = _bn_stats(ycat, cout, 2 * cout, rows, cout, blk.icobn10, pcat)
+            if pcat is not None:                 # both sibling BatchNorms from the same epilogue sums: one launch
+                stat00, stat10 = _empty(4 * cout, torch.float32, dev), _empty(4 * cout, torch.float32, dev)
+                bA, bB = blk.icobn00, blk.icobn10
+                _lib.check(L.gin_bn_stats_from_parts2(pcat[0].data_ptr(), pcat[1], 2 * cout, rows, cout,
+                                                      0, bA.weight.data_ptr(), bA.bias.data_ptr(), float(bA.eps), float(bA.momentum), bA.running_mean.data_ptr(),
+                                                      bA.running_var.data_ptr(), bA.num_batches_tracked.data_ptr(), stat00.data_ptr(),
+                                                      cout, bB.weight.data_ptr(), bB.bias.data_ptr(), float(bB.eps), float(bB.momentum), bB.running_mean.data_ptr(),
+                                                      bB.running_var.data_ptr(), bB.num_batches_tracked.data_ptr(), stat10.data_ptr(), _stream()),
+                           'gin_bn_stats_from_parts2')
+            else:
+                stat00 = _bn_stats(ycat, 0, 2 * cout, rows, cout, blk.icobn00, pcat)
+                stat10 = _bn_stats(ycat, cout, 2 * cout, rows, cout, blk.icobn10, pcat)
             h_b, _, h_w = _bn_act(ycat, 0, 2 * cout, stat00, None, 0, 0, None, B, lvl, cout)
             y01, p01 = _conv_fwd(plan_b, h_b, pk01, blk.conv01.bias.detach(), B, cout, cout, _P(lvl))
             stat01 = _bn_stats(y01, 0, cout, rows, cout, blk.icobn01, p01)
@@ -371,10 +403,13 @@ class _Chain(torch.autograd.Function):
                                                  bs01.data_ptr(), dy01_b.data_ptr(), cout, st['ycat'].data_ptr() + st['ycat'].element_size() * cout, 2 * cout,
                                                  st['stat10'].data_ptr(), bs10.data_ptr(), dycat_b.data_ptr() + 2 * cout, 2 * cout,
                                                  1 if st['ycat'].dtype == torch.float16 else 0, ws.data_ptr(), B, lvl, cout, _stream()), 'gin_bn_act_bwd_pair')
-                dW01 = _conv_wgrad(st['plan_b'], st['h_b'], dy01_b, B, cout, cout, side)
+                blk = st['blk']
+                dW01 = _conv_wgrad(st['plan_b'], st['h_b'], dy01_b, B, cout, cout, side,
+                                   out=_dest((blk.conv01.weight,), (cout, cout, 7)) if side is None else None)
                 d_h = _conv_dgrad(st['plan_b'], dy01_b, st['pk01'], B, cout, cout, _P(lvl))
                 bs00, _ = _bn_bwd(d_h, st['h_b'], st['ycat'], 0, 2 * cout, st['stat00'], B, lvl, cout, dycat_b, 0, 2 * cout)
-                dWcat = _conv_wgrad(st['plan_a'], st['a_b'], dycat_b, B, cin, 2 * cout, side)
+                dWcat = _conv_wgrad(st['plan_a'], st['a_b'], dycat_b, B, cin, 2 * cout, side,
+                                    out=_dest((blk.conv00.weight, blk.conv10.weight), (2 * cout, cin, 7)) if side is None else None)
                 p_in = _P(lvl + 1) if st['kind'] == 'down' else _P(lvl)
                 d_in = _conv_dgrad(st['plan_a'], dycat_b, st['pk_cat'], B, cin, 2 * cout, p_in)
                 if st['kind'] == 'up':

@@ -170,6 +170,12 @@ int gin_bn_stats(const float* y, int64_t ld, int64_t rows, int C, const float* g
 /* The same from per-CTA partial sums `parts` = nparts rows of [2][ld] (here pointing at the first of the C columns wanted). */
 int gin_bn_stats_from_parts(const float* parts, int nparts, int64_t ld, int64_t rows, int C, const float* gamma, const float* beta, float eps,
                             float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked, float* stat, void* stream);
+/* Two BatchNorms from column slices colA / colB of the same partial-sum rows (the two sibling convolutions of a residual block run
+ * as one GEMM) in one launch. */
+int gin_bn_stats_from_parts2(const float* parts, int nparts, int64_t ld, int64_t rows, int C, int colA, const float* gammaA, const float* betaA,
+                             float epsA, float momentumA, float* rmeanA, float* rvarA, int64_t* nbtA, float* statA, int colB,
+                             const float* gammaB, const float* betaB, float epsB, float momentumB, float* rmeanB, float* rvarB,
+                             int64_t* nbtB, float* statB, void* stream);
 /* out = act(y1*scale1 + shift1 [+ y2*scale2 + shift2]) at level `level`: out_b (may be NULL) = 16-bit [B*P + 2B][C] (pixels, then the
  * per-sample pole means) in the forward operand format -- exactly what gin_cast_bf16(which = 0) would produce from out;
  * out_f (may be NULL) = fp32 [B*P][C]; out_w (may be NULL) = the same rows as out_b in bf16 (which = 2: wgrad operand, ReLU mask). */

@@ -65,7 +65,7 @@ dist.all_reduce(flat, op=dist.ReduceOp.SUM)
 flat /= world
 # (3) the graphed data-parallel step
 restore_bn()
-buckets = GradBuckets(model.parameters(), world)
+buckets = GradBuckets(model.parameters(), world, adjacent=fused.weight_pairs(model))
 early_counts = []
 
 

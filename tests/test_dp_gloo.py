@@ -173,3 +173,20 @@ def test_single_rank_is_a_noop():
     g = m.weight.grad.clone()
     b.finish()
     assert torch.equal(g, m.weight.grad) and b.total_bytes() == 4 * (16 + 4)
+
+
+def test_bucket_layout_keeps_sibling_weights_adjacent():
+    """fused.weight_pairs: the two sibling convolutions' weight gradients come out of one wgrad GEMM as ONE tensor; the bucket
+    lays each pair out side by side (never across a bucket boundary) so that kernel can write in place (grad_dest)."""
+    from geniconet_b200.dp import GradBuckets
+    ps = [torch.nn.Parameter(torch.zeros(n)) for n in (6, 10, 4, 8, 12)]
+    b = GradBuckets(ps, 2, bucket_bytes=64, adjacent=[(ps[3], ps[0]), (ps[1],)])
+    assert sorted(id(q) for q in b.params) == sorted(id(q) for q in ps)
+    d = b.grad_dest((ps[3], ps[0]))
+    assert d is not None and d.numel() == 14
+    bi, off = b._slot[id(ps[3])]
+    assert b._slot[id(ps[0])] == (bi, off + 8)
+    views = dict((id(q), v) for _, qs, vs in b.buckets for q, v in zip(qs, vs))
+    assert d.data_ptr() == views[id(ps[3])].data_ptr() and d[8:].data_ptr() == views[id(ps[0])].data_ptr()
+    assert b.grad_dest((ps[0], ps[3])) is None and b.grad_dest((ps[1],)).numel() == 10
+    assert GradBuckets(ps, 1, adjacent=[(ps[3], ps[0])]).grad_dest((ps[3], ps[0])) is None      # single rank: nothing to exchange

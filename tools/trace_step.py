@@ -44,7 +44,8 @@ if world > 1:
     broadcast_parameters(model)
 f = (params['ico']['factor_pos'], params['ico']['factor_nor'], params['ico']['factor_lap'])
 crit = losses.P2PKLD_Loss(args.level, *f, 1.0) if args.model == 'ico2ico_vae' else losses.P2P_Loss(args.level, *f)
-buckets = GradBuckets(model.parameters(), world)
+from geniconet_b200 import fused as _fused                                   # noqa: E402
+buckets = GradBuckets(model.parameters(), world, adjacent=_fused.weight_pairs(model))
 opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=True)
 ids = shard_sample_ids(0, rank, world, min(B, 4))
 xs, ts = zip(*(data.synthetic_mesh(args.level, i) for i in ids))
