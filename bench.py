@@ -340,7 +340,9 @@ def run_ours(args):
     from geniconet_b200 import fused as _fused
     buckets = GradBuckets(model.parameters(), world, adjacent=_fused.weight_pairs(model))
     use_graph = not args.no_graph
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=use_graph)
+    # data parallel: one optimizer per gradient bucket, stepped as soon as that bucket's all-reduce is done -- the last (smallest)
+    # exchange then hides behind the update of the earlier buckets
+    opts = [torch.optim.Adam(ps, lr=1e-4, fused=True, capturable=use_graph) for ps in (buckets.bucket_params() if world > 1 else [list(model.parameters())])]
 
     # one synthetic shard per rank, staged in pinned host memory
     ids = shard_sample_ids(0, rank, world, B)
@@ -353,8 +355,10 @@ def run_ours(args):
         buckets.reset()
         loss = crit(model(x), t)
         loss.backward()
+        for bi, o in enumerate(opts):
+            buckets.finish_bucket(bi)
+            o.step()
         buckets.finish()
-        opt.step()
         return loss
 
     def barrier():

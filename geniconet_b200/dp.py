@@ -158,27 +158,45 @@ class GradBuckets:
             return
         if dist.get_backend(self.group) == 'nccl':
             h = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
-            self._handles.append((h, None))
+            self._handles.append((h, None, bi))
         else:
             h = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-            self._handles.append((h, flat))
+            self._handles.append((h, flat, bi))
+
+    def bucket_params(self):
+        """The parameters of every bucket, in bucket order (one optimizer per bucket can then update a bucket as soon as ITS
+        all-reduce is done, see finish_bucket)."""
+        return [list(ps) for _, ps, _ in self.buckets]
+
+    def _flush(self):
+        for bi, n in enumerate(self._pending):      # buckets with parameters that got no gradient this step
+            if n > 0:
+                self._pending[bi] = 0
+                self._launch(bi)
+
+    def finish_bucket(self, bi):
+        """After backward: wait for bucket `bi` only and expose its averaged gradients as p.grad.  Calling it bucket by bucket
+        with an optimizer per bucket hides the last (smallest, latest) all-reduce behind the update of the earlier buckets."""
+        if self.world <= 1:
+            return
+        self._flush()
+        for k, (h, flat, hb) in enumerate(self._handles):
+            if hb == bi and h is not None:
+                h.wait()
+                if flat is not None:
+                    flat.div_(self.world)
+                self._handles[k] = (None, None, hb)
+        _, ps, views = self.buckets[bi]
+        for p, v in zip(ps, views):
+            p.grad = v
 
     def finish(self):
         """Wait for every bucket and expose the averaged gradients as p.grad; call after backward and before optimizer.step."""
         if self.world <= 1:
             return
-        for bi, n in enumerate(self._pending):      # buckets with parameters that got no gradient this step
-            if n > 0:
-                self._pending[bi] = 0
-                self._launch(bi)
-        for h, flat in self._handles:
-            h.wait()
-            if flat is not None:
-                flat.div_(self.world)
+        for bi in range(len(self.buckets)):
+            self.finish_bucket(bi)
         self._handles = []
-        for _, ps, views in self.buckets:
-            for p, v in zip(ps, views):
-                p.grad = v
         from . import fused
         fused.set_grad_sink(None)
         fused.set_grad_dest(None)

@@ -46,7 +46,7 @@ f = (params['ico']['factor_pos'], params['ico']['factor_nor'], params['ico']['fa
 crit = losses.P2PKLD_Loss(args.level, *f, 1.0) if args.model == 'ico2ico_vae' else losses.P2P_Loss(args.level, *f)
 from geniconet_b200 import fused as _fused                                   # noqa: E402
 buckets = GradBuckets(model.parameters(), world, adjacent=_fused.weight_pairs(model))
-opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=True)
+opts = [torch.optim.Adam(ps, lr=1e-4, fused=True, capturable=True) for ps in (buckets.bucket_params() if world > 1 else [list(model.parameters())])]
 ids = shard_sample_ids(0, rank, world, min(B, 4))
 xs, ts = zip(*(data.synthetic_mesh(args.level, i) for i in ids))
 x = torch.stack(xs).repeat((B + 3) // 4, 1, 1, 1)[:B].cuda()
@@ -57,8 +57,10 @@ def step(xb, tb):
     buckets.reset()
     loss = crit(model(xb), tb)
     loss.backward()
+    for bi, o in enumerate(opts):
+        buckets.finish_bucket(bi)
+        o.step()
     buckets.finish()
-    opt.step()
     return loss
 
 
