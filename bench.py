@@ -303,10 +303,11 @@ def conv_roofline(table, peaks, args, B):
 def run_ours(args):
     world_env = int(os.environ.get('WORLD_SIZE', 1))
     if world_env > 1:
-        # Data parallel: the persistent conv kernels leave GIN_DP_SPARE_SMS SMs to the NCCL kernels, which are held to that many
-        # CTAs -- otherwise the all-reduce cannot overlap backward at all (profiles/r02_dp_overhead_breakdown.md).  Both must be
+        # Experiment switch (off by default): leave GIN_DP_SPARE_SMS SMs to the NCCL kernels and hold NCCL to that many CTAs.
+        # Measured WORSE at every setting (2 ranks: 4.046 ms with 0, 4.064 with 4, 4.122 with 8, 4.153 with 16 spare SMs --
+        # profiles/r02_dp_overhead_breakdown.md): the conv kernels lose more than the exchange gains.  Both variables must be
         # in the environment before the library / NCCL initialise.
-        spare = int(os.environ.get('GIN_DP_SPARE_SMS', '8'))
+        spare = int(os.environ.get('GIN_DP_SPARE_SMS', '0'))
         if spare > 0:
             os.environ.setdefault('GIN_SMS', str(148 - spare))
             os.environ.setdefault('NCCL_MAX_CTAS', str(spare))

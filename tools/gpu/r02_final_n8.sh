@@ -5,5 +5,5 @@ cat gpurun_out/dp_parity_n2.json gpurun_out/dp_parity_n4.json gpurun_out/dp_pari
 port=29600
 run() { out=$1; n=$2; shift 2; port=$((port+1)); if [ $n = 1 ]; then python bench.py $B "$@" > gpurun_out/$out 2> gpurun_out/$out.err; else python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port bench.py --gpus $n $B "$@" > gpurun_out/$out 2> gpurun_out/$out.err; fi; head -c 230 gpurun_out/$out; echo; }
 for n in 1 2 4 8; do run r02_bench_n$n.scale.json $n; done
-for n in 1 8; do run r02_bench_vae_n$n.json $n --model ico2ico_vae; done
-for n in 1 2 4 8; do run r02_bench_i6_n$n.json $n --level 6 --batch 16; done
+run r02_bench_vae_n8.json 8 --model ico2ico_vae
+run r02_bench_i6_n8.json 8 --level 6 --batch 16
