@@ -516,7 +516,8 @@ int gin_upsample_bwd(const void* plan_host, const void* plan_dev, const float* d
   if (rc) return rc;
   if (B == 0) return GIN_OK;
   const long long work = (long long)B * h->Pc * (C / 4);
-  gin::upsample_bwd_kernel<<<grid_for(work, 256, 16), 256, 0, st>>>(plan_words(plan_dev), dy, dx, B, C);
+  if (work < 0x7fffffffLL) gin::upsample_bwd_kernel<unsigned><<<grid_for(work, 256, 16), 256, 0, st>>>(plan_words(plan_dev), dy, dx, B, C);
+  else gin::upsample_bwd_kernel<long long><<<grid_for(work, 256, 16), 256, 0, st>>>(plan_words(plan_dev), dy, dx, B, C);
   return check_launch("upsample_bwd");
 }
 
@@ -674,8 +675,14 @@ int gin_bn_act_fwd(const void* y1, int64_t ld1, const float* stat1, const void* 
   const int ctas = gin::bn::grid_for_rows(((long long)B * P + 2LL * B) * (C >> 3));
   const gin::bn::Src s1{reinterpret_cast<const float*>(y1), (long long)ld1, y_fp16 ? 1 : 0}, s2{reinterpret_cast<const float*>(y2), (long long)ld2, y_fp16 ? 1 : 0};
   const int f16 = (int)gin::fwd_fp16();          // out_b is the next convolution's FORWARD operand copy
-  if (y2) gin::launch_pdl(gin::bn::act_fwd_kernel<true>, dim3(ctas), dim3(256), 0, st, s1, stat1, s2, stat2, relu, reinterpret_cast<__nv_bfloat16*>(out_b), out_f, n, B, P, C, f16, reinterpret_cast<__nv_bfloat16*>(out_w));
-  else gin::launch_pdl(gin::bn::act_fwd_kernel<false>, dim3(ctas), dim3(256), 0, st, s1, stat1, s2, stat2, relu, reinterpret_cast<__nv_bfloat16*>(out_b), out_f, n, B, P, C, f16, reinterpret_cast<__nv_bfloat16*>(out_w));
+  if (!gin::bn::smem_consts(C)) {
+    if (y2) gin::launch_pdl(gin::bn::act_fwd_anyc_kernel<true>, dim3(ctas), dim3(256), 0, st, s1, stat1, s2, stat2, relu, reinterpret_cast<__nv_bfloat16*>(out_b), out_f, n, B, P, C, f16, reinterpret_cast<__nv_bfloat16*>(out_w));
+    else gin::launch_pdl(gin::bn::act_fwd_anyc_kernel<false>, dim3(ctas), dim3(256), 0, st, s1, stat1, s2, stat2, relu, reinterpret_cast<__nv_bfloat16*>(out_b), out_f, n, B, P, C, f16, reinterpret_cast<__nv_bfloat16*>(out_w));
+  } else {
+    auto k = y2 ? (y_fp16 ? gin::bn::act_fwd_kernel<true, true> : gin::bn::act_fwd_kernel<true, false>)
+                : (y_fp16 ? gin::bn::act_fwd_kernel<false, true> : gin::bn::act_fwd_kernel<false, false>);
+    gin::launch_pdl(k, dim3(ctas), dim3(256), 0, st, s1, stat1, s2, stat2, relu, reinterpret_cast<__nv_bfloat16*>(out_b), out_f, n, B, P, C, f16, reinterpret_cast<__nv_bfloat16*>(out_w));
+  }
   return check_launch("bn_act_fwd");
 }
 
@@ -694,7 +701,7 @@ int gin_bn_act_bwd(const float* dout, int64_t ldg, const void* mask_b, const voi
   if (rc) return rc;
   gin::launch_pdl(gin::bn::bwd_final_kernel, dim3(C / 8), dim3(256), 0, st, reinterpret_cast<const float*>(ws), ctas, rows, C, bstat);
   if ((rc = check_launch("bn_bwd_final"))) return rc;
-  gin::launch_pdl(gin::bn::bwd_apply_kernel, dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sy, stat, bstat, reinterpret_cast<__nv_bfloat16*>(dy_b), ldo, dy_f, ldf, n, B, P, C);
+  gin::launch_pdl(!gin::bn::smem_consts(C) ? gin::bn::bwd_apply_anyc_kernel : (y_fp16 ? gin::bn::bwd_apply_kernel<true> : gin::bn::bwd_apply_kernel<false>), dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sy, stat, bstat, reinterpret_cast<__nv_bfloat16*>(dy_b), ldo, dy_f, ldf, n, B, P, C);
   return check_launch("bn_bwd_apply");
 }
 
@@ -711,12 +718,12 @@ int gin_bn_act_bwd_pair(const float* dout, int64_t ldg, const void* mask_b, cons
   const gin::bn::Src sA{reinterpret_cast<const float*>(yA), (long long)ldA, y_fp16 ? 1 : 0}, sB{reinterpret_cast<const float*>(yB), (long long)ldB, y_fp16 ? 1 : 0};
   const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(mask_b);
   const int ctas = gin::bn::grid_for_rows(rows * (C >> 3));
-  gin::launch_pdl(gin::bn::bwd_reduce2_kernel, dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sA, statA, sB, statB, rows, C, reinterpret_cast<float*>(ws));
+  gin::launch_pdl(!gin::bn::smem_consts(C) ? gin::bn::bwd_reduce2_anyc_kernel : (y_fp16 ? gin::bn::bwd_reduce2_kernel<true> : gin::bn::bwd_reduce2_kernel<false>), dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sA, statA, sB, statB, rows, C, reinterpret_cast<float*>(ws));
   int rc = check_launch("bn_bwd_reduce2");
   if (rc) return rc;
   gin::launch_pdl(gin::bn::bwd_final2_kernel, dim3(C / 8), dim3(256), 0, st, reinterpret_cast<const float*>(ws), ctas, rows, C, bstatA, bstatB);
   if ((rc = check_launch("bn_bwd_final2"))) return rc;
-  gin::launch_pdl(gin::bn::bwd_apply2_kernel, dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sA, statA, bstatA, sB, statB, bstatB, reinterpret_cast<__nv_bfloat16*>(dyA_b), ldoA,
+  gin::launch_pdl(!gin::bn::smem_consts(C) ? gin::bn::bwd_apply2_anyc_kernel : (y_fp16 ? gin::bn::bwd_apply2_kernel<true> : gin::bn::bwd_apply2_kernel<false>), dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sA, statA, bstatA, sB, statB, bstatB, reinterpret_cast<__nv_bfloat16*>(dyA_b), ldoA,
                                                    reinterpret_cast<__nv_bfloat16*>(dyB_b), ldoB, n, B, P, C);
   return check_launch("bn_bwd_apply2");
 }
@@ -732,8 +739,10 @@ int gin_upsample_bf16(const void* plan_host, const void* plan_dev, const void* i
   const int ctas = gin::bn::grid_for_rows(((long long)B * h->Pf + 2LL * B) * (C >> 3));
   const int grid = ctas * 4 > 148 * 8 ? 148 * 8 : ctas * 4;
   const int f16 = (int)gin::fwd_fp16();          // both the source copy (when 16-bit) and the result are forward operands
-  if (in_is_f32) gin::launch_pdl(gin::bn::upsample_bf16_kernel<true>, dim3(grid), dim3(256), 0, st, plan_words(plan_dev), in, reinterpret_cast<__nv_bfloat16*>(out_b), 2 << h->level, B, C, f16, reinterpret_cast<__nv_bfloat16*>(out_w));
-  else gin::launch_pdl(gin::bn::upsample_bf16_kernel<false>, dim3(grid), dim3(256), 0, st, plan_words(plan_dev), in, reinterpret_cast<__nv_bfloat16*>(out_b), 2 << h->level, B, C, f16, reinterpret_cast<__nv_bfloat16*>(out_w));
+  const bool small = ((long long)B * h->Pf + 2LL * B) * (C >> 3) < 0x7fffffffLL;
+  auto k = in_is_f32 ? (small ? gin::bn::upsample_bf16_kernel<true, unsigned> : gin::bn::upsample_bf16_kernel<true, long long>)
+                     : (small ? gin::bn::upsample_bf16_kernel<false, unsigned> : gin::bn::upsample_bf16_kernel<false, long long>);
+  gin::launch_pdl(k, dim3(grid), dim3(256), 0, st, plan_words(plan_dev), in, reinterpret_cast<__nv_bfloat16*>(out_b), 2 << h->level, B, C, f16, reinterpret_cast<__nv_bfloat16*>(out_w));
   return check_launch("upsample_bf16");
 }
 

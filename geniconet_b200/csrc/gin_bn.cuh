@@ -243,7 +243,7 @@ GIN_DEVINL void apply_row(const Src& y1, const Src& y2, long long r, int c, cons
 
 template <bool TWO>
 __global__ void __launch_bounds__(256)
-act_fwd_kernel(Src y1, const float* __restrict__ stat1, Src y2, const float* __restrict__ stat2, int relu, __nv_bfloat16* __restrict__ out_b,
+act_fwd_anyc_kernel(Src y1, const float* __restrict__ stat1, Src y2, const float* __restrict__ stat2, int relu, __nv_bfloat16* __restrict__ out_b,
                float* __restrict__ out_f, int nlat, int B, int P, int C, int f16, __nv_bfloat16* __restrict__ out_w) {
   GIN_PDL_SYNC();
   const int C8 = C >> 3;
@@ -324,7 +324,7 @@ bwd_final_kernel(const float* __restrict__ partial, int nblocks, long long rows,
 
 // dy = scale * (g - c1 - yhat*c2) -> bf16 copy (rows + per-sample pole means of dy, row stride ldo) and/or fp32 (row stride ldf)
 __global__ void __launch_bounds__(256)
-bwd_apply_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, Src y, const float* __restrict__ stat,
+bwd_apply_anyc_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, Src y, const float* __restrict__ stat,
                  const float* __restrict__ bstat, __nv_bfloat16* __restrict__ dy_b, long long ldo, float* __restrict__ dy_f, long long ldf,
                  int nlat, int B, int P, int C) {
   GIN_PDL_SYNC();
@@ -400,36 +400,40 @@ GIN_DEVINL void up_pixel(const int32_t* __restrict__ src, const void* __restrict
     for (int k = 0; k < 8; ++k) o[k] = 0.5f * (o[k] + t[k]);
   }
 }
-template <bool F32>
+// Idx: the work-item index type -- unsigned when B*(Pf+2)*C/8 < 2^31 (four 32-bit divisions per item instead of four emulated
+// 64-bit ones, which made this kernel instruction-bound: ncu r02 sm throughput 47 % at 47 % of the HBM rate), else long long.
+template <bool F32, typename Idx>
 __global__ void __launch_bounds__(256)
 upsample_bf16_kernel(const int32_t* __restrict__ plan, const void* __restrict__ xin, __nv_bfloat16* __restrict__ out, int nfine, int B, int C, int f16,
                      __nv_bfloat16* __restrict__ out_w) {
   GIN_PDL_SYNC();
   const GinUpPlanHdr* h = reinterpret_cast<const GinUpPlanHdr*>(plan);
-  const int Pc = h->Pc, Pf = h->Pf, C8 = C >> 3;
+  const int Pc = h->Pc, C8 = C >> 3;
+  const Idx Pf = (Idx)h->Pf, nC8 = (Idx)C8;
   const int32_t* src = plan + h->fwd_off;
   const int32_t* cring = plan + h->ring_off;
-  const long long n_main = (long long)B * Pf * C8, n_all = n_main + 2LL * B * C8;
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n_all; i += gridDim.x * 256LL) {
-    const int c = (int)(i % C8) * 8;
-    const long long row = i / C8;
+  const Idx n_rows = (Idx)B * Pf, n_main = n_rows * nC8, n_all = n_main + (Idx)(2 * B) * nC8;
+  for (Idx i = (Idx)blockIdx.x * 256 + threadIdx.x; i < n_all; i += (Idx)gridDim.x * 256) {
+    const Idx row = i / nC8;
+    const int c = (int)(i - row * nC8) * 8;
     float o[8];
     if (i < n_main) {
-      up_pixel<F32>(src, xin, cring, row / Pf, B, Pc, (int)(row % Pf), C, c, o, f16);
+      const Idx sample = row / Pf;
+      up_pixel<F32>(src, xin, cring, (long long)sample, B, Pc, (int)(row - sample * Pf), C, c, o, f16);
     } else {
-      const long long j = row - (long long)B * Pf;
-      const int pole = (int)(j & 1);
+      const int j = (int)(row - n_rows);
+      const int pole = j & 1;
 #pragma unroll
       for (int k = 0; k < 8; ++k) o[k] = 0.f;
       for (int e = 0; e < 5; ++e) {
         float t[8];
-        up_pixel<F32>(src, xin, cring, j >> 1, B, Pc, ring_pixel(nfine, pole, e), C, c, t, f16);
+        up_pixel<F32>(src, xin, cring, (long long)(j >> 1), B, Pc, ring_pixel(nfine, pole, e), C, c, t, f16);
 #pragma unroll
         for (int k = 0; k < 8; ++k) o[k] = fmaf(0.2f, t[k], o[k]);
       }
     }
-    st8_op(out + row * C + c, o, f16);
-    if (out_w) st8_op(out_w + row * C + c, o, 0);
+    st8_op(out + (size_t)row * C + c, o, f16);
+    if (out_w) st8_op(out_w + (size_t)row * C + c, o, 0);
   }
 }
 
@@ -438,7 +442,7 @@ upsample_bf16_kernel(const int32_t* __restrict__ plan, const void* __restrict__ 
 // mask are read once for both (10 -> 7 bytes per element and pass).  partial[blk][4][C] = sum g (A), sum g*yhatA, sum g (B: same
 // as A, kept for symmetry), sum g*yhatB.
 __global__ void __launch_bounds__(256)
-bwd_reduce2_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, Src yA, const float* __restrict__ statA,
+bwd_reduce2_anyc_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, Src yA, const float* __restrict__ statA,
                    Src yB, const float* __restrict__ statB, long long rows, int C, float* __restrict__ partial) {
   GIN_PDL_SYNC();
   __shared__ float part[3][256][9];
@@ -508,7 +512,7 @@ bwd_final2_kernel(const float* __restrict__ partial, int nblocks, long long rows
 
 // dyA, dyB as bf16 gradient copies (row strides ldoA / ldoB, pole-mean rows included)
 __global__ void __launch_bounds__(256)
-bwd_apply2_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, Src yA, const float* __restrict__ statA,
+bwd_apply2_anyc_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, Src yA, const float* __restrict__ statA,
                   const float* __restrict__ bstatA, Src yB, const float* __restrict__ statB, const float* __restrict__ bstatB,
                   __nv_bfloat16* __restrict__ dyA, long long ldoA, __nv_bfloat16* __restrict__ dyB, long long ldoB, int nlat, int B, int P, int C) {
   GIN_PDL_SYNC();
@@ -550,6 +554,278 @@ bwd_apply2_kernel(const float* __restrict__ dout, long long ldg, const __nv_bflo
     st8_bf16(dyA + (i / C8) * ldoA + c, oA);
     st8_bf16(dyB + (i / C8) * ldoB + c, oB);
   }
+}
+
+// ------------------------------------------------------------------------------------------------ C <= 256: constants in shared memory
+// The streaming kernels above keep every per-channel constant of a thread's 8 channels in registers: 96 (bwd_apply), 98
+// (bwd_reduce2) and 162 (bwd_apply2) registers per thread, i.e. 2, 2 and ONE resident CTA per SM -- 8 to 16 warps cannot keep
+// enough loads in flight to fill HBM (ncu r02: 37-47 % of the copy bandwidth, profiles/r02_membound_*.txt).  The versions below
+// hold the constants in shared memory (pre-combined once per CTA), re-read them every iteration through `ld.shared` that the
+// compiler may not hoist (asm volatile), replace the 64-bit divisions by shifts (C/8 is a power of two) and fit 4+ CTAs per SM.
+constexpr int CST_MAX_C = 256;
+#ifndef GIN_BN_SMEM_DEFAULT
+#define GIN_BN_SMEM_DEFAULT 0
+#endif
+GIN_DEVINL void cst_put(float (*t)[2][32][4], int k, int ch, float v) { t[k][(ch >> 2) & 1][ch >> 3][ch & 3] = v; }
+template <int K>
+GIN_DEVINL void lds8(uint32_t base, float v[8]) {          // constant K of this thread's 8 channels; base = &cst[0][0][c8][0]
+  // "memory": the compiler must see these as reads of the table (its stores are otherwise dead) -- callers therefore issue ALL
+  // their global loads before the first lds8, or the loads would be serialised behind it
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(base), "n"(K * 1024) : "memory");
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(base), "n"(K * 1024 + 512) : "memory");
+}
+GIN_DEVINL int log2_pow2(int v) { return __ffs(v) - 1; }
+// the source format as a template argument: half the loads (and registers) of the run-time switch in ld8_src
+template <bool F16>
+GIN_DEVINL void ld8_y(const Src& s, long long r, int c, float v[8]) {
+  if (!F16) { ld8(s.p + r * s.ld + c, v); return; }
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(s.p) + r * s.ld + c));
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+
+// o = y1*sc1 + (sh1 [+ sh2]) [+ y2*sc2], optional ReLU
+template <bool TWO, bool F16>
+GIN_DEVINL void apply_row_s(const Src& y1, const Src& y2, long long r, int c, uint32_t cb, int relu, float o[8]) {
+  float v[8], k[8];
+  ld8_y<F16>(y1, r, c, v);
+  if (TWO) {
+    float w[8];
+    ld8_y<F16>(y2, r, c, w);
+    lds8<2>(cb, k);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = w[j] * k[j];
+    lds8<1>(cb, k);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] += k[j];
+  } else {
+    lds8<1>(cb, o);
+  }
+  lds8<0>(cb, k);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = fmaf(v[j], k[j], o[j]);
+  if (relu) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+  }
+}
+
+template <bool TWO, bool F16>
+__global__ void __launch_bounds__(256, 4)
+act_fwd_kernel(Src y1, const float* __restrict__ stat1, Src y2, const float* __restrict__ stat2, int relu, __nv_bfloat16* __restrict__ out_b,
+               float* __restrict__ out_f, int nlat, int B, int P, int C, int f16, __nv_bfloat16* __restrict__ out_w) {
+  GIN_PDL_SYNC();
+  __shared__ __align__(16) float cst[3][2][32][4];
+  for (int ch = threadIdx.x; ch < C; ch += 256) {
+    cst_put(cst, 0, ch, stat1[2 * C + ch]);
+    cst_put(cst, 1, ch, stat1[3 * C + ch] + (TWO ? stat2[3 * C + ch] : 0.f));
+    if (TWO) cst_put(cst, 2, ch, stat2[2 * C + ch]);
+  }
+  __syncthreads();
+  const int C8 = C >> 3, sh = log2_pow2(C8), c8 = threadIdx.x & (C8 - 1), c = c8 * 8;
+  const uint32_t cb = (uint32_t)__cvta_generic_to_shared(&cst[0][0][c8][0]);
+  const long long rows = (long long)B * P, n_main = rows << sh, n_all = n_main + ((2LL * B) << sh);
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n_all; i += gridDim.x * 256LL) {
+    const long long row = i >> sh;
+    float o[8];
+    if (i < n_main) {
+      apply_row_s<TWO, F16>(y1, y2, row, c, cb, relu, o);
+      if (out_f) st8(out_f + row * C + c, o);
+    } else {
+      const int j = (int)(row - rows), sample = j >> 1, pole = j & 1;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = 0.f;
+      for (int e = 0; e < 5; ++e) {
+        float t[8];
+        apply_row_s<TWO, F16>(y1, y2, (long long)sample * P + ring_pixel(nlat, pole, e), c, cb, relu, t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = fmaf(0.2f, t[k], o[k]);
+      }
+    }
+    if (out_b) st8_op(out_b + row * C + c, o, f16);
+    if (out_w) st8_op(out_w + row * C + c, o, 0);          // the bf16 twin wgrad reads (and the ReLU mask of the backward)
+  }
+}
+
+// g = dout * (out > 0)
+GIN_DEVINL void masked_grad(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, long long r, int c, int C, float g[8]) {
+  ld8(dout + r * ldg + c, g);
+  if (mask) {
+    bool m[8];
+    ld8_mask(mask + r * C + c, m);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] = m[k] ? g[k] : 0.f;
+  }
+}
+// dy = a*g - b - (y - mean)*e  with  a = scale, b = scale*c1, e = scale*invstd*c2  (constants K0 .. K0+3: a, b, mean, e)
+template <int K0>
+GIN_DEVINL void bn_dy(uint32_t cb, const float g[8], float o[8]) {          // o: in y, out dy
+  float k[8];
+  lds8<K0 + 2>(cb, k);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] -= k[j];
+  lds8<K0 + 3>(cb, k);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] *= k[j];
+  lds8<K0>(cb, k);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = fmaf(k[j], g[j], -o[j]);
+  lds8<K0 + 1>(cb, k);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] -= k[j];
+}
+GIN_DEVINL void bn_dy_consts(float (*cst)[2][32][4], int k0, const float* __restrict__ stat, const float* __restrict__ bstat, int C) {
+  for (int ch = threadIdx.x; ch < C; ch += 256) {
+    const float scale = stat[2 * C + ch];
+    cst_put(cst, k0, ch, scale);
+    cst_put(cst, k0 + 1, ch, scale * bstat[2 * C + ch]);
+    cst_put(cst, k0 + 2, ch, stat[ch]);
+    cst_put(cst, k0 + 3, ch, scale * stat[C + ch] * bstat[3 * C + ch]);
+  }
+}
+
+template <bool F16>
+__global__ void __launch_bounds__(256, 4)
+bwd_apply_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, Src y, const float* __restrict__ stat,
+                 const float* __restrict__ bstat, __nv_bfloat16* __restrict__ dy_b, long long ldo, float* __restrict__ dy_f, long long ldf,
+                 int nlat, int B, int P, int C) {
+  GIN_PDL_SYNC();
+  __shared__ __align__(16) float cst[4][2][32][4];
+  bn_dy_consts(cst, 0, stat, bstat, C);
+  __syncthreads();
+  const int C8 = C >> 3, sh = log2_pow2(C8), c8 = threadIdx.x & (C8 - 1), c = c8 * 8;
+  const uint32_t cb = (uint32_t)__cvta_generic_to_shared(&cst[0][0][c8][0]);
+  const long long rows = (long long)B * P, n_main = rows << sh, n_all = n_main + (dy_b ? (2LL * B) << sh : 0);
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n_all; i += gridDim.x * 256LL) {
+    const long long row = i >> sh;
+    float o[8], g[8];
+    if (i < n_main) {
+      masked_grad(dout, ldg, mask, row, c, C, g);
+      ld8_y<F16>(y, row, c, o);
+      bn_dy<0>(cb, g, o);
+      if (dy_f) st8(dy_f + row * ldf + c, o);
+    } else {
+      const int j = (int)(row - rows), sample = j >> 1, pole = j & 1;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = 0.f;
+      for (int e = 0; e < 5; ++e) {
+        const long long r = (long long)sample * P + ring_pixel(nlat, pole, e);
+        float t[8];
+        masked_grad(dout, ldg, mask, r, c, C, g);
+        ld8_y<F16>(y, r, c, t);
+        bn_dy<0>(cb, g, t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = fmaf(0.2f, t[k], o[k]);
+      }
+    }
+    if (dy_b) st8_bf16(dy_b + row * ldo + c, o);
+  }
+}
+
+// partial[blk][4][C] = sum g | sum g*yhatA | sum g | sum g*yhatB; inside the loop only the means are needed:
+// sum g*yhat = invstd * sum g*(y - mean)
+template <bool F16>
+__global__ void __launch_bounds__(256, 4)
+bwd_reduce2_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, Src yA, const float* __restrict__ statA,
+                   Src yB, const float* __restrict__ statB, long long rows, int C, float* __restrict__ partial) {
+  GIN_PDL_SYNC();
+  __shared__ float part[3][256][9];
+  __shared__ __align__(16) float cst[2][2][32][4];
+  for (int ch = threadIdx.x; ch < C; ch += 256) { cst_put(cst, 0, ch, statA[ch]); cst_put(cst, 1, ch, statB[ch]); }
+  __syncthreads();
+  const int C8 = C >> 3, sh = log2_pow2(C8), c8 = threadIdx.x & (C8 - 1), c = c8 * 8;
+  const uint32_t cb = (uint32_t)__cvta_generic_to_shared(&cst[0][0][c8][0]);
+  const long long n = rows << sh;
+  float s0[8], s1[8], s2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s0[k] = s1[k] = s2[k] = 0.f;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+    const long long r = i >> sh;
+    float g[8], v[8], w[8], m[8];
+    masked_grad(dout, ldg, mask, r, c, C, g);
+    ld8_y<F16>(yA, r, c, v);
+    ld8_y<F16>(yB, r, c, w);
+    lds8<0>(cb, m);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s0[k] += g[k]; s1[k] = fmaf(g[k], v[k] - m[k], s1[k]); }
+    lds8<1>(cb, m);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s2[k] = fmaf(g[k], w[k] - m[k], s2[k]);
+  }
+  {
+    float iA[8], iB[8];
+    ld8(statA + C + c, iA); ld8(statB + C + c, iB);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { part[0][threadIdx.x][k] = s0[k]; part[1][threadIdx.x][k] = s1[k] * iA[k]; part[2][threadIdx.x][k] = s2[k] * iB[k]; }
+  }
+  __syncthreads();
+  float* mine = partial + (size_t)blockIdx.x * 4 * C;
+  for (int i = threadIdx.x; i < 4 * C; i += 256) {
+    const int w = i / C, cc = i - w * C, g8 = cc >> 3, k = cc & 7;
+    const int src = w == 2 ? 0 : (w == 3 ? 2 : w);       // rows: sum g | sum g*yhatA | sum g | sum g*yhatB
+    float acc = 0.f;
+    for (int t = g8; t < 256; t += C8) acc += part[src][t][k];
+    mine[i] = acc;
+  }
+}
+
+template <bool F16>
+__global__ void __launch_bounds__(256, 4)
+bwd_apply2_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, Src yA, const float* __restrict__ statA,
+                  const float* __restrict__ bstatA, Src yB, const float* __restrict__ statB, const float* __restrict__ bstatB,
+                  __nv_bfloat16* __restrict__ dyA, long long ldoA, __nv_bfloat16* __restrict__ dyB, long long ldoB, int nlat, int B, int P, int C) {
+  GIN_PDL_SYNC();
+  __shared__ __align__(16) float cst[8][2][32][4];
+  bn_dy_consts(cst, 0, statA, bstatA, C);
+  bn_dy_consts(cst, 4, statB, bstatB, C);
+  __syncthreads();
+  const int C8 = C >> 3, sh = log2_pow2(C8), c8 = threadIdx.x & (C8 - 1), c = c8 * 8;
+  const uint32_t cb = (uint32_t)__cvta_generic_to_shared(&cst[0][0][c8][0]);
+  const long long rows = (long long)B * P, n_main = rows << sh, n_all = n_main + ((2LL * B) << sh);
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n_all; i += gridDim.x * 256LL) {
+    const long long row = i >> sh;
+    float g[8], o[8], oB[8];
+    if (i < n_main) {
+      masked_grad(dout, ldg, mask, row, c, C, g);
+      ld8_y<F16>(yA, row, c, o);
+      ld8_y<F16>(yB, row, c, oB);
+      bn_dy<0>(cb, g, o);
+      bn_dy<4>(cb, g, oB);
+      st8_bf16(dyA + row * ldoA + c, o);
+      st8_bf16(dyB + row * ldoB + c, oB);
+    } else {
+      // pole-mean rows (2B of them): one BatchNorm after the other keeps the register count of the main path
+      const int j = (int)(row - rows), sample = j >> 1, pole = j & 1;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = oB[k] = 0.f;
+      for (int e = 0; e < 10; ++e) {
+        const long long r = (long long)sample * P + ring_pixel(nlat, pole, e % 5);
+        float t[8];
+        masked_grad(dout, ldg, mask, r, c, C, g);
+        if (e < 5) {
+          ld8_y<F16>(yA, r, c, t);
+          bn_dy<0>(cb, g, t);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = fmaf(0.2f, t[k], o[k]);
+        } else {
+          ld8_y<F16>(yB, r, c, t);
+          bn_dy<4>(cb, g, t);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) oB[k] = fmaf(0.2f, t[k], oB[k]);
+        }
+      }
+      st8_bf16(dyA + row * ldoA + c, o);
+      st8_bf16(dyB + row * ldoB + c, oB);
+    }
+  }
+}
+
+// GIN_BN_SMEM=0: the register-constant kernels (*_anyc_kernel) for every C
+inline bool smem_consts(int C) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GIN_BN_SMEM"); v = e ? (e[0] != '0') : GIN_BN_SMEM_DEFAULT; }
+  return v == 1 && C <= CST_MAX_C;
 }
 
 // CTAs of the streaming BatchNorm kernels: GIN_BN_CTAS (experiments), default 4 per SM

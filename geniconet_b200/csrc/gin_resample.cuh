@@ -47,19 +47,21 @@ upsample_fwd_kernel(const int32_t* __restrict__ plan, const float* __restrict__ 
   }
 }
 
-// dx[b, c, :] = sum_e w[c][e] * dy[b, idx[c][e], :]
+// dx[b, c, :] = sum_e w[c][e] * dy[b, idx[c][e], :].  Idx: unsigned when B*Pc*C/4 < 2^31 (32-bit index arithmetic), else long long.
+template <typename Idx>
 __global__ void __launch_bounds__(256)
 upsample_bwd_kernel(const int32_t* __restrict__ plan, const float* __restrict__ dy, float* __restrict__ dx, int B, int C) {
   const GinUpPlanHdr* h = reinterpret_cast<const GinUpPlanHdr*>(plan);
-  const int Pc = h->Pc, Pf = h->Pf, C4 = C >> 2, deg = h->bwd_deg;
+  const int Pf = h->Pf, deg = h->bwd_deg;
+  const Idx Pc = (Idx)h->Pc, C4 = (Idx)(C >> 2);
   const int32_t* idx = plan + h->bwd_idx_off;
   const float* w = reinterpret_cast<const float*>(plan + h->bwd_w_off);
-  const long long total = (long long)B * Pc * C4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C4) * 4;
-    const long long bp = i / C4;
-    const int p = (int)(bp % Pc);
-    const long long b = bp / Pc;
+  const Idx total = (Idx)B * Pc * C4;
+  for (Idx i = (Idx)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (Idx)gridDim.x * blockDim.x) {
+    const Idx bp = i / C4;
+    const int c = (int)(i - bp * C4) * 4;
+    const Idx b = bp / Pc;
+    const int p = (int)(bp - b * Pc);
     const float* dyb = dy + (size_t)b * Pf * C;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int e = 0; e < deg; ++e) {

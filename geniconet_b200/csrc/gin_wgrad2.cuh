@@ -269,14 +269,17 @@ wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, i
     const int pr = tm.acc[tap], h = tm.half[tap];
     const int unit = (ci >> 6) + n_cblk * (co / n_blk);
     const float* src = partial + ((size_t)unit * slices * 4 + pr) * BM * n_blk + (size_t)(h * 64 + (ci & 63)) * n_blk + (co % n_blk);
-    float a0 = 0.f, a1 = 0.f;
-    int s = 0;
-    for (; s + 1 < slices; s += 2) {
-      a0 += __ldg(src + (size_t)s * 4 * BM * n_blk);
-      a1 += __ldg(src + (size_t)(s + 1) * 4 * BM * n_blk);
+    // eight slices in flight per thread (two measured latency-bound: ~10 us for 25 MB that sit in L2); the adds keep slice order
+    const size_t ss = (size_t)4 * BM * n_blk;
+    float acc = 0.f;
+    for (int s = 0; s < slices; s += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = s + j < slices ? __ldg(src + (size_t)(s + j) * ss) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += v[j];
     }
-    if (s < slices) a0 += __ldg(src + (size_t)s * 4 * BM * n_blk);
-    dW[((size_t)co * Cin + ci) * 7 + tap] = a0 + a1;
+    dW[((size_t)co * Cin + ci) * 7 + tap] = acc;
   }
 }
 
