@@ -33,6 +33,8 @@ def parse():
     ap.add_argument('--level', type=int, default=5)
     ap.add_argument('--batch', type=int, default=None, help='per-GPU batch (default 36 at I5, 16 at I6)')
     ap.add_argument('--conv-impl', default='auto', choices=['auto', 'simt', 'tc'])
+    ap.add_argument('--optimizer', default=os.environ.get('GIN_BENCH_OPTIMIZER', 'torch'), choices=['gin', 'torch'],
+                    help="gin: geniconet_b200.optim.Adam (one launch per step); torch: torch.optim.Adam(fused=True)")
     ap.add_argument('--no-graph', action='store_true', help='issue every launch from Python instead of replaying one CUDA graph per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-table', action='store_true')
@@ -343,7 +345,12 @@ def run_ours(args):
     use_graph = not args.no_graph
     # data parallel: one optimizer per gradient bucket, stepped as soon as that bucket's all-reduce is done -- the last (smallest)
     # exchange then hides behind the update of the earlier buckets
-    opts = [torch.optim.Adam(ps, lr=1e-4, fused=True, capturable=use_graph) for ps in (buckets.bucket_params() if world > 1 else [list(model.parameters())])]
+    if args.optimizer == 'gin':
+        from geniconet_b200.optim import Adam as _Adam
+        make_opt = lambda ps: _Adam(ps, lr=1e-4)
+    else:
+        make_opt = lambda ps: torch.optim.Adam(ps, lr=1e-4, fused=True, capturable=use_graph)
+    opts = [make_opt(ps) for ps in (buckets.bucket_params() if world > 1 else [list(model.parameters())])]
 
     # one synthetic shard per rank, staged in pinned host memory
     ids = shard_sample_ids(0, rank, world, B)
@@ -479,6 +486,7 @@ def run_ours(args):
                 'data': 'synthetic',
                 'config': workload_config(args.model, args.level, B),
                 'details': {'conv_impl': args.conv_impl, 'parallelism': 'dp%d' % world,
+                            'optimizer': 'geniconet_b200.optim.Adam (gin_adam_step, one launch)' if args.optimizer == 'gin' else 'torch.optim.Adam(fused=True)',
                             'launch': 'one CUDA graph replay per step' if use_graph else 'eager (one launch per kernel)'},
                 'e2e': {'value': meshes / (ms_e2e * 1e-3), 'unit': 'meshes/s', 'ms_per_step': ms_e2e,
                         'h2d_bytes_per_step': x_host.numel() * 4 + t_host.numel() * 4, 'd2h_bytes_per_step': 4},

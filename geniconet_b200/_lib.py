@@ -89,6 +89,8 @@ _SIGS = {
     'gin_kld_bwd': (_i, [_vp, _vp, _vp, _f, _vp, _vp, _i64, _vp]),
     'gin_pole_vertices_fwd': (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _i, _i, _vp]),
     'gin_pole_vertices_bwd': (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _vp]),
+    'gin_adam_chunk': (_i, []),
+    'gin_adam_step': (_i, [_vp, _vp, _i, _i, _f, _vp, _f, _f, _f, _f, _vp, _vp]),
     'gin_head_ws_bytes': (_sz, []),
     'gin_head_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i, _i, _vp]),
     'gin_head_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _vp]),

@@ -20,6 +20,7 @@
 #include "gin_wgrad_tcp.cuh"
 #include "gin_loss.cuh"
 #include "gin_narrow.cuh"
+#include "gin_adam.cuh"
 #include "gin_bn.cuh"
 #include "gin_resample.cuh"
 #include "gin_dist.cuh"
@@ -726,6 +727,22 @@ int gin_bn_act_bwd_pair(const float* dout, int64_t ldg, const void* mask_b, cons
   gin::launch_pdl(!gin::bn::smem_consts(C) ? gin::bn::bwd_apply2_anyc_kernel : (y_fp16 ? gin::bn::bwd_apply2_kernel<true> : gin::bn::bwd_apply2_kernel<false>), dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sA, statA, bstatA, sB, statB, bstatB, reinterpret_cast<__nv_bfloat16*>(dyA_b), ldoA,
                                                    reinterpret_cast<__nv_bfloat16*>(dyB_b), ldoB, n, B, P, C);
   return check_launch("bn_bwd_apply2");
+}
+
+// ------------------------------------------------------------------ optimizer step (run.py:446, 250)
+int gin_adam_chunk(void) { return gin::adam::CHUNK; }
+
+int gin_adam_step(const void* table_dev, const int32_t* chunk_first_dev, int count, int total_chunks, float lr, const float* lr_dev, float beta1,
+                  float beta2, float eps, float weight_decay, void* ticket_dev, void* stream) {
+  static_assert(sizeof(gin::adam::Tensor) == sizeof(GinAdamTensor), "GinAdamTensor layout");
+  if (count == 0) return GIN_OK;
+  if (!table_dev || !chunk_first_dev || !ticket_dev || count < 0 || total_chunks < count || !(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f) ||
+      !(eps >= 0.f) || !(weight_decay >= 0.f) || (!lr_dev && !(lr >= 0.f)))
+    return fail(GIN_ERR_ARG, "gin_adam_step: bad argument");
+  const gin::adam::Hyper h{lr, beta1, beta2, eps, weight_decay};
+  gin::adam::step_kernel<<<total_chunks, gin::adam::THREADS, 0, (cudaStream_t)stream>>>(reinterpret_cast<const gin::adam::Tensor*>(table_dev), chunk_first_dev, count, h,
+                                                                                          lr_dev, reinterpret_cast<unsigned int*>(ticket_dev));
+  return check_launch("adam_step");
 }
 
 static int up_hdr(const void* plan_host, const void* plan_dev, const GinUpPlanHdr** out);

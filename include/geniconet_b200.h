@@ -260,6 +260,27 @@ size_t gin_point_mesh_ws_bytes(int B, int N);
 int gin_point_mesh_distance(const float* points, const float* verts, const int32_t* faces, float* dist, int32_t* face_idx,
                             void* ws, int B, int N, int V, int F, void* stream);
 
+/* ------------------------------------------------------------------ device: optimizer step --- */
+/* The Adam step of the training loop (run.py:446 `torch.optim.Adam(model.parameters(), lr)`, run.py:250 `optimizer.step()`) over
+ * a LIST of fp32 tensors in one launch; same arithmetic as torch.optim.Adam (amsgrad = maximize = False, L2 weight_decay):
+ *   t = *step + 1;  g' = g + weight_decay*p;  m += (1-beta1)*(g'-m);  v = beta2*v + (1-beta2)*g'^2;
+ *   p -= lr/(1-beta1^t) * m / (sqrt(v)/sqrt(1-beta2^t) + eps);  *step = t  (written when every tensor has been updated).
+ * table_dev: GinAdamTensor[count] in device memory, all pointers device pointers.  chunk_first_dev: int32[count + 1], prefix sums
+ * of ceil(n / gin_adam_chunk()) over the table (chunk_first[count] = total_chunks).  lr_dev != NULL: the learning rate is read
+ * from the device at run time (a captured graph then follows a scheduler), else `lr`.  ticket_dev: one zero-initialised uint32
+ * owned by the caller (left zero again by every call). */
+typedef struct {
+  float* p;          /* parameter, updated in place */
+  const float* g;    /* gradient */
+  float* m;          /* exp_avg */
+  float* v;          /* exp_avg_sq */
+  float* step;       /* fp32 scalar: number of steps taken so far */
+  int64_t n;         /* elements */
+} GinAdamTensor;
+int gin_adam_chunk(void);
+int gin_adam_step(const void* table_dev, const int32_t* chunk_first_dev, int count, int total_chunks, float lr, const float* lr_dev, float beta1,
+                  float beta2, float eps, float weight_decay, void* ticket_dev, void* stream);
+
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
 int64_t gin_launch_count(void);
 

@@ -46,7 +46,12 @@ f = (params['ico']['factor_pos'], params['ico']['factor_nor'], params['ico']['fa
 crit = losses.P2PKLD_Loss(args.level, *f, 1.0) if args.model == 'ico2ico_vae' else losses.P2P_Loss(args.level, *f)
 from geniconet_b200 import fused as _fused                                   # noqa: E402
 buckets = GradBuckets(model.parameters(), world, adjacent=_fused.weight_pairs(model))
-opts = [torch.optim.Adam(ps, lr=1e-4, fused=True, capturable=True) for ps in (buckets.bucket_params() if world > 1 else [list(model.parameters())])]
+if os.environ.get('GIN_BENCH_OPTIMIZER', 'torch') == 'gin':
+    from geniconet_b200.optim import Adam as _Adam                           # noqa: E402
+    make_opt = lambda ps: _Adam(ps, lr=1e-4)                                 # noqa: E731
+else:
+    make_opt = lambda ps: torch.optim.Adam(ps, lr=1e-4, fused=True, capturable=True)      # noqa: E731
+opts = [make_opt(ps) for ps in (buckets.bucket_params() if world > 1 else [list(model.parameters())])]
 ids = shard_sample_ids(0, rank, world, min(B, 4))
 xs, ts = zip(*(data.synthetic_mesh(args.level, i) for i in ids))
 x = torch.stack(xs).repeat((B + 3) // 4, 1, 1, 1)[:B].cuda()
