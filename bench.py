@@ -33,7 +33,7 @@ def parse():
     ap.add_argument('--level', type=int, default=5)
     ap.add_argument('--batch', type=int, default=None, help='per-GPU batch (default 36 at I5, 16 at I6)')
     ap.add_argument('--conv-impl', default='auto', choices=['auto', 'simt', 'tc'])
-    ap.add_argument('--optimizer', default=os.environ.get('GIN_BENCH_OPTIMIZER', 'torch'), choices=['gin', 'torch'],
+    ap.add_argument('--optimizer', default=os.environ.get('GIN_BENCH_OPTIMIZER', 'gin'), choices=['gin', 'torch'],
                     help="gin: geniconet_b200.optim.Adam (one launch per step); torch: torch.optim.Adam(fused=True)")
     ap.add_argument('--no-graph', action='store_true', help='issue every launch from Python instead of replaying one CUDA graph per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -697,7 +697,8 @@ int gin_bn_act_bwd(const float* dout, int64_t ldg, const void* mask_b, const voi
   const gin::bn::Src sy{reinterpret_cast<const float*>(y), (long long)ld, y_fp16 ? 1 : 0};
   const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(mask_b);
   const int ctas = gin::bn::grid_for_rows(rows * (C >> 3));
-  gin::launch_pdl(gin::bn::bwd_reduce_kernel, dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sy, stat, rows, C, reinterpret_cast<float*>(ws));
+  gin::launch_pdl(!gin::bn::smem_consts(C) ? gin::bn::bwd_reduce_kernel : (y_fp16 ? gin::bn::bwd_reduce_s_kernel<true> : gin::bn::bwd_reduce_s_kernel<false>), dim3(ctas), dim3(256), 0, st,
+                  dout, ldg, mask, sy, stat, rows, C, reinterpret_cast<float*>(ws));
   int rc = check_launch("bn_bwd_reduce");
   if (rc) return rc;
   gin::launch_pdl(gin::bn::bwd_final_kernel, dim3(C / 8), dim3(256), 0, st, reinterpret_cast<const float*>(ws), ctas, rows, C, bstat);

@@ -559,12 +559,14 @@ bwd_apply2_anyc_kernel(const float* __restrict__ dout, long long ldg, const __nv
 // ------------------------------------------------------------------------------------------------ C <= 256: constants in shared memory
 // The streaming kernels above keep every per-channel constant of a thread's 8 channels in registers: 96 (bwd_apply), 98
 // (bwd_reduce2) and 162 (bwd_apply2) registers per thread, i.e. 2, 2 and ONE resident CTA per SM -- 8 to 16 warps cannot keep
-// enough loads in flight to fill HBM (ncu r02: 37-47 % of the copy bandwidth, profiles/r02_membound_*.txt).  The versions below
+// enough loads in flight to fill HBM (ncu r02: 37-47 % of the copy bandwidth, profiles/r02_step_dram_traffic.txt).  The versions below
 // hold the constants in shared memory (pre-combined once per CTA), re-read them every iteration through `ld.shared` that the
-// compiler may not hoist (asm volatile), replace the 64-bit divisions by shifts (C/8 is a power of two) and fit 4+ CTAs per SM.
+// compiler may not hoist (asm volatile), replace the 64-bit divisions by shifts (C/8 is a power of two) and fit 4 CTAs per SM.
+// Measured inside the replayed ico2ico step (profiles/r02_trace_n1.log): bwd_apply2 278 -> 171 us, bwd_apply 240 -> 162,
+// bwd_reduce2 203 -> 124, act_fwd 266 -> 201; the step 3.80 -> 3.46 ms.
 constexpr int CST_MAX_C = 256;
 #ifndef GIN_BN_SMEM_DEFAULT
-#define GIN_BN_SMEM_DEFAULT 0
+#define GIN_BN_SMEM_DEFAULT 1
 #endif
 GIN_DEVINL void cst_put(float (*t)[2][32][4], int k, int ch, float v) { t[k][(ch >> 2) & 1][ch >> 3][ch & 3] = v; }
 template <int K>
@@ -721,6 +723,37 @@ bwd_apply_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloa
     }
     if (dy_b) st8_bf16(dy_b + row * ldo + c, o);
   }
+}
+
+// partial[blk][2][C] = sum g | sum g*yhat (the single-BatchNorm form of bwd_reduce2_kernel below)
+template <bool F16>
+__global__ void __launch_bounds__(256, 4)
+bwd_reduce_s_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, Src y, const float* __restrict__ stat,
+                    long long rows, int C, float* __restrict__ partial) {
+  GIN_PDL_SYNC();
+  __shared__ __align__(16) float cst[1][2][32][4];
+  for (int ch = threadIdx.x; ch < C; ch += 256) cst_put(cst, 0, ch, stat[ch]);
+  __syncthreads();
+  const int C8 = C >> 3, sh = log2_pow2(C8), c8 = threadIdx.x & (C8 - 1), c = c8 * 8;
+  const uint32_t cb = (uint32_t)__cvta_generic_to_shared(&cst[0][0][c8][0]);
+  const long long n = rows << sh;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s0[k] = s1[k] = 0.f;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+    const long long r = i >> sh;
+    float g[8], v[8], m[8];
+    masked_grad(dout, ldg, mask, r, c, C, g);
+    ld8_y<F16>(y, r, c, v);
+    lds8<0>(cb, m);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s0[k] += g[k]; s1[k] = fmaf(g[k], v[k] - m[k], s1[k]); }
+  }
+  float inv[8];
+  ld8(stat + C + c, inv);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s1[k] *= inv[k];
+  block_partials(s0, s1, C, partial);
 }
 
 // partial[blk][4][C] = sum g | sum g*yhatA | sum g | sum g*yhatB; inside the loop only the means are needed:

@@ -256,8 +256,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_patch_kernel(const Params p
 struct TapMap { int8_t acc[8], half[8]; };
 
 // dW[co][ci][tap] = sum over the slices of a unit (fixed order: deterministic); one thread per output, co runs fastest so the
-// partial-sum reads are coalesced rows.  (Splitting the slice loop over several lanes measured slower: the kernel is bound by
-// the 20-40 MB of partials it streams from L2, not by latency.)
+// partial-sum reads are coalesced rows.  (Splitting the slice loop over several lanes measured slower, and so did eight loads in
+// flight per thread instead of two -- 146 vs 117 us per step: the kernel is bound by the 20-40 MB of partials it streams from
+// L2, not by latency.)
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int Cin, int Cout, int n_blk, int slices, int n_cblk, TapMap tm) {
   GIN_PDL_SYNC();
@@ -269,17 +270,14 @@ wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, i
     const int pr = tm.acc[tap], h = tm.half[tap];
     const int unit = (ci >> 6) + n_cblk * (co / n_blk);
     const float* src = partial + ((size_t)unit * slices * 4 + pr) * BM * n_blk + (size_t)(h * 64 + (ci & 63)) * n_blk + (co % n_blk);
-    // eight slices in flight per thread (two measured latency-bound: ~10 us for 25 MB that sit in L2); the adds keep slice order
-    const size_t ss = (size_t)4 * BM * n_blk;
-    float acc = 0.f;
-    for (int s = 0; s < slices; s += 8) {
-      float v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = s + j < slices ? __ldg(src + (size_t)(s + j) * ss) : 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc += v[j];
+    float a0 = 0.f, a1 = 0.f;
+    int s = 0;
+    for (; s + 1 < slices; s += 2) {
+      a0 += __ldg(src + (size_t)s * 4 * BM * n_blk);
+      a1 += __ldg(src + (size_t)(s + 1) * 4 * BM * n_blk);
     }
-    dW[((size_t)co * Cin + ci) * 7 + tap] = acc;
+    if (s < slices) a0 += __ldg(src + (size_t)s * 4 * BM * n_blk);
+    dW[((size_t)co * Cin + ci) * 7 + tap] = a0 + a1;
   }
 }
 

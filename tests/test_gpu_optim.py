@@ -1,6 +1,8 @@
 """geniconet_b200.optim.Adam (gin_adam_step: one launch for the whole parameter list) against torch.optim.Adam, the optimizer
-the reference trains with (run.py:446, 250).  Tolerance: fp32 round-off of one Adam update (rtol 1e-5 / atol 1e-8 on parameters
-that move by ~lr per step) -- both sides evaluate the same formula in fp32 with the bias corrections taken in fp64."""
+the reference trains with (run.py:446, 250).  Both sides evaluate the same formula in fp32 with the bias corrections taken in
+fp64, so they differ by a few ulp of the LARGEST term of each sum: rtol 1e-5 plus, for the moments, an absolute term of 2e-7
+times the gradient scale (squared for exp_avg_sq) -- exp_avg is a signed moving average and its small entries are differences
+of much larger ones (first GPU run: 3.6e-8 absolute on an entry of 1.5e-3 with gradients of order 1)."""
 import pytest
 import torch
 
@@ -19,13 +21,17 @@ def _params(seed, misaligned=True):
     return ps
 
 
+def _scale(i):
+    return 10.0 ** ((i % 5) - 3)
+
+
 def _grads(ps, seed):
     g = torch.Generator().manual_seed(1000 + seed)
-    return [torch.randn(p.shape, generator=g).cuda() * (10.0 ** ((i % 5) - 3)) for i, p in enumerate(ps)]
+    return [torch.randn(p.shape, generator=g).cuda() * _scale(i) for i, p in enumerate(ps)]
 
 
-def _close(a, b, what):
-    torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-8, msg=lambda m: '%s: %s' % (what, m))
+def _close(a, b, what, atol=1e-8):
+    torch.testing.assert_close(a, b, rtol=1e-5, atol=atol, msg=lambda m: '%s: %s' % (what, m))
 
 
 @pytest.mark.parametrize('weight_decay', [0.0, 0.01])
@@ -44,8 +50,8 @@ def test_matches_torch_adam(weight_decay):
     torch.cuda.synchronize()
     for i, (p, q) in enumerate(zip(ours, ref)):
         _close(p, q, 'parameter %d %s' % (i, tuple(p.shape)))
-        _close(o.state[p]['exp_avg'], r.state[q]['exp_avg'], 'exp_avg %d' % i)
-        _close(o.state[p]['exp_avg_sq'], r.state[q]['exp_avg_sq'], 'exp_avg_sq %d' % i)
+        _close(o.state[p]['exp_avg'], r.state[q]['exp_avg'], 'exp_avg %d' % i, atol=2e-7 * _scale(i))
+        _close(o.state[p]['exp_avg_sq'], r.state[q]['exp_avg_sq'], 'exp_avg_sq %d' % i, atol=2e-7 * _scale(i) ** 2)
         assert float(o.state[p]['step']) == 12.0 == float(r.state[q]['step'])
 
 

@@ -46,7 +46,7 @@ f = (params['ico']['factor_pos'], params['ico']['factor_nor'], params['ico']['fa
 crit = losses.P2PKLD_Loss(args.level, *f, 1.0) if args.model == 'ico2ico_vae' else losses.P2P_Loss(args.level, *f)
 from geniconet_b200 import fused as _fused                                   # noqa: E402
 buckets = GradBuckets(model.parameters(), world, adjacent=_fused.weight_pairs(model))
-if os.environ.get('GIN_BENCH_OPTIMIZER', 'torch') == 'gin':
+if os.environ.get('GIN_BENCH_OPTIMIZER', 'gin') == 'gin':
     from geniconet_b200.optim import Adam as _Adam                           # noqa: E402
     make_opt = lambda ps: _Adam(ps, lr=1e-4)                                 # noqa: E731
 else:
