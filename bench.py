@@ -357,7 +357,6 @@ def run_ours(args):
     xs, ts = zip(*(data.synthetic_mesh(args.level, i) for i in ids))
     x_host, t_host = torch.stack(xs).pin_memory(), torch.stack(ts).pin_memory()
     x_dev, t_dev = x_host.cuda(), t_host.cuda()
-    loss_host = torch.zeros(1).pin_memory()
 
     def step(x, t):
         buckets.reset()
@@ -376,12 +375,14 @@ def run_ours(args):
 
     per_rank_ms = []          # ms per step of every rank, one list per timed() call (the reported time is the maximum)
 
-    def timed(fn, steps):
+    def timed(fn, steps, finish=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
+        if finish is not None:
+            finish()                                      # host work that belongs to the timed steps (the last loss read-back)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
@@ -423,7 +424,10 @@ def run_ours(args):
 
     # End to end: every step copies ITS batch from pinned host memory and reads its loss back.  As a data loader would, the
     # host->device copy of the next batch runs on a copy stream into a staging buffer while the current step computes; the
-    # step then starts with a device-side copy from the staging buffer into the graph's static inputs.
+    # step then starts with a device-side copy from the staging buffer into the graph's static inputs.  The loss of step k goes
+    # to a pinned two-slot ring with a non-blocking copy and is read by the host once step k+1 has been enqueued (a training
+    # loop that logs its loss one step late), so the device never waits for the host; every loss, the last one included
+    # (read_last), is read inside the timed region.
     copy_stream = torch.cuda.Stream()
     x_stage, t_stage = torch.empty_like(x_dev), torch.empty_like(t_dev)
     staged, consumed = torch.cuda.Event(), torch.cuda.Event()
@@ -449,13 +453,35 @@ def run_ours(args):
             consumed.record(main)
             prefetch()
             loss = step(xd, td)
-        loss_host.copy_(loss.detach().reshape(1), non_blocking=False)
+        k = ring['k']
+        loss_ring[k & 1:(k & 1) + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        ring['event'][k & 1] = torch.cuda.Event()
+        ring['event'][k & 1].record()
+        ring['k'] = k + 1
+        read_loss((k - 1) & 1)
+
+    loss_ring = torch.zeros(2).pin_memory()
+    ring = {'k': 0, 'event': [None, None], 'losses': []}
+
+    def read_loss(slot):
+        ev = ring['event'][slot]
+        if ev is not None:
+            ev.synchronize()
+            ring['losses'].append(float(loss_ring[slot]))
+            ring['event'][slot] = None
+
+    def read_last():
+        read_loss((ring['k'] - 1) & 1)
 
     consumed.record(torch.cuda.current_stream())
     prefetch()
     for _ in range(2):
         e2e_step()
-    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    read_last()
+    ring['losses'] = []
+    ms_e2e = timed(e2e_step, args.steps, finish=read_last) / args.steps
+    if len(ring['losses']) != args.steps:
+        raise SystemExit('bench.py: %d losses read back in %d end-to-end steps' % (len(ring['losses']), args.steps))
     clk = clocks.stop() if rank == 0 else None
     final_loss = float(last.detach())
 
@@ -489,7 +515,8 @@ def run_ours(args):
                             'optimizer': 'geniconet_b200.optim.Adam (gin_adam_step, one launch)' if args.optimizer == 'gin' else 'torch.optim.Adam(fused=True)',
                             'launch': 'one CUDA graph replay per step' if use_graph else 'eager (one launch per kernel)'},
                 'e2e': {'value': meshes / (ms_e2e * 1e-3), 'unit': 'meshes/s', 'ms_per_step': ms_e2e,
-                        'h2d_bytes_per_step': x_host.numel() * 4 + t_host.numel() * 4, 'd2h_bytes_per_step': 4},
+                        'h2d_bytes_per_step': x_host.numel() * 4 + t_host.numel() * 4, 'd2h_bytes_per_step': 4,
+                        'loss_readback': 'every step, read by the host one step late (pinned ring); %d of %d read inside the timed region' % (len(ring['losses']), args.steps)},
                 'gpu_launches': int(launches), 'clocks': clk, 'loss': final_loss,
                 'ms_per_step_per_rank': per_rank_ms[0] if per_rank_ms else None,
                 'tflops_algorithmic': FLOP_PER_MESH.get((args.model, args.level), 0) * meshes / (ms_step * 1e-3) / 1e12,

@@ -30,15 +30,21 @@ for r in rows[hi + 1:]:
         continue
     d = per.setdefault(r[idc], {'name': re.sub(r'^void ', '', re.sub(r'\(.*', '', r[kn]))[:90]})
     d[r[mn]] = v
+# whole steps only: keep the launches after the first p2p_final_kernel (the end of a loss forward) up to and including the last one
+marks = [i for i, d in enumerate(per.values()) if 'p2p_final_kernel' in d['name']]
+launches = list(per.values())
+if steps <= 0 and len(marks) >= 2:
+    launches = launches[marks[0] + 1:marks[-1] + 1]
+    steps = float(len(marks) - 1)
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
-for d in per.values():
+for d in launches:
     a = agg[d['name']]
     a[0] += 1
     a[1] += d.get('gpu__time_duration.sum', 0.0)
     a[2] += d.get('dram__bytes_read.sum', 0.0)
     a[3] += d.get('dram__bytes_write.sum', 0.0)
-if steps <= 0:          # one p2p_final_kernel per loss forward = per training step
-    steps = float(max(1, sum(a[0] for k, a in agg.items() if 'p2p_final_kernel' in k)))
+if steps <= 0:
+    steps = 1.0
 peak = 6546.2
 try:
     peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')))['hbm_gbs']
@@ -46,7 +52,7 @@ except Exception:
     pass
 tt = sum(a[1] for a in agg.values())
 print('# %d launches (%g step[s]); device time %.1f us/step; DRAM read %.1f MB + write %.1f MB per step; HBM peak %.0f GB/s (MEASURED_PEAKS.json)' % (
-    len(per), steps, tt * 1e6 / steps, sum(a[2] for a in agg.values()) / 1e6 / steps, sum(a[3] for a in agg.values()) / 1e6 / steps, peak))
+    len(launches), steps, tt * 1e6 / steps, sum(a[2] for a in agg.values()) / 1e6 / steps, sum(a[3] for a in agg.values()) / 1e6 / steps, peak))
 print('# %-78s %6s %10s %6s %9s %9s %8s %6s' % ('kernel', 'n/step', 'us/step', 'share', 'rd MB', 'wr MB', 'GB/s', 'of pk'))
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     gbs = (a[2] + a[3]) / a[1] / 1e9 if a[1] else 0.0
