@@ -50,8 +50,9 @@ def test_matches_torch_adam(weight_decay):
     torch.cuda.synchronize()
     for i, (p, q) in enumerate(zip(ours, ref)):
         _close(p, q, 'parameter %d %s' % (i, tuple(p.shape)))
-        _close(o.state[p]['exp_avg'], r.state[q]['exp_avg'], 'exp_avg %d' % i, atol=2e-7 * _scale(i))
-        _close(o.state[p]['exp_avg_sq'], r.state[q]['exp_avg_sq'], 'exp_avg_sq %d' % i, atol=2e-7 * _scale(i) ** 2)
+        eff = _scale(i) + weight_decay * float(q.detach().abs().max())      # size of g + weight_decay * p
+        _close(o.state[p]['exp_avg'], r.state[q]['exp_avg'], 'exp_avg %d' % i, atol=2e-7 * eff)
+        _close(o.state[p]['exp_avg_sq'], r.state[q]['exp_avg_sq'], 'exp_avg_sq %d' % i, atol=2e-7 * eff ** 2)
         assert float(o.state[p]['step']) == 12.0 == float(r.state[q]['step'])
 
 
