@@ -3,6 +3,8 @@ the reference trains with (run.py:446, 250).  Both sides evaluate the same formu
 fp64, so they differ by a few ulp of the LARGEST term of each sum: rtol 1e-5 plus, for the moments, an absolute term of 2e-7
 times the gradient scale (squared for exp_avg_sq) -- exp_avg is a signed moving average and its small entries are differences
 of much larger ones (first GPU run: 3.6e-8 absolute on an entry of 1.5e-3 with gradients of order 1)."""
+import copy
+
 import pytest
 import torch
 
@@ -84,12 +86,14 @@ def test_state_dict_is_interchangeable_with_torch():
     with torch.no_grad():
         for p, q in zip(ours, ref):
             q.copy_(p)
-    r.load_state_dict(o.state_dict())
+    # deepcopy: Optimizer.load_state_dict keeps tensors that already have the right dtype and device BY REFERENCE (a checkpoint
+    # that went through torch.save / torch.load is a copy anyway); two optimizers sharing exp_avg would both update it
+    r.load_state_dict(copy.deepcopy(o.state_dict()))
     o2 = Adam(_params(2), lr=3e-4)
     with torch.no_grad():
         for p, q in zip(ours, o2.param_groups[0]['params']):
             q.copy_(p)
-    o2.load_state_dict(r.state_dict())                       # and back again
+    o2.load_state_dict(copy.deepcopy(r.state_dict()))        # and back again
     third = o2.param_groups[0]['params']
     for step in range(3, 6):
         gs = _grads(ours, step)
