@@ -12,10 +12,11 @@ written down BEFORE measuring: loss and per-term losses 2e-2 relative, output 5e
 (committed as profiles/r02_parity_full_configs.json).
 
 What was measured against that bar (B200, r02, fp16 forward operands + bf16 gradient operands): ico2ico meets it everywhere
-(min cosine 0.9994 at random init, 0.9999 conditioned, 0.9997 at I6).  ico2ico_vae under the reference's 0.6/0.2/0.2 loss meets it
-on average (mean 0.997 conditioned) but NOT for every parameter: the reconstruction gradient entering the decoder is
+(min cosine 0.9988-0.9994 at random init, 0.9999 conditioned, 0.9997 at I6, depending on the build).  ico2ico_vae under the reference's 0.6/0.2/0.2 loss meets it
+on average (mean 0.9975 conditioned) but NOT for every parameter: the reconstruction gradient entering the decoder is
 high-frequency (normals, Laplacian), the adjoint upsampling attenuates it level by level while every dgrad re-injects bf16
-rounding at full scale, so the cosine decays from 0.9999 (head) to 0.988 at decoder.0; the encoder, whose gradient is dominated
+rounding at full scale, so the cosine decays from 0.9999 (head) to 0.985-0.988 at decoder.0 (the conditioned state is produced by
+this path's own 100 Adam steps, so the figure moves with every numerical change of the path: 0.985 / 0.988 / 0.997 over r02's builds); the encoder, whose gradient is dominated
 by the exactly computed KL term, is back at 0.998.  That is a KNOWN LIMIT of bf16 gradient operands, not a tolerance: the VAE
 test below asserts mean >= 0.99 and records the per-parameter minimum, which must not fall below VAE_DEEP_MIN = 0.98.  The
 200-step loss curves of this path and of the exact-fp32 path coincide (profiles/r02_precision_study.md).
