@@ -688,7 +688,7 @@ int gin_bn_act_fwd(const void* y1, int64_t ld1, const float* stat1, const void* 
 }
 
 int gin_bn_act_bwd(const float* dout, int64_t ldg, const void* mask_b, const void* y, int64_t ld, int y_fp16, const float* stat, float* bstat, void* dy_b,
-                   int64_t ldo, float* dy_f, int64_t ldf, void* ws, int B, int level, int C, void* stream) {
+                   int64_t ldo, float* dy_f, int64_t ldf, void* ws, int B, int level, int C, int relu_from_y, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (!dout || !y || !stat || !bstat || !ws || (!dy_b && !dy_f) || B <= 0 || level < 0 || level > 9 || !bn_shape_ok(C))
     return fail(GIN_ERR_ARG, "gin_bn_act_bwd: bad argument");
@@ -697,13 +697,18 @@ int gin_bn_act_bwd(const float* dout, int64_t ldg, const void* mask_b, const voi
   const gin::bn::Src sy{reinterpret_cast<const float*>(y), (long long)ld, y_fp16 ? 1 : 0};
   const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(mask_b);
   const int ctas = gin::bn::grid_for_rows(rows * (C >> 3));
-  gin::launch_pdl(!gin::bn::smem_consts(C) ? gin::bn::bwd_reduce_kernel : (y_fp16 ? gin::bn::bwd_reduce_s_kernel<true> : gin::bn::bwd_reduce_s_kernel<false>), dim3(ctas), dim3(256), 0, st,
-                  dout, ldg, mask, sy, stat, rows, C, reinterpret_cast<float*>(ws));
+  const bool smem = gin::bn::smem_consts(C);
+  const int from_y = (relu_from_y && mask && smem) ? 1 : 0;      // the register-constant kernels always read the mask
+  float* part = reinterpret_cast<float*>(ws);
+  if (!smem) gin::launch_pdl(gin::bn::bwd_reduce_kernel, dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sy, stat, rows, C, part);
+  else gin::launch_pdl(y_fp16 ? gin::bn::bwd_reduce_s_kernel<true> : gin::bn::bwd_reduce_s_kernel<false>, dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sy, stat, rows, C, part, from_y);
   int rc = check_launch("bn_bwd_reduce");
   if (rc) return rc;
   gin::launch_pdl(gin::bn::bwd_final_kernel, dim3(C / 8), dim3(256), 0, st, reinterpret_cast<const float*>(ws), ctas, rows, C, bstat);
   if ((rc = check_launch("bn_bwd_final"))) return rc;
-  gin::launch_pdl(!gin::bn::smem_consts(C) ? gin::bn::bwd_apply_anyc_kernel : (y_fp16 ? gin::bn::bwd_apply_kernel<true> : gin::bn::bwd_apply_kernel<false>), dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sy, stat, bstat, reinterpret_cast<__nv_bfloat16*>(dy_b), ldo, dy_f, ldf, n, B, P, C);
+  __nv_bfloat16* dyb = reinterpret_cast<__nv_bfloat16*>(dy_b);
+  if (!smem) gin::launch_pdl(gin::bn::bwd_apply_anyc_kernel, dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sy, stat, bstat, dyb, ldo, dy_f, ldf, n, B, P, C);
+  else gin::launch_pdl(y_fp16 ? gin::bn::bwd_apply_kernel<true> : gin::bn::bwd_apply_kernel<false>, dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sy, stat, bstat, dyb, ldo, dy_f, ldf, n, B, P, C, from_y);
   return check_launch("bn_bwd_apply");
 }
 
@@ -711,7 +716,7 @@ size_t gin_bn_pair_ws_bytes(int C) { return C <= 0 ? 0 : (size_t)gin::bn::MAX_CT
 
 int gin_bn_act_bwd_pair(const float* dout, int64_t ldg, const void* mask_b, const void* yA, int64_t ldA, const float* statA, float* bstatA,
                         void* dyA_b, int64_t ldoA, const void* yB, int64_t ldB, const float* statB, float* bstatB, void* dyB_b, int64_t ldoB,
-                        int y_fp16, void* ws, int B, int level, int C, void* stream) {
+                        int y_fp16, void* ws, int B, int level, int C, int relu_from_y, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (!dout || !yA || !yB || !statA || !statB || !bstatA || !bstatB || !dyA_b || !dyB_b || !ws || B <= 0 || level < 0 || level > 9 || !bn_shape_ok(C))
     return fail(GIN_ERR_ARG, "gin_bn_act_bwd_pair: bad argument");
@@ -720,13 +725,18 @@ int gin_bn_act_bwd_pair(const float* dout, int64_t ldg, const void* mask_b, cons
   const gin::bn::Src sA{reinterpret_cast<const float*>(yA), (long long)ldA, y_fp16 ? 1 : 0}, sB{reinterpret_cast<const float*>(yB), (long long)ldB, y_fp16 ? 1 : 0};
   const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(mask_b);
   const int ctas = gin::bn::grid_for_rows(rows * (C >> 3));
-  gin::launch_pdl(!gin::bn::smem_consts(C) ? gin::bn::bwd_reduce2_anyc_kernel : (y_fp16 ? gin::bn::bwd_reduce2_kernel<true> : gin::bn::bwd_reduce2_kernel<false>), dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sA, statA, sB, statB, rows, C, reinterpret_cast<float*>(ws));
+  const bool smem = gin::bn::smem_consts(C);
+  const int from_y = (relu_from_y && mask && smem) ? 1 : 0;
+  float* part = reinterpret_cast<float*>(ws);
+  if (!smem) gin::launch_pdl(gin::bn::bwd_reduce2_anyc_kernel, dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sA, statA, sB, statB, rows, C, part);
+  else gin::launch_pdl(y_fp16 ? gin::bn::bwd_reduce2_kernel<true> : gin::bn::bwd_reduce2_kernel<false>, dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sA, statA, sB, statB, rows, C, part, from_y);
   int rc = check_launch("bn_bwd_reduce2");
   if (rc) return rc;
   gin::launch_pdl(gin::bn::bwd_final2_kernel, dim3(C / 8), dim3(256), 0, st, reinterpret_cast<const float*>(ws), ctas, rows, C, bstatA, bstatB);
   if ((rc = check_launch("bn_bwd_final2"))) return rc;
-  gin::launch_pdl(!gin::bn::smem_consts(C) ? gin::bn::bwd_apply2_anyc_kernel : (y_fp16 ? gin::bn::bwd_apply2_kernel<true> : gin::bn::bwd_apply2_kernel<false>), dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sA, statA, bstatA, sB, statB, bstatB, reinterpret_cast<__nv_bfloat16*>(dyA_b), ldoA,
-                                                   reinterpret_cast<__nv_bfloat16*>(dyB_b), ldoB, n, B, P, C);
+  __nv_bfloat16 *da = reinterpret_cast<__nv_bfloat16*>(dyA_b), *db = reinterpret_cast<__nv_bfloat16*>(dyB_b);
+  if (!smem) gin::launch_pdl(gin::bn::bwd_apply2_anyc_kernel, dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sA, statA, bstatA, sB, statB, bstatB, da, ldoA, db, ldoB, n, B, P, C);
+  else gin::launch_pdl(y_fp16 ? gin::bn::bwd_apply2_kernel<true> : gin::bn::bwd_apply2_kernel<false>, dim3(ctas), dim3(256), 0, st, dout, ldg, mask, sA, statA, bstatA, sB, statB, bstatB, da, ldoA, db, ldoB, n, B, P, C, from_y);
   return check_launch("bn_bwd_apply2");
 }
 

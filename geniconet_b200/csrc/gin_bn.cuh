@@ -595,18 +595,19 @@ GIN_DEVINL void apply_row_s(const Src& y1, const Src& y2, long long r, int c, ui
   if (TWO) {
     float w[8];
     ld8_y<F16>(y2, r, c, w);
+    // explicit intrinsics (never contracted): the backward kernels re-evaluate exactly this expression for the ReLU mask
     lds8<2>(cb, k);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = w[j] * k[j];
+    for (int j = 0; j < 8; ++j) o[j] = __fmul_rn(w[j], k[j]);
     lds8<1>(cb, k);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] += k[j];
+    for (int j = 0; j < 8; ++j) o[j] = __fadd_rn(o[j], k[j]);
   } else {
     lds8<1>(cb, o);
   }
   lds8<0>(cb, k);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) o[j] = fmaf(v[j], k[j], o[j]);
+  for (int j = 0; j < 8; ++j) o[j] = __fmaf_rn(v[j], k[j], o[j]);
   if (relu) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
@@ -650,15 +651,40 @@ act_fwd_kernel(Src y1, const float* __restrict__ stat1, Src y2, const float* __r
   }
 }
 
-// g = dout * (out > 0)
-GIN_DEVINL void masked_grad(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, long long r, int c, int C, float g[8]) {
+// g = dout * (out > 0).  The mask is either READ from an activation copy (mask != null, from_y == 0) or RE-EVALUATED from the
+// BatchNorm input(s) and constants exactly as act_fwd_kernel computed out (from_y != 0: saves the 2 B / element of the mask read;
+// relu_from_y<> below, called once the y values are in registers); mask == null and from_y == 0: no ReLU.
+GIN_DEVINL void masked_grad(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, int from_y, long long r, int c, int C, float g[8]) {
   ld8(dout + r * ldg + c, g);
-  if (mask) {
+  if (mask && !from_y) {
     bool m[8];
     ld8_mask(mask + r * C + c, m);
 #pragma unroll
     for (int k = 0; k < 8; ++k) g[k] = m[k] ? g[k] : 0.f;
   }
+}
+// out = relu(y*scale + shift): constants KSC = scale, KSH = shift
+template <int KSC, int KSH>
+GIN_DEVINL void relu_from_y(uint32_t cb, const float y[8], float g[8]) {
+  float k[8], t[8];
+  lds8<KSH>(cb, t);
+  lds8<KSC>(cb, k);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = __fmaf_rn(y[j], k[j], t[j]) > 0.f ? g[j] : 0.f;
+}
+// out = relu(yA*scaleA + (yB*scaleB + (shiftA + shiftB))): constants KA = scaleA, KB = scaleB, KSH = shiftA + shiftB
+template <int KA, int KB, int KSH>
+GIN_DEVINL void relu_from_y2(uint32_t cb, const float yA[8], const float yB[8], float g[8]) {
+  float k[8], t[8];
+  lds8<KB>(cb, k);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) t[j] = __fmul_rn(yB[j], k[j]);
+  lds8<KSH>(cb, k);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) t[j] = __fadd_rn(t[j], k[j]);
+  lds8<KA>(cb, k);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = __fmaf_rn(yA[j], k[j], t[j]) > 0.f ? g[j] : 0.f;
 }
 // dy = a*g - b - (y - mean)*e  with  a = scale, b = scale*c1, e = scale*invstd*c2  (constants K0 .. K0+3: a, b, mean, e)
 template <int K0>
@@ -691,10 +717,11 @@ template <bool F16>
 __global__ void __launch_bounds__(256, 4)
 bwd_apply_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, Src y, const float* __restrict__ stat,
                  const float* __restrict__ bstat, __nv_bfloat16* __restrict__ dy_b, long long ldo, float* __restrict__ dy_f, long long ldf,
-                 int nlat, int B, int P, int C) {
+                 int nlat, int B, int P, int C, int from_y) {
   GIN_PDL_SYNC();
-  __shared__ __align__(16) float cst[4][2][32][4];
+  __shared__ __align__(16) float cst[5][2][32][4];
   bn_dy_consts(cst, 0, stat, bstat, C);
+  for (int ch = threadIdx.x; ch < C; ch += 256) cst_put(cst, 4, ch, stat[3 * C + ch]);
   __syncthreads();
   const int C8 = C >> 3, sh = log2_pow2(C8), c8 = threadIdx.x & (C8 - 1), c = c8 * 8;
   const uint32_t cb = (uint32_t)__cvta_generic_to_shared(&cst[0][0][c8][0]);
@@ -703,8 +730,9 @@ bwd_apply_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloa
     const long long row = i >> sh;
     float o[8], g[8];
     if (i < n_main) {
-      masked_grad(dout, ldg, mask, row, c, C, g);
+      masked_grad(dout, ldg, mask, from_y, row, c, C, g);
       ld8_y<F16>(y, row, c, o);
+      if (from_y) relu_from_y<0, 4>(cb, o, g);
       bn_dy<0>(cb, g, o);
       if (dy_f) st8(dy_f + row * ldf + c, o);
     } else {
@@ -714,8 +742,9 @@ bwd_apply_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloa
       for (int e = 0; e < 5; ++e) {
         const long long r = (long long)sample * P + ring_pixel(nlat, pole, e);
         float t[8];
-        masked_grad(dout, ldg, mask, r, c, C, g);
+        masked_grad(dout, ldg, mask, from_y, r, c, C, g);
         ld8_y<F16>(y, r, c, t);
+        if (from_y) relu_from_y<0, 4>(cb, t, g);
         bn_dy<0>(cb, g, t);
 #pragma unroll
         for (int k = 0; k < 8; ++k) o[k] = fmaf(0.2f, t[k], o[k]);
@@ -729,10 +758,10 @@ bwd_apply_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloa
 template <bool F16>
 __global__ void __launch_bounds__(256, 4)
 bwd_reduce_s_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, Src y, const float* __restrict__ stat,
-                    long long rows, int C, float* __restrict__ partial) {
+                    long long rows, int C, float* __restrict__ partial, int from_y) {
   GIN_PDL_SYNC();
-  __shared__ __align__(16) float cst[1][2][32][4];
-  for (int ch = threadIdx.x; ch < C; ch += 256) cst_put(cst, 0, ch, stat[ch]);
+  __shared__ __align__(16) float cst[3][2][32][4];
+  for (int ch = threadIdx.x; ch < C; ch += 256) { cst_put(cst, 0, ch, stat[ch]); cst_put(cst, 1, ch, stat[2 * C + ch]); cst_put(cst, 2, ch, stat[3 * C + ch]); }
   __syncthreads();
   const int C8 = C >> 3, sh = log2_pow2(C8), c8 = threadIdx.x & (C8 - 1), c = c8 * 8;
   const uint32_t cb = (uint32_t)__cvta_generic_to_shared(&cst[0][0][c8][0]);
@@ -743,8 +772,9 @@ bwd_reduce_s_kernel(const float* __restrict__ dout, long long ldg, const __nv_bf
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
     const long long r = i >> sh;
     float g[8], v[8], m[8];
-    masked_grad(dout, ldg, mask, r, c, C, g);
+    masked_grad(dout, ldg, mask, from_y, r, c, C, g);
     ld8_y<F16>(y, r, c, v);
+    if (from_y) relu_from_y<1, 2>(cb, v, g);
     lds8<0>(cb, m);
 #pragma unroll
     for (int k = 0; k < 8; ++k) { s0[k] += g[k]; s1[k] = fmaf(g[k], v[k] - m[k], s1[k]); }
@@ -761,11 +791,14 @@ bwd_reduce_s_kernel(const float* __restrict__ dout, long long ldg, const __nv_bf
 template <bool F16>
 __global__ void __launch_bounds__(256, 4)
 bwd_reduce2_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, Src yA, const float* __restrict__ statA,
-                   Src yB, const float* __restrict__ statB, long long rows, int C, float* __restrict__ partial) {
+                   Src yB, const float* __restrict__ statB, long long rows, int C, float* __restrict__ partial, int from_y) {
   GIN_PDL_SYNC();
   __shared__ float part[3][256][9];
-  __shared__ __align__(16) float cst[2][2][32][4];
-  for (int ch = threadIdx.x; ch < C; ch += 256) { cst_put(cst, 0, ch, statA[ch]); cst_put(cst, 1, ch, statB[ch]); }
+  __shared__ __align__(16) float cst[5][2][32][4];
+  for (int ch = threadIdx.x; ch < C; ch += 256) {
+    cst_put(cst, 0, ch, statA[ch]); cst_put(cst, 1, ch, statB[ch]);
+    cst_put(cst, 2, ch, statA[2 * C + ch]); cst_put(cst, 3, ch, statB[2 * C + ch]); cst_put(cst, 4, ch, statA[3 * C + ch] + statB[3 * C + ch]);
+  }
   __syncthreads();
   const int C8 = C >> 3, sh = log2_pow2(C8), c8 = threadIdx.x & (C8 - 1), c = c8 * 8;
   const uint32_t cb = (uint32_t)__cvta_generic_to_shared(&cst[0][0][c8][0]);
@@ -776,9 +809,10 @@ bwd_reduce2_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfl
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
     const long long r = i >> sh;
     float g[8], v[8], w[8], m[8];
-    masked_grad(dout, ldg, mask, r, c, C, g);
+    masked_grad(dout, ldg, mask, from_y, r, c, C, g);
     ld8_y<F16>(yA, r, c, v);
     ld8_y<F16>(yB, r, c, w);
+    if (from_y) relu_from_y2<2, 3, 4>(cb, v, w, g);
     lds8<0>(cb, m);
 #pragma unroll
     for (int k = 0; k < 8; ++k) { s0[k] += g[k]; s1[k] = fmaf(g[k], v[k] - m[k], s1[k]); }
@@ -807,11 +841,13 @@ template <bool F16>
 __global__ void __launch_bounds__(256, 4)
 bwd_apply2_kernel(const float* __restrict__ dout, long long ldg, const __nv_bfloat16* __restrict__ mask, Src yA, const float* __restrict__ statA,
                   const float* __restrict__ bstatA, Src yB, const float* __restrict__ statB, const float* __restrict__ bstatB,
-                  __nv_bfloat16* __restrict__ dyA, long long ldoA, __nv_bfloat16* __restrict__ dyB, long long ldoB, int nlat, int B, int P, int C) {
+                  __nv_bfloat16* __restrict__ dyA, long long ldoA, __nv_bfloat16* __restrict__ dyB, long long ldoB, int nlat, int B, int P, int C,
+                  int from_y) {
   GIN_PDL_SYNC();
-  __shared__ __align__(16) float cst[8][2][32][4];
+  __shared__ __align__(16) float cst[9][2][32][4];
   bn_dy_consts(cst, 0, statA, bstatA, C);
   bn_dy_consts(cst, 4, statB, bstatB, C);
+  for (int ch = threadIdx.x; ch < C; ch += 256) cst_put(cst, 8, ch, statA[3 * C + ch] + statB[3 * C + ch]);
   __syncthreads();
   const int C8 = C >> 3, sh = log2_pow2(C8), c8 = threadIdx.x & (C8 - 1), c = c8 * 8;
   const uint32_t cb = (uint32_t)__cvta_generic_to_shared(&cst[0][0][c8][0]);
@@ -820,9 +856,10 @@ bwd_apply2_kernel(const float* __restrict__ dout, long long ldg, const __nv_bflo
     const long long row = i >> sh;
     float g[8], o[8], oB[8];
     if (i < n_main) {
-      masked_grad(dout, ldg, mask, row, c, C, g);
+      masked_grad(dout, ldg, mask, from_y, row, c, C, g);
       ld8_y<F16>(yA, row, c, o);
       ld8_y<F16>(yB, row, c, oB);
+      if (from_y) relu_from_y2<0, 4, 8>(cb, o, oB, g);
       bn_dy<0>(cb, g, o);
       bn_dy<4>(cb, g, oB);
       st8_bf16(dyA + row * ldoA + c, o);
@@ -835,7 +872,13 @@ bwd_apply2_kernel(const float* __restrict__ dout, long long ldg, const __nv_bflo
       for (int e = 0; e < 10; ++e) {
         const long long r = (long long)sample * P + ring_pixel(nlat, pole, e % 5);
         float t[8];
-        masked_grad(dout, ldg, mask, r, c, C, g);
+        masked_grad(dout, ldg, mask, from_y, r, c, C, g);
+        if (from_y) {
+          float u[8];
+          ld8_y<F16>(yA, r, c, t);
+          ld8_y<F16>(yB, r, c, u);
+          relu_from_y2<0, 4, 8>(cb, t, u, g);
+        }
         if (e < 5) {
           ld8_y<F16>(yA, r, c, t);
           bn_dy<0>(cb, g, t);

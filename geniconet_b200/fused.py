@@ -252,15 +252,22 @@ def _bn_act(y1, col1, ld1, stat1, y2, col2, ld2, stat2, B, level, C, want_b=True
     return out_b, out_f, out_w
 
 
-def _bn_bwd(dout, mask_b, y, col0, ld, stat, B, level, C, dy_b=None, dy_b_col=0, ldo=0, want_f=False):
-    """Returns (bstat [4C]: dbeta, dgamma, ..., dy_f or None); writes the bf16 gradient copy into dy_b[:, dy_b_col:dy_b_col+C]."""
+# GIN_BN_MASK_FROM_Y=1: the BatchNorm backward kernels re-evaluate the ReLU mask from y and the BatchNorm constants instead of
+# reading it from the activation copy (include/geniconet_b200.h: relu_from_y)
+_MASK_FROM_Y = 1 if _os.environ.get('GIN_BN_MASK_FROM_Y', '0') == '1' else 0
+
+
+def _bn_bwd(dout, mask_b, y, col0, ld, stat, B, level, C, dy_b=None, dy_b_col=0, ldo=0, want_f=False, mask_from_y=None):
+    """Returns (bstat [4C]: dbeta, dgamma, ..., dy_f or None); writes the bf16 gradient copy into dy_b[:, dy_b_col:dy_b_col+C].
+    mask_b must be the activation copy _bn_act produced from (y, stat) with ReLU (it may then be re-evaluated instead of read)."""
     dev = dout.device
     bstat = _empty(4 * C, torch.float32, dev)
     ws = _empty(L.gin_bn_ws_bytes(C), torch.uint8, dev)
     dy_f = _empty((B * _P(level), C), torch.float32, dev) if want_f else None
     _lib.check(L.gin_bn_act_bwd(dout.data_ptr(), C, mask_b.data_ptr() if mask_b is not None else None, y.data_ptr() + y.element_size() * col0, ld,
                                 1 if y.dtype == torch.float16 else 0, stat.data_ptr(), bstat.data_ptr(), (dy_b.data_ptr() + 2 * dy_b_col) if dy_b is not None else None, ldo,
-                                dy_f.data_ptr() if want_f else None, C, ws.data_ptr(), B, level, C, _stream()), 'gin_bn_act_bwd')
+                                dy_f.data_ptr() if want_f else None, C, ws.data_ptr(), B, level, C,
+                                _MASK_FROM_Y if mask_from_y is None else int(mask_from_y), _stream()), 'gin_bn_act_bwd')
     return bstat, dy_f
 
 
@@ -402,7 +409,7 @@ class _Chain(torch.autograd.Function):
                 _lib.check(L.gin_bn_act_bwd_pair(d.data_ptr(), cout, st['out_b'].data_ptr(), st['y01'].data_ptr(), cout, st['stat01'].data_ptr(),
                                                  bs01.data_ptr(), dy01_b.data_ptr(), cout, st['ycat'].data_ptr() + st['ycat'].element_size() * cout, 2 * cout,
                                                  st['stat10'].data_ptr(), bs10.data_ptr(), dycat_b.data_ptr() + 2 * cout, 2 * cout,
-                                                 1 if st['ycat'].dtype == torch.float16 else 0, ws.data_ptr(), B, lvl, cout, _stream()), 'gin_bn_act_bwd_pair')
+                                                 1 if st['ycat'].dtype == torch.float16 else 0, ws.data_ptr(), B, lvl, cout, _MASK_FROM_Y, _stream()), 'gin_bn_act_bwd_pair')
                 blk = st['blk']
                 dW01 = _conv_wgrad(st['plan_b'], st['h_b'], dy01_b, B, cout, cout, side,
                                    out=_dest((blk.conv01.weight,), (cout, cout, 7)) if side is None else None)

@@ -184,15 +184,19 @@ int gin_bn_act_fwd(const void* y1, int64_t ld1, const float* stat1, const void* 
                    int y_fp16, int relu, void* out_b, float* out_f, void* out_w, int B, int level, int C, void* stream);
 /* backward of out = act(bn(y) [+ ...]) with respect to y: g = dout * (mask_b > 0) (mask_b = a 16-bit copy of out, either format; NULL: no ReLU),
  * bstat[4][C] = dbeta, dgamma, mean(g), mean(g*yhat);  dy = scale*(g - mean(g) - yhat*mean(g*yhat)) is written as the bf16
- * copy dy_b [B*P + 2B][.] with row stride ldo (pole-mean rows included) and / or as fp32 dy_f with row stride ldf. */
+ * copy dy_b [B*P + 2B][.] with row stride ldo (pole-mean rows included) and / or as fp32 dy_f with row stride ldf.
+ * relu_from_y != 0 (with mask_b != NULL): the caller states that mask_b is the output of gin_bn_act_fwd(y, stat, relu = 1) itself; the
+ * kernels may then re-evaluate out > 0 from y and stat (bit-identical arithmetic) instead of reading the mask -- 2 B / element
+ * less traffic in each of the two passes. */
 int gin_bn_act_bwd(const float* dout, int64_t ldg, const void* mask_b, const void* y, int64_t ld, int y_fp16, const float* stat, float* bstat,
-                   void* dy_b, int64_t ldo, float* dy_f, int64_t ldf, void* ws, int B, int level, int C, void* stream);
+                   void* dy_b, int64_t ldo, float* dy_f, int64_t ldf, void* ws, int B, int level, int C, int relu_from_y, void* stream);
 /* Backward of out = relu(bnA(yA) + bnB(yB)) (the residual output of models.py:38-39, 60-61) with respect to yA and yB in one pass pair:
- * both BatchNorms see the same g = dout * (mask_b > 0), which is read once.  ws: gin_bn_pair_ws_bytes(C). */
+ * both BatchNorms see the same g = dout * (mask_b > 0), which is read once.  ws: gin_bn_pair_ws_bytes(C).
+ * relu_from_y != 0: mask_b is the output of gin_bn_act_fwd(yA, statA, yB, statB, relu = 1); see gin_bn_act_bwd. */
 size_t gin_bn_pair_ws_bytes(int C);
 int gin_bn_act_bwd_pair(const float* dout, int64_t ldg, const void* mask_b, const void* yA, int64_t ldA, const float* statA, float* bstatA,
                         void* dyA_b, int64_t ldoA, const void* yB, int64_t ldB, const float* statB, float* bstatB, void* dyB_b, int64_t ldoB,
-                        int y_fp16, void* ws, int B, int level, int C, void* stream);
+                        int y_fp16, void* ws, int B, int level, int C, int relu_from_y, void* stream);
 /* IcoUpsampleS2S.forward whose result exists only as the next convolution's operand copy out_b = 16-bit [B*Pf + 2B][C] in the
  * forward operand format (upsample plan), plus (out_w, may be NULL) its bf16 twin for wgrad.  in: the fp32 coarse map
  * [B*Pc][C] (in_is_f32 = 1) or its forward-format operand copy [B*Pc + 2B][C] (0). */

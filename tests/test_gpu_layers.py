@@ -292,10 +292,12 @@ def test_reparam_draws_fresh_noise_under_graph_replay():
     assert abs(outs[2].std().item() - 1.0) < 0.05
 
 
+@pytest.mark.parametrize('from_y', [0, 1])
 @pytest.mark.parametrize('C,level,B,two', [(64, 3, 3, False), (128, 2, 5, True), (256, 2, 2, True)])
-def test_fused_bn_act_matches_torch(C, level, B, two):
+def test_fused_bn_act_matches_torch(C, level, B, two, from_y):
     """gin_bn_stats / gin_bn_act_fwd / gin_bn_act_bwd(_pair) against torch's own BatchNorm2d (training) + add + ReLU + autograd
-    (models.py:37-39, 59-61): statistics, running buffers, the bf16 operand copy incl. pole rows, dgamma / dbeta and dy."""
+    (models.py:37-39, 59-61): statistics, running buffers, the bf16 operand copy incl. pole rows, dgamma / dbeta and dy.
+    from_y = 1: the backward re-evaluates the ReLU mask from y and the BatchNorm constants instead of reading the activation copy."""
     from geniconet_b200 import _lib, fused
     L = _lib.lib
     torch.manual_seed(0)
@@ -350,11 +352,11 @@ def test_fused_bn_act_matches_torch(C, level, B, two):
         ws = torch.empty(L.gin_bn_pair_ws_bytes(C), dtype=torch.uint8, device=dev)
         _lib.check(L.gin_bn_act_bwd_pair(d.data_ptr(), C, out_w.data_ptr(), ybuf.data_ptr() + 4 * col0, ld, stat1.data_ptr(), bsA.data_ptr(),
                                          dyA.data_ptr(), C, y2.data_ptr(), C, stat2.data_ptr(), bsB.data_ptr(), dyB.data_ptr(), C, 0, ws.data_ptr(),
-                                         B, level, C, torch.cuda.current_stream().cuda_stream))
+                                         B, level, C, from_y, torch.cuda.current_stream().cuda_stream))
         pairs = [(bsA, dyA, y1r, refbn[0]), (bsB, dyB, y2r, refbn[1])]
     else:
         dyA = torch.empty(B * P + 2 * B, C, dtype=torch.bfloat16, device=dev)
-        bsA, dyf = fused._bn_bwd(d, out_w, ybuf, col0, ld, stat1, B, level, C, dy_b=dyA, dy_b_col=0, ldo=C, want_f=True)
+        bsA, dyf = fused._bn_bwd(d, out_w, ybuf, col0, ld, stat1, B, level, C, dy_b=dyA, dy_b_col=0, ldo=C, want_f=True, mask_from_y=from_y)
         assert torch.allclose(dyf, y1r.grad, rtol=1e-3, atol=1e-5)
         pairs = [(bsA, dyA, y1r, refbn[0])]
     torch.cuda.synchronize()
