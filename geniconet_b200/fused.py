@@ -252,9 +252,10 @@ def _bn_act(y1, col1, ld1, stat1, y2, col2, ld2, stat2, B, level, C, want_b=True
     return out_b, out_f, out_w
 
 
-# GIN_BN_MASK_FROM_Y=1: the BatchNorm backward kernels re-evaluate the ReLU mask from y and the BatchNorm constants instead of
-# reading it from the activation copy (include/geniconet_b200.h: relu_from_y)
-_MASK_FROM_Y = 1 if _os.environ.get('GIN_BN_MASK_FROM_Y', '0') == '1' else 0
+# The BatchNorm backward kernels re-evaluate the ReLU mask from y and the BatchNorm constants instead of reading it from the
+# activation copy (include/geniconet_b200.h: relu_from_y): 2 B / element less in each pass, step 3.40 -> 3.27 ms on the same box
+# (profiles/r02_ab_mask_*.json).  GIN_BN_MASK_FROM_Y=0 reads the mask.
+_MASK_FROM_Y = 0 if _os.environ.get('GIN_BN_MASK_FROM_Y', '1') == '0' else 1
 
 
 def _bn_bwd(dout, mask_b, y, col0, ld, stat, B, level, C, dy_b=None, dy_b_col=0, ldo=0, want_f=False, mask_from_y=None):
