@@ -23,9 +23,14 @@ class GradBuckets:
 
     Autograd is left to ASSIGN each parameter's gradient (p.grad is None at the start of a step), which costs no kernel; with
     pre-allocated bucket views as p.grad every parameter paid one accumulate (add) launch per step -- 78 launches at ico2ico.
-    When the last gradient of a bucket has arrived, the bucket's gradients are copied into its flat buffer with one
-    multi-tensor launch and the all-reduce of that buffer starts, overlapping the rest of backward.  finish() waits and points
-    p.grad at the reduced views.  With world_size 1 nothing is copied or exchanged at all.
+    Gradients reach their bucket slot in one of three ways: (1) the fused chains' wgrad kernels write weight gradients straight
+    into the slot (grad_dest; sibling weights whose gradient one kernel produces are laid out side by side, `adjacent`) -- the
+    copies that used to gather them cost 115 us per step, more than the exchange; (2) the chains hand the remaining gradients
+    (BatchNorm weight / bias, conv bias) over from inside their backward (early_grads), copied with one multi-tensor launch when
+    the bucket is complete; (3) everything else arrives through autograd's post-accumulate hooks.  When the last gradient of a
+    bucket is there its all-reduce starts, overlapping the rest of backward.  finish_bucket(i) waits for bucket i only and points
+    p.grad at the reduced views (one optimizer per bucket can then update it while later buckets are still in flight); finish()
+    does so for all.  With world_size 1 nothing is copied or exchanged at all.
     """
 
     def __init__(self, params, world_size, bucket_bytes=None, process_group=None, adjacent=()):
