@@ -66,3 +66,21 @@ def test_cpu_parameters_raise():
         Adam([p]).step()
     q = torch.nn.Parameter(torch.zeros(4))
     Adam([q]).step()                                             # nothing has a gradient: nothing to do, nothing raised
+
+
+def test_reference_scheduler_accepts_the_optimizer():
+    """run.py:447-449 wraps the optimizer in CyclicLR(optimizer, lr_base, lr_max, cycle_momentum=False) and steps it after every
+    batch (run.py:252-254): the scheduler must construct over our optimizer and drive its group learning rate."""
+    from geniconet_b200.optim import Adam
+    p = torch.nn.Parameter(torch.zeros(3))
+    opt = Adam([p], lr=1e-4)
+    sched = torch.optim.lr_scheduler.CyclicLR(opt, 1e-5, 1e-3, cycle_momentum=False)
+    ref_opt = torch.optim.Adam([torch.nn.Parameter(torch.zeros(3))], lr=1e-4)
+    ref_sched = torch.optim.lr_scheduler.CyclicLR(ref_opt, 1e-5, 1e-3, cycle_momentum=False)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')                         # "scheduler.step() before optimizer.step()": no step is taken here
+        for _ in range(5):
+            sched.step()
+            ref_sched.step()
+            assert opt.param_groups[0]['lr'] == ref_opt.param_groups[0]['lr']
